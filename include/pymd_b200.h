@@ -1,0 +1,145 @@
+/* libpymd_b200 -- C ABI of the B200-native generalized-Langevin stepping path.
+ *
+ * The reference (phyjtlu/pymd) has no FFI for this path: it is the Python classes
+ * md / phbath / ebath.  pymd_b200/{md,phbath,ebath}.py keep
+ * those class interfaces and call the entry points below through ctypes; each entry
+ * point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (pymd_last_error() explains);
+ *     the reference's "print + sys.exit()" convention becomes a Python exception.
+ *   - "host" pointers are plain C arrays in the reference's own shapes (row-major);
+ *     the library copies/pads what it needs.  "dev" pointers are device memory
+ *     BORROWED for the lifetime of the binding (torch tensors on the Python side).
+ *   - ensemble layout: every per-trajectory array has the trajectory index FASTEST,
+ *     e.g. p is [nd][ldb] doubles.  ldb (the padded ensemble size) is a multiple of 32.
+ *   - all launches go to the cudaStream_t passed as `stream` (void* here); no hidden
+ *     synchronisation.  One ctx per process per GPU; not re-entrant.
+ */
+#ifndef PYMD_B200_H
+#define PYMD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pymd_ctx pymd_ctx;
+
+#define PYMD_MAX_BATHS 8
+#define PYMD_MAX_CONSTRAINTS 16
+
+const char* pymd_last_error(void);
+int pymd_version(void);
+
+/* md.__init__ (md.py:59-125): nd = md.nph, ldb = padded ensemble size, dt, nmd. */
+int pymd_ctx_create(int nd, int ldb, int nbath, double dt, int nmd, int device, pymd_ctx** out);
+int pymd_ctx_destroy(pymd_ctx* ctx);
+
+/* md.setDyn result (md.py:211-250): host dyn[nd][nd] as md.dyn holds it after the
+ * eigen clean-up; used as f = -dyn.q (md.potforce, md.py:483-484). */
+int pymd_set_dyn(pymd_ctx* ctx, const double* dyn_host);
+
+/* md.constraint (md.py:66, ApplyConstraint md.py:739-762): host c[n][nd]; rows are
+ * normalised as the reference does on every call; zero rows stay zero. */
+int pymd_set_constraints(pymd_ctx* ctx, const double* constr_host, int n);
+
+/* md.AddBath (md.py:160-176) + the operands of bath.bforce:
+ *   phbath.bforce (phbath.py:192-202): kernel[ml][nc][nc], friction scaled by dt when ml>1
+ *                                       (dt_scaled=1), unscaled for the local Debye bath.
+ *   ebath.bforce  (ebath.py:180-199):  ml=1, kernel[0] = efric + bias*zeta2 (acts on p),
+ *                                       aq = bias*(exim - zeta1) (acts on q), dt_scaled=0.
+ * cids_host[nc] are the connected dofs (phbath.py:52, ebath.py:33).  aq_host may be NULL. */
+int pymd_bath_set(pymd_ctx* ctx, int b, int nc, const int* cids_host, int ml,
+                  const double* kernel_host, const double* aq_host, int dt_scaled);
+
+/* md.p, md.q (md.py:105-106): dev [nd][ldb]. */
+int pymd_bind_state(pymd_ctx* ctx, double* p_dev, double* q_dev);
+
+/* md.phis restricted to the bath's dofs (md.py:292-301, functions.rpadleft): a ring
+ * buffer dev [ring_len][ncp][ldb], ncp = pymd_bath_ncp(nc), ring_len >= ml-1+block
+ * (see pymd_ring_len).  Only non-local baths (ml>1) need one. */
+int pymd_bath_ncp(int nc);
+int pymd_ring_len(int ml, int block);
+int pymd_bind_history(pymd_ctx* ctx, int b, double* ring_dev, int ring_len);
+
+/* bath.noise (phbath.py:157, ebath.py:147): dev [nmd][nc][ldb]. */
+int pymd_bind_noise(pymd_ctx* ctx, int b, const double* noise_dev);
+
+/* md.ps, md.qs (md.py:146-147, written at md.py:322-324; NULL when savepq is False),
+ * md.etot (md.py:119,328): dev [nmd][nd][ldb], [nmd][nd][ldb], [nmd][ldb]. */
+int pymd_bind_outputs(pymd_ctx* ctx, double* ps_dev, double* qs_dev, double* etot_dev);
+
+/* bath.cur (md.py:342): dev [nmd][ldb];  md.fhis[b] restricted to the bath's dofs
+ * (md.py:343; NULL = not recorded): dev [nmd][nc][ldb]. */
+int pymd_bind_bath_outputs(pymd_ctx* ctx, int b, double* cur_dev, double* fhis_dev);
+
+/* md.ResetHis (md.py:292-301): zero every ring, forget cached forces. */
+int pymd_reset_history(pymd_ctx* ctx, void* stream);
+/* Tell the library that p/q were modified from outside (md.initialise, a resume):
+ * the cached potential force (md.potforce's q0/f0, md.py:456-457) is dropped. */
+int pymd_invalidate_cache(pymd_ctx* ctx);
+
+/* History access for checkpoint/resume (md.dump writes phis, md.py:700-703): copies the
+ * newest `nrows` rows (newest first, like md.phis) of bath b to/from dev [nrows][nc][ldb]. */
+int pymd_history_get(pymd_ctx* ctx, int b, double* out_dev, int nrows, void* stream);
+int pymd_history_set(pymd_ctx* ctx, int b, const double* in_dev, int nrows, void* stream);
+
+/* nsteps calls of md.vv (md.py:315-358) starting at md.t = t0, for the whole ensemble.
+ * mode: 0 = auto, 1 = per-step GEMM pipeline, 2 = fused on-chip step kernel. */
+int pymd_step(pymd_ctx* ctx, long long t0, int nsteps, int mode, void* stream);
+/* number of kernel launches issued by this ctx so far */
+long long pymd_launch_count(const pymd_ctx* ctx);
+
+/* ---- noise generation: noise.phnoise / noise.enoise (noise.py:38-88, 135-190) --------
+ * factors: L[f] = U_f diag(sqrt(max(lambda_f,0))) for f = 0..nmd/2, dev [nf][nc][nc]
+ * (real part; imaginary part NULL for phonon baths).  xi: standard normals dev
+ * [nf][nc][ldb].  Computes X_f = L_f xi_f, the Hermitian mirror (noise.py:74-81), the
+ * w->t transform myfft.iFourier1D (myfft.py:35-52: fft/(nmd*dt)) and keeps the real part.
+ * out: dev [nmd][nc][ldb].  work: dev scratch of pymd_noise_work_bytes(). */
+size_t pymd_noise_work_bytes(int nmd, int nc, int ldb);
+int pymd_noise_generate(const double* lre_dev, const double* lim_dev, const double* xi_dev,
+                        int nmd, int nc, int ldb, double dt, double* out_dev, void* work_dev,
+                        void* stream);
+
+/* N.random.normal replacement (noise.py:282): counter-based Philox4x32-10 + Box-Muller.
+ * Element (row r, trajectory n) depends only on (seed, stream_id, r, traj0+n): results do
+ * not depend on how the ensemble is sharded over GPUs.  out: dev [rows][ldb]. */
+int pymd_philox_normal(double* out_dev, long long rows, int ldb, uint64_t seed, uint32_t stream_id,
+                       long long traj0, void* stream);
+/* N.random.rand replacement (md.py:280). */
+int pymd_philox_uniform(double* out_dev, long long rows, int ldb, uint64_t seed, uint32_t stream_id,
+                        long long traj0, void* stream);
+
+/* ---- md.initialise (md.py:253-290): q = sum_i U[:,i] am_i cos(2 pi r_i),
+ * p = -sum_i hw_i U[:,i] am_i sin(2 pi r_i), constraints applied after every mode.
+ * U_host[nd][nd] (columns = modes), am_host[nd], hw_host[nd]; r: dev [nd][ldb]. */
+int pymd_init_state(pymd_ctx* ctx, const double* U_host, const double* hw_host,
+                    const double* am_host, const double* r_dev, void* stream);
+
+/* ---- spectrum.powerspec / powerspec2 (spectrum.py:8-45) summed over the ensemble:
+ * traj: dev [nmd][nd][ldb] (md.qs or md.ps); out: dev [nmd] receives
+ * sum_{traj<nvalid} sum_dof |Fourier1D(traj)|^2 / (dt*nmd)  (times w_i^2 when wsq != 0).
+ * The nd*ldb columns are transformed chunk_cols at a time (0 = all at once; multiple of 32);
+ * work: dev scratch of pymd_powerspec_work_bytes().  The sum is deterministic. */
+size_t pymd_powerspec_work_bytes(int nmd, int nd, int ldb, long long chunk_cols);
+int pymd_powerspec(const double* traj_dev, int nmd, int nd, int ldb, int nvalid, double dt, int wsq,
+                   double* out_dev, void* work_dev, long long chunk_cols, void* stream);
+
+/* Batched complex FFT along the slowest axis: data dev [n][cols] complex128 in place,
+ * sign = -1 (numpy fft) or +1 (numpy ifft, unscaled). */
+int pymd_fft_columns(double* data_dev, int n, long long cols, int sign, void* work_dev, void* stream);
+/* bytes of scratch pymd_fft_columns needs */
+size_t pymd_fft_work_bytes(int n, long long cols);
+
+/* General tensor-core product used by tests and by setup-on-device:
+ * Y[M][ldb] = alpha * A_host-uploaded... (device pointers, A row-major [M][lda], lda % 32 == 0) */
+int pymd_gemm(const double* a_dev, int lda, const double* x_dev, double* y_dev, int M, int K, int ldb,
+              double alpha, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYMD_B200_H */

@@ -1,0 +1,74 @@
+// Context and device-side parameter blocks of the stepping engine.
+#pragma once
+#include <vector>
+
+#include "../../include/pymd_b200.h"
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace pymd {
+
+constexpr int kBlockT = 16;   // time-block length of the fused path (ring sizing uses it too)
+
+struct BathDev {
+    int nc, ncp, ml, R;
+    int has_aq, nonlocal;
+    const int* inv;        // [nd] -> local index or -1
+    const int* cids;       // [nc]
+    const double* noise;   // [nmd][nc][ldb]
+    double* cur;           // [nmd][ldb]
+    double* fhis;          // [nmd][nc][ldb] or null
+    double* ring;          // [R][ncp][ldb]
+    double* g;             // [ncp][ldb]   head term  Hd.p_c (- Aq.q_c)
+    double* uq;            // [ncp][ldb]   Aq.q'_c
+    double* tail_cur;      // [T][nc][ldb]
+    double* tail_next;
+};
+
+struct StepDev {
+    int nd, ldb, nbath, nmd, ncon;
+    double dt;
+    double *p, *q, *ps, *qs, *etot;
+    double *ph, *qn, *p1, *fpotn, *fpotc, *fbase, *h;
+    int* samef;            // [ldb] 1 = use cached force fpotn, 0 = use fpotc
+    const double* con;     // [ncon][nd] normalised constraint vectors
+    BathDev b[PYMD_MAX_BATHS];
+};
+
+struct BathHost {
+    bool set = false;
+    int nc = 0, ncp = 0, ml = 1, dt_scaled = 0, has_aq = 0;
+    std::vector<int> cids;
+    std::vector<double> kernel;   // [ml][nc][nc]
+    std::vector<double> aq;       // [nc][nc]
+    // device operands owned by the ctx
+    int* d_cids = nullptr;
+    int* d_inv = nullptr;
+    double* d_head = nullptr;     // [ncp][lda]  alpha * kernel[0]
+    double* d_aq = nullptr;       // [ncp][lda]
+    double* d_krev = nullptr;     // [nc][Lk]    reversed, padded kernel table (tail operand)
+    double* d_kintra = nullptr;   // [kBlockT][nc][nc] dt*K[1..T] for the fused path
+    long long Lk = 0;
+    int padf = 0;
+    int lda = 0;
+    int R = 0;
+    long long hcount = 0;         // rows appended since the last reset
+};
+
+}  // namespace pymd
+
+struct pymd_ctx {
+    int nd = 0, ldb = 0, nbath = 0, nmd = 0, device = 0, ncon = 0;
+    double dt = 0;
+    int ldn = 0;                       // padded row length of nd x nd operands
+    pymd::BathHost bath[PYMD_MAX_BATHS];
+    std::vector<double> dyn, con;
+    double* d_dyn = nullptr;           // [nd][ldn]
+    double* d_mp = nullptr;            // [nd][ldn]  sum_b scatter(alpha_b kernel_b[0])
+    double* d_con = nullptr;           // [ncon][nd]
+    void* ws = nullptr;                // workspace
+    size_t ws_bytes = 0;
+    pymd::StepDev sd{};
+    bool finalized = false, fpot_valid = false, tail_valid = false;
+    long long launches = 0;
+};

@@ -1,0 +1,31 @@
+// Batched FFT along the SLOW axis of [n][cols] arrays (cols = dof x trajectory, contiguous),
+// Stockham autosort, radix-8/4/2 register passes, every access coalesced over columns.
+#pragma once
+#include "common.cuh"
+
+namespace pymd {
+
+// device table W[t] = exp(-2 pi i t / N), t < N  (cached per (device, N); host-computed)
+const double2* twiddle_table(int N);
+
+enum FftLoad { LOAD_C = 0, LOAD_REAL_PAIRS = 1 };
+enum FftStore { STORE_C = 0, STORE_REAL_ROWS = 1 };
+
+struct FftPlan {
+    int n;                // complex length (power of two)
+    long long cols;       // columns transformed
+    int sign;             // -1 numpy fft, +1 numpy ifft (unscaled)
+    FftLoad load;         // LOAD_REAL_PAIRS: src is real [2n][src_ld], z[m] = x[2m] + i x[2m+1]
+    FftStore store;       // STORE_REAL_ROWS: dst real [2n][dst_ld]: row 2m = scale*re, row 2m+1 = scale*im
+    long long src_ld, dst_ld;
+    double scale;
+};
+
+// Runs all passes.  `src` is read by the first pass only (never written unless it aliases a
+// work buffer); intermediates ping-pong between bufA and bufB (each n*cols complex);
+// the result of the last pass lands in `dst` (complex [n][cols] for STORE_C).
+// Returns PYMD_* status; *npasses receives the number of launches.
+int fft_columns(const void* src, void* dst, double2* bufA, double2* bufB, const FftPlan& plan,
+                cudaStream_t stream, int* npasses);
+
+}  // namespace pymd

@@ -1,0 +1,168 @@
+// See gemm.cuh.  One producer warp (TMA bulk row copies) + four DMMA warps per CTA.
+#include "gemm.cuh"
+
+namespace pymd {
+
+namespace {
+
+constexpr int BK = 32;         // K rows per pipeline stage
+constexpr int LDA = BK + 4;    // padded so the A-fragment LDS is bank-conflict free (ld % 16 == 4)
+constexpr int STAGES = 3;
+constexpr int NCOMPUTE = 4;    // DMMA warps, arranged 2 (M) x 2 (N)
+
+template <int BM, int BN>
+struct __align__(16) Smem {
+    double A[STAGES][BM][LDA];
+    double B[STAGES][BK][BN + 4];
+    uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+};
+
+template <int BM, int BN>
+__global__ void __launch_bounds__((NCOMPUTE + 1) * 32) gemm_kernel(const GemmArgs g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<BM, BN>& s = *reinterpret_cast<Smem<BM, BN>*>(smem_raw);
+    constexpr int LDB = BN + 4;
+    constexpr int WTM = BM / 2, WTN = BN / 2, MT = WTM / 8, NT = WTN / 8;
+    static_assert(MT >= 1 && NT >= 1, "tile too small");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&s.full[i], 1);
+            mbar_init(&s.empty[i], NCOMPUTE);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    int ntiles = 0;
+    for (int sg = 0; sg < g.nseg; ++sg) ntiles += (g.seg_hi[sg] - g.seg_lo[sg] + BK - 1) / BK;
+
+    if (warp == NCOMPUTE) {
+        // ------------------------------ producer ------------------------------
+        const int ncols = min(BN, g.N - n0);
+        const uint32_t xbytes = static_cast<uint32_t>(ncols) * 8u;
+        int it = 0;
+        for (int sg = 0; sg < g.nseg; ++sg) {
+            for (int k0 = g.seg_lo[sg]; k0 < g.seg_hi[sg]; k0 += BK, ++it) {
+                const int st = it % STAGES;
+                if (it >= STAGES) mbar_wait(&s.empty[st], ((it / STAGES) - 1) & 1);
+                const int kvalid = min(BK, g.seg_hi[sg] - k0);
+                uint32_t mybytes = 0;
+                // X rows: one bulk copy per valid row, zero fill for the rest of the tile.
+                if (lane < kvalid) {
+                    const int k = k0 + lane;
+                    const long long row = g.x_idx ? g.x_idx[k] : k;
+                    bulk_g2s(&s.B[st][lane][0], g.x_base + row * g.x_ld + n0, xbytes, &s.full[st]);
+                    mybytes += xbytes;
+                } else {
+                    for (int c = 0; c < BN; ++c) s.B[st][lane][c] = 0.0;
+                }
+                // A rows: BK contiguous doubles each.
+                for (int r = lane; r < BM; r += 32) {
+                    const int m = m0 + r;
+                    if (m < g.M) {
+                        const double* src = g.a_base + (long long)(m % g.a_mod) * g.a_ld +
+                                            (long long)(m / g.a_mod) * g.a_ls + g.seg_aoff[sg] + k0;
+                        bulk_g2s(&s.A[st][r][0], src, BK * 8, &s.full[st]);
+                        mybytes += BK * 8;
+                    }
+                }
+                uint32_t total = mybytes;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+                __syncwarp();   // zero-fill stores ordered before the arrive below
+                if (lane == 0) mbar_arrive_expect_tx(&s.full[st], total);
+            }
+        }
+        return;
+    }
+
+    // ------------------------------ DMMA warps ------------------------------
+    const int wm = warp >> 1, wn = warp & 1;
+    const int lr = lane >> 2, lc = lane & 3;
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int it = 0; it < ntiles; ++it) {
+        const int st = it % STAGES;
+        mbar_wait(&s.full[st], (it / STAGES) & 1);
+        const double* As = &s.A[st][wm * WTM + lr][lc];
+        const double* Bs = &s.B[st][lc][wn * WTN + lr];
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double a[MT], b[NT];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) a[i] = As[i * 8 * LDA + kk];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) b[j] = Bs[kk * LDB + j * 8];
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.empty[st]);
+    }
+
+    // ------------------------------ epilogue ------------------------------
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int m = m0 + wm * WTM + i * 8 + lr;
+        if (m >= g.M) continue;
+        const long long row = g.y_idx ? g.y_idx[m] : m;
+        double* yrow = g.y_base + row * g.y_ld;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int n = n0 + wn * WTN + j * 8 + 2 * lc;
+            if (n >= g.N) continue;
+            double2 v = make_double2(g.alpha * acc[i][j][0], g.alpha * acc[i][j][1]);
+            double2* dst = reinterpret_cast<double2*>(yrow + n);
+            if (g.accumulate) {
+                double2 o = *dst;
+                v.x += o.x;
+                v.y += o.y;
+            }
+            *dst = v;
+        }
+    }
+}
+
+template <int BM, int BN>
+int launch_t(const GemmArgs& a, cudaStream_t stream) {
+    static bool configured = false;
+    const int smem = static_cast<int>(sizeof(Smem<BM, BN>));
+    if (!configured) {
+        PYMD_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BM, BN>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM);
+    gemm_kernel<BM, BN><<<grid, (NCOMPUTE + 1) * 32, smem, stream>>>(a);
+    PYMD_CUDA_CHECK(cudaGetLastError());
+    return PYMD_OK;
+}
+
+}  // namespace
+
+int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+    PYMD_REQUIRE(a.M > 0 && a.N > 0 && (a.N % 2) == 0, "gemm: bad shape M=%d N=%d", a.M, a.N);
+    PYMD_REQUIRE(a.nseg >= 0 && a.nseg <= 2, "gemm: nseg=%d", a.nseg);
+    for (int sg = 0; sg < a.nseg; ++sg)
+        PYMD_REQUIRE(((a.seg_aoff[sg] + a.seg_lo[sg]) % 2) == 0 && (a.a_ld % 2) == 0 && (a.a_ls % 2) == 0,
+                     "gemm: A rows must be 16-byte aligned");
+    PYMD_REQUIRE((a.x_ld % 2) == 0 && (a.y_ld % 2) == 0, "gemm: X/Y leading dims must be even");
+    // Tile choice: fill the 148 SMs first, then grow the tile for operand reuse.
+    const long long ctas64 = (long long)((a.N + 63) / 64) * ((a.M + 63) / 64);
+    if (a.M > 32 && ctas64 >= 148) return launch_t<64, 64>(a, stream);
+    if (a.M > 16) return launch_t<32, 32>(a, stream);
+    return launch_t<16, 32>(a, stream);
+}
+
+}  // namespace pymd

@@ -1,0 +1,598 @@
+"""Langevin molecular dynamics with the reference's ``md`` class interface (md.py:23-705),
+stepping an ENSEMBLE of independent trajectories on one B200 through libpymd_b200.
+
+Same constructor, methods and attributes as the reference, so driver scripts written for
+pymd (tests/test.py style hand loops, examples/*.py ending in ``mdrun.Run()``) drive it
+unchanged.  New optional keyword arguments, all defaulting to the reference behaviour of
+one trajectory: ``batch`` (ensemble size), ``seed``, ``device``, ``traj0`` (global index of
+the first local trajectory, for multi-GPU sharding), ``step_mode``, ``record_fhis``.
+
+There is no CPU fallback: the time loop, noise generation and spectra run in CUDA.
+"""
+import ctypes as C
+import os
+import time
+
+import numpy as N
+from numpy import linalg as LA
+
+from . import _lib
+from . import units as U
+from .functions import bose
+from .matrix import chkShape, symmetrize
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class md(object):
+    def __init__(self, dt, nmd, T, syslist=None, axyz=None, harmonic=False, dyn=None, savepq=True,
+                 nrep=1, npie=8, constr=None, batch=1, seed=None, device=None, traj0=0, step_mode=0,
+                 record_fhis=False):
+        self.sint = None
+        self.brennerrun = None
+        self.lammpsrun = None
+        self.constraint = constr
+        self.nrep = nrep
+        self.dt, self.nmd = dt, nmd
+        self.harmonic = harmonic
+        self.T = T
+        self.npie = npie
+        self.power = N.zeros((self.nmd, 2))
+        self.power2 = N.zeros((self.nmd, 2))
+        self.batch = int(batch)
+        self.ldb = _round_up(self.batch, 32)
+        self.seed = seed
+        self.traj0 = int(traj0)
+        self.step_mode = step_mode
+        self.record_fhis = record_fhis
+        self.write_files = True
+        self.outdir = "."
+        self._device = device
+        self.SetXyz(axyz)
+        self.syslist = self.na = self.nph = None
+        if syslist is not None:                                     # md.py:79-89
+            if len(syslist) > self.nta or min(syslist) < 0 or max(syslist) > self.nta - 1:
+                raise ValueError("syslist out of range")
+            self.syslist = N.array(syslist, dtype='int')
+            self.na = len(syslist)
+            self.nph = 3 * len(syslist)
+        elif axyz is not None:                                      # md.py:90-95
+            self.syslist = N.array(range(len(axyz)), dtype='int')
+            self.na = len(self.syslist)
+            self.nph = 3 * len(self.syslist)
+        self.ml = 1
+        self.t = 0
+        self.baths = []
+        self._ctx = None
+        self._ctx_key = None
+        self._p = self._q = None
+        self._ps = self._qs = self._etot = None
+        self._rings = {}
+        self._fhis = {}
+        self._ninit = 0
+        self.setDyn(dyn)
+        self.savepq = savepq
+
+    # ------------------------------------------------------------------ plain setters
+    def info(self):
+        print("--------------------------------------------")
+        print("Basis information of the MD simulation:")
+        print("Harmonic force: %s" % self.harmonic)
+        print("System atom number: %s" % self.na)
+        print("MD time step: %s" % self.dt)
+        print("MD number of steps: %s" % self.nmd)
+        print("MD memory kernel length: %s" % self.ml)
+        print("Number of baths attached: %s" % len(self.baths))
+        print("Ensemble size (trajectories on this GPU): %s" % self.batch)
+        if self.dyn is None:
+            print("md.info: No dynamical matrix input!")
+
+    def SetT(self, T):
+        self.T = T
+
+    def SetMD(self, dt, nmd):
+        self.dt, self.nmd = dt, nmd
+        self._drop_ctx()
+
+    def SetHarm(self, harmonic):
+        self.harmonic = harmonic
+
+    def SetXyz(self, axyz):
+        if axyz is not None:
+            self.xyz = N.array([a[1:] for a in axyz], dtype='d').flatten()
+            self.els = [a[0] for a in axyz]
+            self.nta = len(axyz)
+        else:
+            self.xyz = self.els = self.nta = None
+
+    def SetSyslist(self, syslist):
+        self.syslist = N.array(syslist)
+        self.na = len(syslist)
+        self.nph = 3 * len(syslist)
+        if self.xyz is not None and len(self.syslist) > self.nta:
+            raise ValueError("md.SetSyslist:system atom number larger than total atom number")
+
+    def setDyn(self, dyn=None):
+        """Symmetrise, clamp negative eigenvalues to zero and rebuild the dynamical matrix
+        from its eigen-decomposition (md.py:211-250).  Host numpy, as in the reference."""
+        if dyn is None:
+            self.dyn = self.hw = self.U = None
+            return
+        ndyn = N.array(dyn)
+        n = chkShape(ndyn)
+        if self.nph is not None and self.nph != n:
+            raise ValueError("md.setDyn: the dimension of dynamical matrix is wrong!")
+        self.nph = n
+        av, au = LA.eigh(symmetrize(ndyn))
+        av = N.where(av < 0, 0.0, av)
+        self.hw = N.sqrt(av)
+        self.U = N.array(au)
+        self.dyn = (self.U * av) @ self.U.T
+        self._drop_ctx()
+
+    def AddBath(self, bath):
+        """md.py:160-176."""
+        if self.dt != bath.dt:
+            raise ValueError("md.AddBath: md time step dt not consistent!")
+        if self.nmd != bath.nmd:
+            raise ValueError("md.AddBath: number of md steps nmd not consistent!")
+        bath._attach(self.batch, None if self.seed is None else self.seed + 7919 * (len(self.baths) + 1),
+                     self.traj0, self._dev())
+        self.baths.append(bath)
+        if bath.ml > self.ml:
+            self.ml = bath.ml
+        self._drop_ctx()
+
+    def AddSint(self, sint):
+        self.sint = sint
+
+    def AddBint(self, bint):
+        self.brennerrun = bint
+
+    def AddLMPint(self, lint):
+        self.lammpsrun = lint
+
+    # ------------------------------------------------------------------ device plumbing
+    def _dev(self):
+        import torch
+        if self._device is None:
+            self._device = torch.device("cuda", torch.cuda.current_device())
+        elif not isinstance(self._device, torch.device):
+            self._device = torch.device(self._device)
+        return self._device
+
+    def _drop_ctx(self):
+        if getattr(self, "_ctx", None) is not None:
+            _lib.load().pymd_ctx_destroy(self._ctx)
+        self._ctx = None
+
+    def __del__(self):
+        try:
+            self._drop_ctx()
+        except Exception:
+            pass
+
+    def _zeros(self, *shape):
+        import torch
+        return torch.zeros(shape, dtype=torch.float64, device=self._dev())
+
+    def _ensure(self):
+        """Create the library context and device arrays once the configuration is known."""
+        if self.sint is not None or self.brennerrun is not None or self.lammpsrun is not None:
+            raise NotImplementedError(
+                "external force drivers (SIESTA/Brenner/LAMMPS) need a per-step host callback and are "
+                "outside the GPU stepping path; attach a dynamical matrix instead")
+        if self.nph is None:
+            raise ValueError("md: number of degrees of freedom unknown (give axyz, syslist or dyn)")
+        if self._ctx is not None:
+            return
+        import torch
+        lib = _lib.load()
+        dev = self._dev()
+        torch.cuda.set_device(dev)
+        nd, ldb = self.nph, self.ldb
+        ctx = C.c_void_p()
+        _lib.call("pymd_ctx_create", nd, ldb, len(self.baths), float(self.dt), int(self.nmd),
+                  dev.index or 0, C.byref(ctx))
+        self._ctx = ctx
+        if self.dyn is not None:
+            d = N.ascontiguousarray(self.dyn, dtype=N.float64)
+            _lib.call("pymd_set_dyn", ctx, d.ctypes.data)
+        if self.constraint is not None:
+            c = N.ascontiguousarray(N.array(self.constraint, dtype=N.float64))
+            if c.ndim != 2 or c.shape[1] != nd:
+                raise ValueError("ApplyConstraint:shape error")
+            _lib.call("pymd_set_constraints", ctx, c.ctypes.data, c.shape[0])
+        if self._p is None or tuple(self._p.shape) != (nd, ldb):
+            self._p, self._q = self._zeros(nd, ldb), self._zeros(nd, ldb)
+        _lib.call("pymd_bind_state", ctx, self._p.data_ptr(), self._q.data_ptr())
+        if self._etot is None or tuple(self._etot.shape) != (self.nmd, ldb):
+            self._etot = self._zeros(self.nmd, ldb)
+        for b, bath in enumerate(self.baths):
+            if bath.kernel is None:
+                raise ValueError("md: bath %d has no memory kernel (call bath.gmem() before AddBath)" % b)
+            ker = N.ascontiguousarray(N.asarray(bath.kernel, dtype=N.float64)[:bath.ml])
+            cids = N.ascontiguousarray(bath.cids, dtype=N.int32)
+            aq = bath._aq_matrix()
+            if hasattr(bath, "_ap_matrix"):
+                ker = N.ascontiguousarray(bath._ap_matrix()[None, :, :], dtype=N.float64)
+            aqc = None if aq is None else N.ascontiguousarray(aq, dtype=N.float64)
+            _lib.call("pymd_bath_set", ctx, b, bath.nc, cids.ctypes.data, int(bath.ml), ker.ctypes.data,
+                      None if aqc is None else aqc.ctypes.data, 1 if bath.ml > 1 else 0)
+            if bath.ml > 1:
+                R = lib.pymd_ring_len(int(bath.ml), 0)
+                ncp = lib.pymd_bath_ncp(bath.nc)
+                if b not in self._rings or tuple(self._rings[b].shape) != (R, ncp, ldb):
+                    self._rings[b] = self._zeros(R, ncp, ldb)
+                _lib.call("pymd_bind_history", ctx, b, self._rings[b].data_ptr(), R)
+            if self.record_fhis:
+                self._fhis[b] = self._zeros(self.nmd, bath.nc, ldb)
+        self._savepq_alloc()
+
+    def _savepq_alloc(self):
+        if self._savepq and self.nph is not None:
+            shape = (self.nmd, self.nph, self.ldb)
+            if self._ps is None or tuple(self._ps.shape) != shape:
+                self._ps, self._qs = self._zeros(*shape), self._zeros(*shape)
+        else:
+            self._ps = self._qs = None
+
+    def _bind(self):
+        """(Re)bind every borrowed device array; cheap, done before each library call."""
+        ctx = self._ctx
+        _lib.call("pymd_bind_outputs", ctx, _lib.ptr(self._ps), _lib.ptr(self._qs), self._etot.data_ptr())
+        for b, bath in enumerate(self.baths):
+            if bath._noise_dev is None:
+                raise ValueError("md.vv: bath %d has no noise, call bath.gnoi() first" % b)
+            if tuple(bath._noise_dev.shape) != (self.nmd, bath.nc, self.ldb):
+                raise ValueError("md.vv: bath %d noise has the wrong shape (ensemble %d)" % (b, self.batch))
+            _lib.call("pymd_bind_noise", ctx, b, bath._noise_dev.data_ptr())
+            _lib.call("pymd_bind_bath_outputs", ctx, b, bath._alloc_cur().data_ptr(), _lib.ptr(self._fhis.get(b)))
+
+    # ------------------------------------------------------------------ state access
+    @property
+    def savepq(self):
+        return self._savepq
+
+    @savepq.setter
+    def savepq(self, v):
+        self._savepq = bool(v)
+        if not v:
+            self._ps = self._qs = None
+
+    def ResetSavepq(self, savepq=True):
+        """md.py:143-150: (re)allocate and zero the saved trajectories."""
+        self._savepq = bool(savepq)
+        if self.nmd is None or self.nph is None:
+            raise ValueError("md.ResetSavepq: nmd or nph is not set!")
+        self._savepq_alloc()
+        if self._ps is not None:
+            self._ps.zero_()
+            self._qs.zero_()
+
+    def _host(self, t, lead):
+        """device [..., ldb] -> host; trajectory axis first for an ensemble, dropped for batch 1."""
+        a = t[..., :self.batch].cpu().numpy()
+        if self.batch == 1:
+            return a[..., 0]
+        return N.moveaxis(a, -1, 0)
+
+    def _upload(self, dst, value):
+        import torch
+        a = N.asarray(value, dtype=N.float64)
+        want = tuple(dst.shape[:-1])
+        if a.shape == want:
+            a = N.broadcast_to(a[..., None], want + (self.batch,))
+        elif a.shape == (self.batch,) + want:
+            a = N.moveaxis(a, 0, -1)
+        else:
+            raise ValueError("expected shape %s or %s" % (want, (self.batch,) + want))
+        dst.zero_()
+        dst[..., :self.batch] = torch.as_tensor(N.ascontiguousarray(a), dtype=torch.float64).to(dst.device)
+
+    @property
+    def p(self):
+        return [] if self._p is None else self._host(self._p, True)
+
+    @p.setter
+    def p(self, v):
+        self._ensure()
+        self._upload(self._p, v)
+        _lib.call("pymd_invalidate_cache", self._ctx)
+
+    @property
+    def q(self):
+        return [] if self._q is None else self._host(self._q, True)
+
+    @q.setter
+    def q(self, v):
+        self._ensure()
+        self._upload(self._q, v)
+        _lib.call("pymd_invalidate_cache", self._ctx)
+
+    @property
+    def ps(self):
+        return None if self._ps is None else self._host(self._ps, True)
+
+    @property
+    def qs(self):
+        return None if self._qs is None else self._host(self._qs, True)
+
+    @property
+    def etot(self):
+        return N.zeros(self.nmd) if self._etot is None else self._host(self._etot, True)
+
+    @property
+    def fhis(self):
+        """Bath forces of the first evaluation of each step (md.py:343), restricted to the
+        bath's dofs and only when ``record_fhis=True`` (the reference keeps nmd x nph per bath
+        per trajectory, which cannot be materialised for an ensemble)."""
+        out = []
+        for b, bath in enumerate(self.baths):
+            if b not in self._fhis:
+                out.append(None)
+                continue
+            loc = self._host(self._fhis[b], True)
+            full = N.zeros(loc.shape[:-1] + (self.nph,))
+            full[..., bath.cids] = loc
+            out.append(full)
+        return out
+
+    @property
+    def fbaths(self):
+        return [None] * len(self.baths)
+
+    @property
+    def phis(self):
+        """Velocity history, newest first, shape (ml, nph) like the reference (md.py:296-298);
+        only the columns a non-local bath reads are kept on the device."""
+        return self._history()
+
+    def _history(self):
+        import torch
+        self._ensure()
+        out = N.zeros(((self.batch,) if self.batch > 1 else ()) + (self.ml, self.nph))
+        for b, bath in enumerate(self.baths):
+            if bath.ml <= 1:
+                continue
+            buf = self._zeros(bath.ml, bath.nc, self.ldb)
+            _lib.call("pymd_history_get", self._ctx, b, buf.data_ptr(), int(bath.ml), _lib.stream_ptr())
+            out[..., :bath.ml, bath.cids] = self._host(buf, True)
+        return out
+
+    def set_history(self, phis):
+        """Restore the velocity history (resume path, md.py:550-551/576-582)."""
+        import torch
+        self._ensure()
+        phis = N.asarray(phis, dtype=N.float64)
+        for b, bath in enumerate(self.baths):
+            if bath.ml <= 1:
+                continue
+            buf = self._zeros(bath.ml, bath.nc, self.ldb)
+            self._upload(buf, phis[..., :bath.ml, :][..., bath.cids])
+            _lib.call("pymd_history_set", self._ctx, b, buf.data_ptr(), int(bath.ml), _lib.stream_ptr())
+
+    # ------------------------------------------------------------------ the reference's methods
+    def energy(self):
+        """Kinetic energy 0.5 p.p of the current state (md.py:154-158)."""
+        import torch
+        e = 0.5 * (self._p[:, :self.batch] ** 2).sum(0).cpu().numpy()
+        return float(e[0]) if self.batch == 1 else e
+
+    def initialise(self, r=None):
+        """Quantum initial displacements/velocities from the eigenmodes (md.py:253-290).
+        ``r``: optional uniforms in [0,1), shape (nph,) or (nph, batch) / (batch, nph); by
+        default one Philox stream per trajectory."""
+        import torch
+        self._ensure()
+        self.t = 0
+        if self.dyn is None:
+            self._p.zero_()
+            self._q.zero_()
+            _lib.call("pymd_invalidate_cache", self._ctx)
+            return
+        nd = self.nph
+        hw = N.ascontiguousarray(self.hw, dtype=N.float64)
+        with N.errstate(divide="ignore", invalid="ignore"):
+            am = N.where(hw < 0.01, 0.0, ((bose(hw, self.T) + 0.5) * 2.0 / N.where(hw > 0, hw, 1.0)) ** 0.5)
+        am = N.ascontiguousarray(am, dtype=N.float64)
+        rdev = self._zeros(nd, self.ldb)
+        if r is None:
+            seed = self.seed if self.seed is not None else int(N.random.randint(0, 2 ** 31 - 1))
+            _lib.call("pymd_philox_uniform", rdev.data_ptr(), nd, self.ldb, int(seed), 0xFFFF0000 + self._ninit,
+                      self.traj0, _lib.stream_ptr())
+            self._ninit += 1
+        else:
+            ra = N.asarray(r, dtype=N.float64)
+            if ra.shape == (nd,):
+                ra = N.broadcast_to(ra[:, None], (nd, self.batch))
+            elif ra.shape == (self.batch, nd):
+                ra = ra.T
+            elif ra.shape != (nd, self.batch):
+                raise ValueError("r must have shape (nph,), (nph, batch) or (batch, nph)")
+            rdev[:, :self.batch] = torch.as_tensor(N.ascontiguousarray(ra)).to(rdev.device)
+        Um = N.ascontiguousarray(self.U, dtype=N.float64)
+        _lib.call("pymd_init_state", self._ctx, Um.ctypes.data, hw.ctypes.data, am.ctypes.data,
+                  rdev.data_ptr(), _lib.stream_ptr())
+        if self.batch < self.ldb:
+            self._p[:, self.batch:] = 0.0
+            self._q[:, self.batch:] = 0.0
+        self.pinit, self.qinit = self.p, self.q
+
+    def ResetHis(self):
+        """Zero the friction-kernel history (md.py:292-301)."""
+        if self.nph is None or self.ml is None:
+            raise ValueError("self.nph and self.ml are not set!")
+        self._ensure()
+        _lib.call("pymd_reset_history", self._ctx, _lib.stream_ptr())
+
+    def steps(self, n):
+        """n consecutive md.vv steps for the whole ensemble in one library call."""
+        self._ensure()
+        self._bind()
+        _lib.call("pymd_step", self._ctx, int(self.t), int(n), int(self.step_mode), _lib.stream_ptr())
+        self.t = int(self.t) + int(n)
+
+    def vv(self):
+        """One modified velocity-Verlet step (md.py:315-358)."""
+        self.steps(1)
+
+    def potforce(self, q):
+        """-dyn.q for a host vector (md.py:444-492, dynamical-matrix branch)."""
+        import torch
+        if self.dyn is None:
+            raise ValueError("no driver, no md")
+        d = torch.as_tensor(self.dyn, dtype=torch.float64, device=self._dev())
+        return (-(d @ torch.as_tensor(N.asarray(q, dtype=float), device=self._dev()))).cpu().numpy()
+
+    def force(self, t, p, q, id=0):
+        """Potential + bath forces for ONE host state (md.py:360-383), using the current device
+        history; diagnostic helper (the time loop never calls it)."""
+        phis = self._history() if self.batch == 1 else self._history()[0]
+        qhis = N.zeros_like(phis)
+        if id == 0:
+            phis[0], qhis[0] = p, q
+        else:
+            phis = N.concatenate((N.asarray([p]), phis[:-1]), axis=0)
+            qhis[0] = q
+        f = self.potforce(q)
+        for b in self.baths:
+            f = f + b.bforce(t + id, phis, qhis)
+        return f
+
+    def GetPower(self):
+        """Ensemble-averaged power spectra from the saved trajectories (md.py:303-313,
+        spectrum.py:8-45)."""
+        if not self.savepq or self._ps is None:
+            raise ValueError("md.GetPower: trajectories not saved! you need to set savepq to True!")
+        from .spectrum import ensemble_powerspec
+        dw = 2. * N.pi / self.dt / self.nmd
+        w = dw * N.arange(self.nmd)
+        s1 = ensemble_powerspec(self._qs, self.dt, self.nmd, self.batch, wsq=True)
+        s2 = ensemble_powerspec(self._ps, self.dt, self.nmd, self.batch, wsq=False)
+        self.power_sum, self.power2_sum = s1, s2              # sums over local trajectories (for allreduce)
+        self.power = N.stack((w, s1 / self.batch), axis=1)
+        self.power2 = N.stack((w, s2 / self.batch), axis=1)
+
+    def Run(self):
+        """nrep consecutive segments of nmd steps each: fresh noise per segment, npie pieces
+        with a checkpoint after each, running mean of the spectra, kappa/power text outputs
+        (md.py:523-652)."""
+        self.initialise()
+        self.ResetHis()
+        self.curmean = N.zeros((self.nrep, len(self.baths)))
+        for j in range(self.nrep):
+            ipie = -1
+            state = self._resume(j)
+            if state == "finished":
+                continue
+            if state is not None:
+                ipie = state
+            else:
+                for b in self.baths:
+                    b.gnoi()
+                self.ResetSavepq(self._savepq)
+            for i in range(ipie + 1, self.npie):
+                self.steps(self.nmd // self.npie)
+                self.dump(i, j)
+            power, power2 = N.copy(self.power), N.copy(self.power2)
+            if self._savepq:
+                self.GetPower()
+                self.power = (power * j + self.power) / float(j + 1)       # md.py:604-607
+                self.power2 = (power2 * j + self.power2) / float(j + 1)
+            self.dump(self.npie - 1, j)
+            for ii, b in enumerate(self.baths):
+                self.curmean[j, ii] = float(b._cur_dev[:, :self.batch].mean().item()) * U.curcof
+            if self.write_files:
+                self._write_outputs(j)
+
+    # ------------------------------------------------------------------ outputs / checkpoints
+    def _write_outputs(self, j):
+        """kappa.<T>.bath<i>.run<j>.dat, power.<T>.run<j>.dat, power2.<T>.run<j>.dat
+        (md.py:616-652); spectra truncated at 1.5 max(hw)."""
+        for ii in range(len(self.baths)):
+            with open(os.path.join(self.outdir, "kappa.%s.bath%d.run%d.dat" % (self.T, ii, j)), "w") as fk:
+                fk.write("%i %f    %f \n" % (j, self.T, self.curmean[j, ii]))
+        for name, arr in (("power", self.power), ("power2", self.power2)):
+            with open(os.path.join(self.outdir, "%s.%s.run%d.dat" % (name, self.T, j)), "w") as f:
+                lim = None if self.hw is None else 1.5 * max(self.hw)
+                for i in range(len(arr)):
+                    if lim is not None and not arr[i, 0] < lim:
+                        break
+                    f.write("%f     %f \n" % (arr[i, 0], arr[i, 1]))
+
+    def _ckpt_name(self, j):
+        return os.path.join(self.outdir, "MD%d.npz" % j)
+
+    def dump(self, ipie, id):
+        """Checkpoint with the reference's variable names (md.py:654-705); NetCDF is not
+        available in this image, so the container is a numpy .npz."""
+        if not self.write_files:
+            return
+        d = dict(power=self.power, power2=self.power2, energy=self.etot, p=self.p, q=self.q,
+                 t=N.array([self.t]), ipie=N.array([ipie]), phis=self._history(),
+                 created=N.array([time.time()]))
+        if self._savepq:
+            d["ps"], d["qs"] = self.ps, self.qs
+        for i, b in enumerate(self.baths):
+            d["noise%d" % i] = b.noise
+            d["cur%d" % i] = b.cur
+        tmp = self._ckpt_name(id) + ".tmp.npz"
+        N.savez(tmp, **d)
+        os.replace(tmp, self._ckpt_name(id))
+
+    def _resume(self, j):
+        """md.py:541-582: resume an unfinished segment, skip a finished one, or chain the
+        state from the previous segment's checkpoint."""
+        fn, fnm = self._ckpt_name(j), self._ckpt_name(j - 1)
+        if self.write_files and os.path.isfile(fn):
+            d = N.load(fn)
+            ipie = int(d["ipie"][0])
+            if ipie + 1 < self.npie:
+                self.p, self.q = d["p"], d["q"]
+                self.t = int(d["t"][0])
+                self.set_history(d["phis"])
+                self.power, self.power2 = d["power"], d["power2"]
+                for i, b in enumerate(self.baths):
+                    b.noise = d["noise%d" % i]
+                self.ResetSavepq(self._savepq)
+                if self._savepq and "ps" in d:
+                    self._upload(self._ps, d["ps"])
+                    self._upload(self._qs, d["qs"])
+                return ipie
+            if ipie + 1 == self.npie:
+                self.power, self.power2 = d["power"], d["power2"]
+                self.t = int(d["t"][0])
+                return "finished"
+            raise ValueError("ipie error")
+        if self.write_files and os.path.isfile(fnm):
+            d = N.load(fnm)
+            self.p, self.q = d["p"], d["q"]
+            self.t = int(d["t"][0])
+            if d["phis"].shape[-2:] == (self.ml, self.nph):
+                self.set_history(d["phis"])
+        return None
+
+
+def sameq(q1, q2):
+    """md.py:724-736."""
+    if len(q1) != len(q2):
+        return False
+    return bool(N.max(N.abs(N.asarray(q1) - N.asarray(q2))) < 10e-10)
+
+
+def ApplyConstraint(f, constr=None):
+    """Remove the components of a host vector f along each normalised constraint vector
+    (md.py:739-762); all dot products use the un-projected f."""
+    if constr is None:
+        return f
+    f = N.array(f, dtype=float)
+    c = N.array(constr, dtype=float)
+    nf = 1.0 * f
+    for i in range(c.shape[0]):
+        nn = LA.norm(c[i])
+        ci = c[i] / nn if nn != 0 else c[i]
+        nf = nf - N.dot(f, ci) * ci
+    return nf

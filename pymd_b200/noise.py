@@ -1,0 +1,149 @@
+"""Coloured quantum noise (reference noise.py).
+
+Host side (setup, identical for every trajectory of the ensemble, done with numpy exactly
+as the reference does): the noise covariance per positive frequency and its
+eigen-decomposition, packed as spectral factors L_f = U_f diag(sqrt(max(lambda_f, 0))).
+
+Device side (per trajectory, libpymd_b200): white noise (Philox or supplied), X_f = L_f xi_f,
+Hermitian mirror, w->t FFT, real part  (noise.py:61-88, 156-190, vargau 252-284).
+"""
+import numpy as N
+
+from . import units as U
+from . import _lib
+from .functions import bose, flinterp
+from .matrix import chkShape, hermitianize
+
+
+def equ(w, cut, T, classical=False, zpmotion=True):
+    """2 hw (n_B(hw,T) + zp) for hw < cut, else 0; 2 kb T in the classical limit and at
+    hw == 0 (noise.py:229-250).  ``w`` may be an array."""
+    hw = U.hbar * N.asarray(w, dtype=float)
+    zp = 0.5 if zpmotion is True else 0.0
+    if classical:
+        val = N.full_like(hw, 2.0 * U.kb * T)
+    else:
+        val = N.where(hw == 0, 2.0 * U.kb * T, 2.0 * hw * (zp + bose(hw, T)))
+    out = N.where(hw < cut, val, 0.0)
+    return out if out.ndim else float(out)
+
+
+def phnoisew(gamma, wl, T, phcut, classical=False, zpmotion=True):
+    """Phonon noise spectrum equ(w) gamma(w) on the wl grid (noise.py:16-34)."""
+    gamma = N.asarray(gamma)
+    e = equ(N.asarray(wl), phcut, T, classical, zpmotion)
+    return e.reshape((-1,) + (1,) * (gamma.ndim - 1)) * gamma
+
+
+def _electron_cov(w, efric, exim, exip, bias, T, ecut, classical, zpmotion, delta=1.0):
+    """noise.py:103-127 / 156-170: equilibrium part + the two bias-shifted parts."""
+    w = N.asarray(w, dtype=float)
+    efric, exim, exip = N.asarray(efric), N.asarray(exim), N.asarray(exip)
+    aw = (delta * equ(w, ecut, T, classical, zpmotion))[:, None, None]
+    awm = (delta * equ(U.hbar * w - bias, ecut, T, classical, zpmotion))[:, None, None]
+    awp = (delta * equ(U.hbar * w + bias, ecut, T, classical, zpmotion))[:, None, None]
+    amat = aw * efric + (-0.5 * aw * exip + 0.5 * awm * (exip + 1j * exim)) \
+        + (-0.5 * aw * exip + 0.5 * awp * (exip - 1j * exim))
+    return 0.5 * (amat + N.conj(N.transpose(amat, (0, 2, 1))))
+
+
+def enoisew(wl, efric, exim, exip, bias, T, ecut, classical=False, zpmotion=True):
+    """Electron noise spectrum on the wl grid, no sampling (noise.py:91-129)."""
+    nc = chkShape(efric)
+    if chkShape(exim) != nc or chkShape(exip) != nc:
+        raise ValueError("enoisew: efric shape error!")
+    return _electron_cov(wl, efric, exim, exip, bias, T, ecut, classical, zpmotion)
+
+
+class SpectralFactors:
+    """lam[f, i], U[f, :, i] (as numpy.linalg.eigh returns them) and L = U sqrt(max(lam,0))."""
+
+    def __init__(self, lam, vec):
+        self.lam, self.U = lam, vec
+        self.L = vec * N.sqrt(N.maximum(lam, 0.0))[:, None, :]
+        self.complex = N.iscomplexobj(vec)
+
+    def as_oracle(self):
+        return self.lam, self.U
+
+
+def phonon_factors(gamma, wl, T, phcut, dt, nmd, classical=False, zpmotion=True):
+    """Covariance delta*equ(w_f)*gamma~(w_f), f = 0..nmd/2 (noise.py:61-66), eigh (noise.py:69)."""
+    nf = int(nmd / 2) + 1
+    dw = 2.0 * N.pi / dt / nmd
+    delta = dt * nmd
+    w = dw * N.arange(nf)
+    amat = (delta * equ(w, phcut, T, classical, zpmotion))[:, None, None] * flinterp(w, wl, N.asarray(gamma))
+    amat = 0.5 * (amat + N.conj(N.transpose(amat, (0, 2, 1))))
+    lam, vec = N.linalg.eigh(amat)
+    return SpectralFactors(lam, vec)
+
+
+def electron_factors(efric, exim, exip, bias, T, ecut, dt, nmd, classical=False, zpmotion=True):
+    """Bias-dependent Hermitian covariance (noise.py:156-170), eigh (noise.py:172)."""
+    nf = int(nmd / 2) + 1
+    dw = 2.0 * N.pi / dt / nmd
+    w = dw * N.arange(nf)
+    amat = _electron_cov(w, efric, exim, exip, bias, T, ecut, classical, zpmotion, delta=dt * nmd)
+    lam, vec = N.linalg.eigh(amat)
+    return SpectralFactors(lam, vec)
+
+
+# ------------------------------------------------------------------ device pipeline
+def white_noise(nf, nc, ldb, seed, stream_id, traj0=0, device=None):
+    """Standard normals [nf][nc][ldb] from the library's Philox generator (replaces the
+    sequential N.random.normal draws of noise.vargau, noise.py:282)."""
+    import torch
+    xi = torch.empty((nf, nc, ldb), dtype=torch.float64, device=device or "cuda")
+    _lib.call("pymd_philox_normal", xi.data_ptr(), nf * nc, ldb, int(seed) & (2 ** 64 - 1),
+              int(stream_id) & 0xFFFFFFFF, int(traj0), _lib.stream_ptr())
+    return xi
+
+
+def generate(factors, xi, dt, nmd, out=None):
+    """noise[t][i][traj] on the device from spectral factors and white noise xi [nf][nc][ldb]."""
+    import torch
+    nf, nc, ldb = xi.shape
+    if nf != int(nmd / 2) + 1 or factors.L.shape != (nf, nc, nc):
+        raise ValueError("noise.generate: shape mismatch")
+    dev = xi.device
+    lre = torch.as_tensor(N.ascontiguousarray(factors.L.real), dtype=torch.float64, device=dev)
+    lim = torch.as_tensor(N.ascontiguousarray(factors.L.imag), dtype=torch.float64, device=dev) \
+        if factors.complex else None
+    if out is None:
+        out = torch.empty((nmd, nc, ldb), dtype=torch.float64, device=dev)
+    work = torch.empty(_lib.load().pymd_noise_work_bytes(nmd, nc, ldb), dtype=torch.uint8, device=dev)
+    _lib.call("pymd_noise_generate", lre.data_ptr(), _lib.ptr(lim), xi.data_ptr(), nmd, nc, ldb, float(dt),
+              out.data_ptr(), work.data_ptr(), _lib.stream_ptr())
+    return out
+
+
+def _as_device_xi(xi, nf, nc, batch, ldb, device):
+    """Accept user-supplied normals shaped (nf, nc) or (nf, nc, batch); pad to ldb."""
+    import torch
+    x = torch.as_tensor(N.asarray(xi) if not hasattr(xi, "device") else xi, dtype=torch.float64)
+    if x.dim() == 2:
+        x = x[:, :, None]
+    if x.shape[0] != nf or x.shape[1] != nc or x.shape[2] != batch:
+        raise ValueError("xi must have shape (%d, %d[, %d])" % (nf, nc, batch))
+    full = torch.zeros((nf, nc, ldb), dtype=torch.float64, device=device)
+    full[:, :, :batch] = x.to(device)
+    return full
+
+
+def phnoise(gamma, wl, T, phcut, dt, nmd, classical=False, zpmotion=True, xi=None, seed=0):
+    """Single-trajectory convenience with the reference's signature (noise.py:38): returns a
+    host array (nmd, nc).  Runs on the GPU."""
+    import torch
+    fac = phonon_factors(gamma, wl, T, phcut, dt, nmd, classical, zpmotion)
+    nf, nc = fac.lam.shape
+    x = white_noise(nf, nc, 32, seed, 0) if xi is None else _as_device_xi(xi, nf, nc, 1, 32, "cuda")
+    return generate(fac, x, dt, nmd)[:, :, 0].cpu().numpy()
+
+
+def enoise(efric, exim, exip, bias, T, ecut, dt, nmd, classical=False, zpmotion=True, xi=None, seed=0):
+    """Single-trajectory convenience with the reference's signature (noise.py:135)."""
+    fac = electron_factors(efric, exim, exip, bias, T, ecut, dt, nmd, classical, zpmotion)
+    nf, nc = fac.lam.shape
+    x = white_noise(nf, nc, 32, seed, 0) if xi is None else _as_device_xi(xi, nf, nc, 1, 32, "cuda")
+    return generate(fac, x, dt, nmd)[:, :, 0].cpu().numpy()

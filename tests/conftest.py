@@ -39,3 +39,17 @@ def golden():
                 self._c[name] = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
             return self._c[name]
     return G()
+
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+@pytest.fixture(scope="session")
+def cuda():
+    """GPU tests must FAIL (not skip) without a device or without the native library."""
+    import torch
+    assert torch.cuda.is_available(), "GPU test selected but no CUDA device is visible"
+    import __graft_entry__ as ge
+    ge.build()
+    from pymd_b200 import _lib
+    _lib.load()
+    return torch.device("cuda", 0)

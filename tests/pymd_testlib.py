@@ -1,0 +1,124 @@
+"""Shared builders for the parity tests: the same synthetic junction is set up once through
+pymd_b200 (device) and once through the oracle, fed identical white noise / phases / spectral
+factors, and stepped side by side."""
+import numpy as np
+
+from oracle import pymd_oracle as O
+from pymd_b200 import synth
+from pymd_b200.ebath import ebath
+from pymd_b200.md import md
+from pymd_b200.phbath import phbath
+
+CASES = {
+    # name: junction args, md/bath parameters
+    "ph2": dict(nd=12, ncl=3, ncr=3, seed=11, dt=8.0, nmd=64, T=300.0, dT=20.0, ml=8, nw=40, hwcut=0.03,
+                ebath=False, constraint=False),
+    "eph": dict(nd=12, ncl=3, ncr=3, seed=21, dt=1.0, nmd=32, T=100.0, dT=0.0, ml=6, nw=30, hwcut=0.03,
+                ebath=True, bias=0.3, constraint=True),
+    "chain39": dict(nd=39, ncl=15, ncr=15, seed=3, dt=8.0, nmd=128, T=300.0, dT=30.0, ml=100, nw=200, hwcut=0.03,
+                    ebath=False, constraint=False),
+    "aubz": dict(nd=60, ncl=15, ncr=15, seed=4, dt=1.0, nmd=64, T=300.0, dT=10.0, ml=100, nw=200, hwcut=0.03,
+                 ebath=True, bias=0.5, constraint=True),
+    "ragged": dict(nd=21, ncl=6, ncr=9, seed=5, dt=4.0, nmd=32, T=77.0, dT=5.0, ml=19, nw=50, hwcut=0.03,
+                   ebath=True, bias=0.2, constraint=False, nce=12),
+}
+
+
+def junction(c):
+    return synth.synth(c["nd"], c["ncl"], c["ncr"], seed=c["seed"], constraint=c["constraint"],
+                       nc_e=c.get("nce"))
+
+
+def make_baths(mod_ph, mod_eb, j, c, **kw):
+    baths = []
+    if c["ebath"]:
+        baths.append(mod_eb(j.cats_e, c["T"], c["dt"], c["nmd"], wmax=1.0, nw=500, bias=c["bias"], efric=j.efric,
+                            exim=j.exim, exip=j.exip, zeta1=j.zeta1, zeta2=j.zeta2, **kw))
+    pl = mod_ph(c["T"] + c["dT"] / 2, j.cats_l, c["hwcut"], c["nw"], c["dt"], c["nmd"], ml=c["ml"], sig=j.SigL,
+                gwl=j.wl, **kw)
+    pr = mod_ph(c["T"] - c["dT"] / 2, j.cats_r, c["hwcut"], c["nw"], c["dt"], c["nmd"], ml=c["ml"], sig=j.SigR,
+                gwl=j.wl, **kw)
+    pl.gmem(); pr.gmem()
+    return baths + [pl, pr]
+
+
+def device_md(c, batch, savepq=True, step_mode=0, **kw):
+    j = junction(c)
+    m = md(c["dt"], c["nmd"], c["T"], axyz=j.axyz, harmonic=True, dyn=j.DynMat, savepq=savepq,
+           constr=None if j.constr is None else j.constr.copy(), batch=batch, step_mode=step_mode, **kw)
+    m.write_files = False
+    for b in make_baths(phbath, ebath, j, c):
+        m.AddBath(b)
+    return m, j
+
+
+def oracle_md(c, j, share_kernels_from=None):
+    m = O.md(c["dt"], c["nmd"], c["T"], axyz=j.axyz, harmonic=True, dyn=j.DynMat,
+             constr=None if j.constr is None else j.constr.copy())
+    for i, b in enumerate(make_baths(O.phbath, O.ebath, j, c)):
+        if share_kernels_from is not None and hasattr(b, "gmem") and not getattr(b, "local", True):
+            b.kernel = np.asarray(share_kernels_from.baths[i].kernel)
+        m.AddBath(b)
+    return m
+
+
+def draw(c, m, batch, seed, nrep=1):
+    """White noise per segment/bath, shape (nf, nc, batch), and phases (nd, batch)."""
+    rng = np.random.default_rng(seed)
+    nf = c["nmd"] // 2 + 1
+    xi = [[rng.standard_normal((nf, b.nc, batch)) for b in m.baths] for _ in range(nrep)]
+    r = rng.uniform(0, 1, (c["nd"], batch))
+    return xi, r
+
+
+def run_oracle(c, j, dev, xi, r, n, nsteps, nrep=1):
+    """Trajectory n of the ensemble through the oracle; returns dict of records per segment."""
+    om = oracle_md(c, j)
+    om.initialise(r=r[:, n])
+    om.ResetHis()
+    recs = []
+    for rep in range(nrep):
+        for b, ob in enumerate(om.baths):
+            ob.gnoi(xi=xi[rep][b][:, :, n], factors=dev.baths[b].spectral_factors().as_oracle())
+        om.ResetSavepq()
+        for _ in range(nsteps):
+            om.vv()
+        recs.append(dict(ps=om.ps.copy(), qs=om.qs.copy(), etot=om.etot.copy(),
+                         cur=[ob.cur.copy() for ob in om.baths], noise=[ob.noise.copy() for ob in om.baths],
+                         p=om.p.copy(), q=om.q.copy(), phis=om.phis.copy()))
+    return om, recs
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+# ---- numpy mirror of the library's Philox4x32-10 streams ---------------------------------
+def philox4x32(c0, c1, c2, c3, k0, k1):
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    c = [np.asarray(x, dtype=np.uint64) for x in (c0, c1, c2, c3)]
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = [(hi1 ^ c[1] ^ k0) & mask, lo1, (hi0 ^ c[3] ^ k1) & mask, lo0]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return c
+
+
+def philox_uniforms(rows, ldb, seed, stream_id, traj0=0):
+    r = np.arange(rows, dtype=np.uint64)[:, None] + np.zeros((1, ldb), dtype=np.uint64)
+    tr = np.uint64(traj0) + np.arange(ldb, dtype=np.uint64)[None, :] + np.zeros((rows, 1), dtype=np.uint64)
+    x = philox4x32(r & np.uint64(0xFFFFFFFF), r >> np.uint64(32), tr & np.uint64(0xFFFFFFFF),
+                   np.uint64(stream_id) + 0 * tr, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    u1 = (((x[1] << np.uint64(32)) | x[0]) >> np.uint64(11)).astype(np.float64) + 0.5
+    u2 = (((x[3] << np.uint64(32)) | x[2]) >> np.uint64(11)).astype(np.float64) + 0.5
+    return u1 / 9007199254740992.0, u2 / 9007199254740992.0
+
+
+def philox_normals(rows, ldb, seed, stream_id, traj0=0):
+    u1, u2 = philox_uniforms(rows, ldb, seed, stream_id, traj0)
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)

@@ -1,0 +1,157 @@
+"""Host-side setup tables of pymd_b200 (vectorised numpy) against the golden vectors minted
+from the reference and against the oracle.  Tolerances: these tables differ from the
+reference only in summation order (vectorised mean / tensordot), so 1e-13 relative to the
+largest entry; element-wise functions must agree exactly."""
+import numpy as np
+import pytest
+
+from oracle import pymd_oracle as O
+from pymd_b200 import synth
+from pymd_b200 import functions as F
+from pymd_b200 import noise as PN
+from pymd_b200 import harmonic as H
+from pymd_b200.phbath import phbath, gamt
+from pymd_b200.ebath import ebath
+from pymd_b200.md import md, ApplyConstraint, sameq
+
+
+def relmax(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+
+
+@pytest.mark.filterwarnings("ignore:overflow")
+def test_scalar_tables_exact(golden):
+    g = golden("setup")
+    assert np.array_equal(F.flinterp(g["fl_xq"], g["fl_xs"], g["fl_ys"]), g["fl_out"])
+    for x, y in zip(g["fl_xq"], g["fl_out"]):
+        assert F.flinterp(float(x), g["fl_xs"], g["fl_ys"]) == y
+    wq = g["wq"]
+    assert np.array_equal(np.array([F.bose(wq, T) for T in (0.0, 4.2, 300.0)]), g["bose_tab"])
+    eq = np.array([[PN.equ(wq, 0.03, T, cl, zp) for T in (0.0, 300.0)]
+                   for cl in (False, True) for zp in (True, False)])
+    assert np.array_equal(eq, g["equ_tab"])
+    assert F.bose(0.01, 300.0) == O.bose(0.01, 300.0) and F.bose(0.0, 300.0) == 0.0
+    assert F.nearest(0.9, [0, 1, 2]) == 1
+
+
+def test_flinterp_matrix_valued_matches_oracle():
+    j = synth.synth(12, 6, 3, seed=41)
+    gam = -np.imag(j.SigL[1:]) / j.wl[1:, None, None]
+    xs = j.wl[1:]
+    xq = np.concatenate(([0.0, xs[0], xs[-1], 1.0], np.random.default_rng(0).uniform(0, 0.07, 50)))
+    got = F.flinterp(xq, xs, gam)
+    for i, x in enumerate(xq):
+        assert np.array_equal(got[i], O.flinterp(x, xs, gam))
+
+
+def test_kernel_tables_vs_reference(golden):
+    c, g = golden.cfg("ph2"), golden("ph2")
+    j = synth.synth(12, 3, 3, seed=11)
+    pl = phbath(c["T"] + c["dT"] / 2, j.cats_l, c["hwcut"], c["nw"], c["dt"], c["nmd"], ml=c["ml"], sig=j.SigL, gwl=j.wl)
+    pl.gmem()
+    assert np.array_equal(pl.gamma, g["gamma0"])
+    assert pl.kernel.shape == g["kernel0"].shape and relmax(pl.kernel, g["kernel0"]) < 1e-13
+    assert list(pl.cids) == [0, 1, 2] and pl.nc == 3 and not pl.local and pl.wmax == 0.06
+
+
+def test_eta_ad_kernel_vs_reference(golden):
+    c, g = golden.cfg("setup"), golden("setup")
+    j = synth.synth(12, 6, 3, seed=41)
+    pa = phbath(c["T"], j.cats_l, c["hwcut"], c["nw"], c["dt"], c["nmd"], ml=c["ml"], sig=j.SigL, gwl=j.wl,
+                eta_ad=c["eta_ad"])
+    pa.gmem()
+    assert relmax(pa.kernel, g["kernel"]) < 1e-13
+    assert relmax(pa.gamma, g["gamma_new"]) < 1e-13
+    assert np.array_equal(pa.gammaOld, g["gamma_old"])
+
+
+def test_debye_bath_is_local(golden):
+    c, g = golden.cfg("debye"), golden("debye")
+    pd = phbath(c["Tph"], [0, 2], c["debye"], c["nw"], c["dt"], c["nmd"], classical=True, zpmotion=False)
+    pd.gmem()
+    assert pd.local and pd.ml == 1 and np.array_equal(pd.kernel, g["kernel0"])
+
+
+def test_ebath_matrices_and_errors(golden):
+    g = golden("eph")
+    c = golden.cfg("eph")
+    j = synth.synth(12, 3, 3, seed=21, constraint=True)
+    eb = ebath(j.cats_e, c["T"], c["dt"], c["nmd"], wmax=1.0, nw=500, bias=c["bias"], efric=j.efric, exim=j.exim,
+               exip=j.exip, zeta1=j.zeta1, zeta2=j.zeta2)
+    ob = O.ebath(j.cats_e, c["T"], c["dt"], c["nmd"], wmax=1.0, nw=500, bias=c["bias"], efric=j.efric, exim=j.exim,
+                 exip=j.exip, zeta1=j.zeta1, zeta2=j.zeta2)
+    for k in ("efric", "exim", "exip", "zeta1", "zeta2"):
+        assert np.array_equal(getattr(eb, k), getattr(ob, k))
+    assert eb.ml == 1 and eb.nc == 12 and eb.kernel.shape == (1, 12, 12)
+    eb.GetSig(); ob.GetSig()
+    assert np.allclose(eb.sig, ob.sig, rtol=1e-15, atol=0)
+    with pytest.raises(ValueError):
+        ebath(j.cats_e, 1.0, 1.0, 16, efric=np.eye(5))
+    assert ebath([0], 1.0, 1.0, 16).ebath is False
+
+
+def test_spectral_factors_reproduce_covariance(golden):
+    """L L^dagger == covariance wherever it is PSD, and lam/U equal numpy.linalg.eigh of the
+    oracle's covariance matrices (same LAPACK call => same gauge)."""
+    c = golden.cfg("eph")
+    j = synth.synth(12, 3, 3, seed=21)
+    pl = phbath(c["T"], j.cats_l, c["hwcut"], c["nw"], c["dt"], c["nmd"], ml=c["ml"], sig=j.SigL, gwl=j.wl)
+    fac = pl.spectral_factors()
+    for f in range(c["nmd"] // 2 + 1):
+        cov = O.phonon_cov(f, pl.gamma, pl.gwl, pl.T, pl.wmax, pl.dt, pl.nmd, False, True)
+        av, au = np.linalg.eigh(cov)
+        assert np.array_equal(fac.lam[f], av) and np.array_equal(fac.U[f], au)
+        assert np.allclose(fac.L[f] @ fac.L[f].conj().T, (au * np.maximum(av, 0)) @ au.T, rtol=1e-12, atol=1e-30)
+    eb = ebath(j.cats_e, c["T"], c["dt"], c["nmd"], wmax=1.0, nw=500, bias=c["bias"], efric=j.efric, exim=j.exim,
+               exip=j.exip)
+    fe = eb.spectral_factors()
+    assert fe.complex
+    for f in (0, 1, 7, c["nmd"] // 2):
+        cov = O.electron_cov(f, eb.efric, eb.exim, eb.exip, eb.bias, eb.T, eb.wmax, eb.dt, eb.nmd, False, True)
+        assert relmax(fe.lam[f], np.linalg.eigvalsh(cov)) < 1e-12
+        pos = (fe.U[f] * np.maximum(fe.lam[f], 0)) @ fe.U[f].conj().T
+        assert np.allclose(fe.L[f] @ fe.L[f].conj().T, pos, rtol=1e-12, atol=1e-30)
+
+
+def test_noise_spectra_and_harmonic_vs_reference(golden):
+    g = golden("setup")
+    Ds = H.Drs(g["h_wl"], g["h_dyn"], g["h_se"])
+    assert relmax(H.DDos(g["h_wl"], Ds), g["h_DDos"]) < 1e-12
+    assert relmax(H.PP(g["h_wl"], Ds, g["h_noise"]), g["h_PP"]) < 1e-12
+    assert relmax(H.UU(g["h_wl"], Ds, g["h_noise"]), g["h_UU"]) < 1e-12
+    j = synth.synth(12, 6, 3, seed=41)
+    wl = g["h_wl"]
+    gam = np.array([-O.flinterp(w, j.wl, j.SigL).imag / w for w in wl])
+    assert np.array_equal(PN.phnoisew(gam, wl, 150.0, 0.03), O.phnoisew(gam, wl, 150.0, 0.03))
+    a = PN.enoisew(wl, j.efric, j.exim, j.exip, 0.3, 100.0, 1.0)
+    b = O.enoisew(wl, j.efric, j.exim, j.exip, 0.3, 100.0, 1.0)
+    assert relmax(a, b) < 1e-14
+    assert relmax(H.SigE(wl, j.efric, j.exim, j.zeta1, j.zeta2, 0.3), O.SigE(wl, j.efric, j.exim, j.zeta1, j.zeta2, 0.3)) < 1e-15
+
+
+def test_setdyn_and_helpers(golden):
+    g = golden("ph2")
+    m = md(8.0, 64, 300.0, dyn=g["dyn_in"])
+    assert relmax(m.dyn, g["dyn"]) < 1e-13 and relmax(m.hw, g["hw"]) < 1e-12
+    assert m.nph == 12 and m.ml == 1 and m.t == 0
+    bad = g["dyn_in"].copy()
+    bad[0, 0] = -1.0                       # negative eigenvalue must be clamped (md.py:228-237)
+    m2 = md(8.0, 64, 300.0, dyn=bad)
+    assert m2.hw.min() >= 0 and np.linalg.eigvalsh(m2.dyn).min() > -1e-18
+    c = np.array([[1.0, 2.0, 0.0], [0.0, 0.0, 3.0]])
+    f = np.array([0.3, -0.2, 0.9])
+    assert np.array_equal(ApplyConstraint(f, c), O.ApplyConstraint(f, c))
+    assert ApplyConstraint(f, None) is f
+    assert sameq([1.0, 2.0], [1.0, 2.0 + 1e-10]) and not sameq([1.0], [1.0, 2.0]) and not sameq([1.0], [1.1])
+    with pytest.raises(ValueError):
+        md(8.0, 64, 300.0, axyz=[["Au", 0, 0, 0]], dyn=g["dyn_in"])
+    with pytest.raises(ValueError):
+        m.AddBath(phbath(300.0, [0], 0.03, 10, 4.0, 64))        # dt mismatch (md.py:164-166)
+
+
+def test_gamt_vs_oracle_large_table():
+    j = synth.synth(12, 6, 3, seed=5)
+    gam = -np.imag(j.SigL[1:]) / j.wl[1:, None, None]
+    wl = [0.06 * i / 60 for i in range(60)]
+    tl = [4.0 * i for i in range(12)]
+    assert relmax(gamt(tl, wl, j.wl[1:], gam), O.gamt(tl, wl, j.wl[1:], gam)) < 1e-13
