@@ -4,14 +4,10 @@ The reference's bath protocol (what md touches): .dt, .nmd
 .noise, .cur, .gnoi(), .bforce(t, phis, qhis).  The extra optional knobs here (batch, seed,
 xi=) default to the reference's single-trajectory behaviour.
 """
-import itertools
-
 import numpy as N
 
 from . import _lib
 from . import noise as _noise
-
-_uid = itertools.count(1)
 
 
 def _round_up(x, m):
@@ -20,7 +16,7 @@ def _round_up(x, m):
 
 class BathBase(object):
     def _init_ensemble(self, batch=None, seed=None, device=None):
-        self._uid = next(_uid)
+        self._index = 0                # position in md.baths (selects the Philox stream)
         self._batch = batch            # None until attached (md.AddBath) or first gnoi()
         self._seed = seed
         self._device = device
@@ -40,7 +36,8 @@ class BathBase(object):
     def ldb(self):
         return _round_up(self.batch, 32)
 
-    def _attach(self, batch, seed, traj0, device):
+    def _attach(self, batch, seed, traj0, device, index=0):
+        self._index = index
         if self._batch is not None and self._batch != batch:
             raise ValueError("bath was set up for an ensemble of %d, md has %d" % (self._batch, batch))
         self._batch = batch
@@ -80,7 +77,7 @@ class BathBase(object):
             if self._seed is None:
                 self._seed = int(N.random.randint(0, 2 ** 31 - 1))
             x = _noise.white_noise(nf, self.nc, self.ldb, self._seed,
-                                   (self._uid << 16) ^ self._ngnoi, self._traj0, dev)
+                                   ((self._index + 1) << 16) ^ self._ngnoi, self._traj0, dev)
             if self.batch < self.ldb:
                 x[:, :, self.batch:] = 0.0          # padding trajectories stay at rest
         else:

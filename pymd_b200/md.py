@@ -139,7 +139,7 @@ class md(object):
         if self.nmd != bath.nmd:
             raise ValueError("md.AddBath: number of md steps nmd not consistent!")
         bath._attach(self.batch, None if self.seed is None else self.seed + 7919 * (len(self.baths) + 1),
-                     self.traj0, self._dev())
+                     self.traj0, self._dev(), index=len(self.baths))
         self.baths.append(bath)
         if bath.ml > self.ml:
             self.ml = bath.ml
@@ -290,7 +290,7 @@ class md(object):
         else:
             raise ValueError("expected shape %s or %s" % (want, (self.batch,) + want))
         dst.zero_()
-        dst[..., :self.batch] = torch.as_tensor(N.ascontiguousarray(a), dtype=torch.float64).to(dst.device)
+        dst[..., :self.batch] = torch.as_tensor(N.array(a, dtype=N.float64, order='C'), dtype=torch.float64).to(dst.device)
 
     @property
     def p(self):
@@ -557,6 +557,7 @@ class md(object):
                 self.power, self.power2 = d["power"], d["power2"]
                 for i, b in enumerate(self.baths):
                     b.noise = d["noise%d" % i]
+                    self._upload(b._alloc_cur(), d["cur%d" % i])
                 self.ResetSavepq(self._savepq)
                 if self._savepq and "ps" in d:
                     self._upload(self._ps, d["ps"])
