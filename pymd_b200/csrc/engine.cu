@@ -307,8 +307,10 @@ int finalize(pymd_ctx* c) {
     d.samef = reinterpret_cast<int*>(w);
     d.con = c->d_con;
     d.nd = nd; d.ldb = ldb; d.nbath = c->nbath; d.nmd = c->nmd; d.ncon = c->ncon; d.dt = c->dt;
+    if (c->d_aqT) { cudaFree(c->d_aqT); c->d_aqT = nullptr; }
     c->finalized = true;
     c->fpot_valid = false;
+    c->fpotc_valid = false;
     c->tail_valid = false;
     return PYMD_OK;
 }
@@ -372,6 +374,11 @@ static int generic_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) 
         fill_int_kernel<<<(c->ldb + 255) / 256, 256, 0, st>>>(d.samef, 0, c->ldb);
         c->launches++;
         c->fpot_valid = true;
+        c->fpotc_valid = true;
+    }
+    if (c->ncon > 0 && !c->fpotc_valid) {      // coming from the fused path: refresh -K q(t)
+        if ((rc = compute_fpotc(c, st))) return rc;
+        c->fpotc_valid = true;
     }
     if (!c->tail_valid) {
         for (int b = 0; b < c->nbath; ++b)
@@ -455,7 +462,7 @@ int pymd_ctx_destroy(pymd_ctx* c) {
         cudaFree(H.d_cids); cudaFree(H.d_inv); cudaFree(H.d_head); cudaFree(H.d_aq);
         cudaFree(H.d_krev); cudaFree(H.d_kintra);
     }
-    cudaFree(c->d_dyn); cudaFree(c->d_mp); cudaFree(c->d_con); cudaFree(c->ws);
+    cudaFree(c->d_dyn); cudaFree(c->d_mp); cudaFree(c->d_con); cudaFree(c->d_aqT); cudaFree(c->ws);
     delete c;
     return PYMD_OK;
 }

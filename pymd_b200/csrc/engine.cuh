@@ -66,9 +66,10 @@ struct pymd_ctx {
     double* d_dyn = nullptr;           // [nd][ldn]
     double* d_mp = nullptr;            // [nd][ldn]  sum_b scatter(alpha_b kernel_b[0])
     double* d_con = nullptr;           // [ncon][nd]
+    double* d_aqT = nullptr;           // [nd][ldn]  q-coupled operator scattered to nd x nd (fused path)
     void* ws = nullptr;                // workspace
     size_t ws_bytes = 0;
     pymd::StepDev sd{};
-    bool finalized = false, fpot_valid = false, tail_valid = false;
+    bool finalized = false, fpot_valid = false, tail_valid = false, fpotc_valid = false;
     long long launches = 0;
 };

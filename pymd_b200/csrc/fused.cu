@@ -1,10 +1,707 @@
-// Fused on-chip step kernel (mode 2) -- placeholder until the per-step pipeline is parity-green.
+// Fused on-chip step kernel (mode 2): up to FT consecutive md.vv steps (reference md.py:315-358)
+// for a tile of 8*NT trajectories per CTA, without leaving the SM.
+//
+//   * The three nd x nd operators -- dyn (md.py:484), the summed k=0 bath heads
+//     Mp = sum_b scatter(alpha_b K_b[0]) (phbath.py:197-201 / ebath.py:191,194) and the q-coupled
+//     electron operator AqT (ebath.py:192-193) -- are held in REGISTERS as DMMA A-fragments: warp w
+//     owns rows 8w..8w+7, so one mat-vec round is ks DMMA.8x8x4 per 8 trajectories per warp.
+//   * State vectors (head velocity, q', half-kick, base force) live in shared memory, [64][N+4]
+//     doubles; the B-fragment read (ld % 16 == 4) and the C-fragment write are conflict free.
+//   * Memory-kernel friction: the block-Toeplitz GEMM (launch_tail, koff = 2) has already
+//     produced P[s] = dt sum_{k>=s+2} K[k] p(t0+1+s-k), the part that only needs history older
+//     than this block; the causal in-block part sum_{k=1}^{s+1} dt K[k] p(t0+1+s-k) is contracted
+//     here from an in-smem block history.  So the velocity history is read from HBM once per FT
+//     steps instead of once per step.
+//   * The three force evaluations of a step are sequential (each head depends on the previous
+//     result): three rounds A/B/C separated by one __syncthreads each; the head buffer is
+//     double buffered so no extra barrier protects it.
+//   * Per-bath heat currents (md.py:342) need the per-bath force only through scalars
+//     p.g_b; they are produced as warp-shuffle column reductions into per-warp slots and summed
+//     in a fixed order (deterministic, no atomics).
+#include <algorithm>
+#include <vector>
+
 #include "engine.cuh"
 
 namespace pymd {
-int fused_supported(const pymd_ctx*) { return 0; }
-int fused_step(pymd_ctx*, long long, int, cudaStream_t) {
-    pymd_set_error("fused path not built");
-    return PYMD_ESTATE;
+
+int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st);
+
+namespace {
+
+constexpr int FW = 8;        // warps per CTA
+constexpr int NDP = 64;      // padded rows (8 per warp)
+constexpr int FT = 8;        // steps per block
+constexpr int MAXKS = 16;    // k-steps of the nd x nd operators (nd <= 64)
+
+struct FusedBath {
+    int nc, ncp, ml, nonlocal, R, slot0, ntap, ldk;
+    int off_hd, off_kin, off_hist, off_nb, off_cids, off_inrem;   // smem offsets (doubles / ints)
+    const double* noise;
+    const double* P;          // [FT][nc][ldb] pre-block tail
+    double* tail_cur;         // [nc][ldb] tail(t) carried between launches
+    double* ring;
+    double* cur;
+    const double* head_g;     // [nc][lda]
+    const double* kin_g;      // [kBlockT][nc][nc]
+    const int* cids_g;
+    const int* inv_g;
+    int lda;
+};
+
+struct FusedParams {
+    int nd, ks, ldb, ldn, nbath, nmd, ncon, nsteps, rem, aq, carry_valid;
+    long long t0;
+    double dt;
+    double *p, *q, *ps, *qs, *etot, *fpotn;
+    int* samef;
+    const double *dyn, *mp, *aqT, *con;
+    int off_xp0, off_xp1, off_xq, off_ph, off_fb, off_curp, off_conp, off_maxp, off_conv, off_inv;
+    int smem_doubles;
+    FusedBath b[PYMD_MAX_BATHS];
+};
+
+__device__ __forceinline__ double colsum8(double v) {     // sum over the 8 lanes sharing lane%4
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
 }
+__device__ __forceinline__ double colmax8(double v) {
+    v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 4));
+    v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 8));
+    v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 16));
+    return v;
+}
+
+template <int NT>
+__device__ __forceinline__ void zero_acc(double (&a)[NT][2]) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j) a[j][0] = a[j][1] = 0.0;
+}
+
+// acc[j] += A(rows of this warp) . X[:, 8j..8j+7]   (A fragments in registers, X in smem)
+template <int NT>
+__device__ __forceinline__ void matvec1(const double (&a)[MAXKS], int ks, const double* X, int LD,
+                                        double (&acc)[NT][2], int lr, int lc) {
+#pragma unroll
+    for (int k = 0; k < MAXKS; ++k) {
+        if (k < ks) {
+            const double* xr = X + (4 * k + lc) * LD + lr;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) dmma884(acc[j][0], acc[j][1], a[k], xr[8 * j]);
+        }
+    }
+}
+// two operators sharing one B operand
+template <int NT>
+__device__ __forceinline__ void matvec2(const double (&a0)[MAXKS], const double (&a1)[MAXKS], int ks,
+                                        const double* X, int LD, double (&acc0)[NT][2],
+                                        double (&acc1)[NT][2], int lr, int lc) {
+#pragma unroll
+    for (int k = 0; k < MAXKS; ++k) {
+        if (k < ks) {
+            const double* xr = X + (4 * k + lc) * LD + lr;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const double b = xr[8 * j];
+                dmma884(acc0[j][0], acc0[j][1], a0[k], b);
+                dmma884(acc1[j][0], acc1[j][1], a1[k], b);
+            }
+        }
+    }
+}
+
+template <int NT, bool HASQ, bool HASCON>
+__global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) {
+    constexpr int N = 8 * NT, LD = N + 4;
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+    const int row = 8 * w + lr;                 // operator row owned by this thread
+    const int col0 = blockIdx.x * N;            // first trajectory of this CTA
+    const int nd = P.nd, ks = P.ks, nb = P.nbath;
+    const size_t ldb = P.ldb;
+    const double dt = P.dt, dt2 = P.dt * P.dt;
+
+    double* XPb[2] = {sm + P.off_xp0, sm + P.off_xp1};
+    double* XQ = sm + P.off_xq;
+    double* PH = sm + P.off_ph;
+    double* FB = sm + P.off_fb;
+    double* CURP = sm + P.off_curp;             // [(nb+1)][FW][N]
+    double* CONP = sm + P.off_conp;             // [ncon][2][FW][N]
+    double* MAXP = sm + P.off_maxp;             // [FW][N]
+    double* CONV = sm + P.off_conv;             // [ncon][NDP]
+    int* INV = reinterpret_cast<int*>(sm + P.off_inv);   // [nb][NDP]
+
+    // ------------------------------------------------------------------ prologue
+    for (int i = tid; i < P.smem_doubles; i += FW * 32) sm[i] = 0.0;
+    __syncthreads();
+    for (int b = 0; b < nb; ++b) {
+        const FusedBath& B = P.b[b];
+        for (int i = tid; i < NDP; i += FW * 32) INV[b * NDP + i] = i < nd ? B.inv_g[i] : -1;
+        int* CIDS = reinterpret_cast<int*>(sm + B.off_cids);
+        int* INREM = reinterpret_cast<int*>(sm + B.off_inrem);
+        for (int i = tid; i < B.ncp; i += FW * 32) {
+            CIDS[i] = B.cids_g[i < B.nc ? i : B.nc - 1];
+            INREM[i] = (P.rem >= 0 && i < B.nc) ? (P.b[P.rem].inv_g[B.cids_g[i]] >= 0) : 0;
+        }
+        if (b != P.rem) {
+            double* HD = sm + B.off_hd;
+            for (int e = tid; e < B.nc * B.nc; e += FW * 32)
+                HD[(e / B.nc) * B.ldk + e % B.nc] = B.head_g[(size_t)(e / B.nc) * B.lda + e % B.nc];
+        }
+        if (B.nonlocal) {
+            double* KIN = sm + B.off_kin;
+            for (int e = tid; e < B.ntap * B.nc * B.nc; e += FW * 32) {
+                const int k = e / (B.nc * B.nc), r = (e / B.nc) % B.nc, cc = e % B.nc;
+                KIN[(k * B.ncp + r) * B.ldk + cc] = B.kin_g[e];
+            }
+        }
+    }
+    for (int e = tid; e < P.ncon * nd; e += FW * 32) CONV[(e / nd) * NDP + e % nd] = P.con[e];
+
+    double aD[MAXKS], aM[MAXKS], aQ[MAXKS];
+#pragma unroll
+    for (int k = 0; k < MAXKS; ++k) {
+        const bool ok = k < ks && row < nd;
+        aD[k] = ok ? P.dyn[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
+        aM[k] = ok ? P.mp[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
+        aQ[k] = (HASQ && ok) ? P.aqT[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
+    }
+    // state of this CTA's trajectories
+    int cur = 0;
+    if (row < nd) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int n = 8 * j + 2 * lc;
+            *reinterpret_cast<double2*>(&XPb[0][row * LD + n]) =
+                *reinterpret_cast<const double2*>(&P.p[(size_t)row * ldb + col0 + n]);
+            *reinterpret_cast<double2*>(&XQ[row * LD + n]) =
+                *reinterpret_cast<const double2*>(&P.q[(size_t)row * ldb + col0 + n]);
+        }
+    }
+    // noise minus tail at time t0 for every bath
+    {
+        const int tn0 = (int)(P.t0 % P.nmd);
+        for (int b = 0; b < nb; ++b) {
+            const FusedBath& B = P.b[b];
+            double* NB = sm + B.off_nb;                 // buffer 0
+            for (int e = tid; e < B.nc * N; e += FW * 32) {
+                const int r = e / N, n = e % N;
+                double v = B.noise[((size_t)tn0 * B.nc + r) * ldb + col0 + n];
+                if (B.nonlocal) v -= B.tail_cur[(size_t)r * ldb + col0 + n];
+                NB[r * LD + n] = v;
+            }
+        }
+    }
+    __syncthreads();
+
+    double fpot[NT][2], uq[NT][2];          // potential force / q-coupled bath force at q(t), own rows
+    zero_acc<NT>(fpot);
+    zero_acc<NT>(uq);
+    if (!HASCON) {
+        if (HASQ) matvec2<NT>(aD, aQ, ks, XQ, LD, fpot, uq, lr, lc);
+        else matvec1<NT>(aD, ks, XQ, LD, fpot, lr, lc);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) { fpot[j][0] = -fpot[j][0]; fpot[j][1] = -fpot[j][1]; }
+    } else {
+        // constrained runs carry md.potforce's cache (md.py:456-457) across launches
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int n = 8 * j + 2 * lc;
+            if (P.carry_valid && row < nd) {
+                fpot[j][0] = P.fpotn[(size_t)row * ldb + col0 + n];
+                fpot[j][1] = P.fpotn[(size_t)row * ldb + col0 + n + 1];
+            }
+        }
+        for (int e = tid; e < FW * N; e += FW * 32)
+            MAXP[e] = (P.carry_valid && P.samef[col0 + e % N]) ? 0.0 : 1.0;
+        __syncthreads();
+    }
+    int nbuf = 0;                           // NB buffer holding noise-minus-tail at time t
+
+    // ------------------------------------------------------------------ time loop
+    for (int s = 0; s < P.nsteps; ++s) {
+        const long long t = P.t0 + s;
+        const int tn = (int)(t % P.nmd), tn1 = (int)((t + 1) % P.nmd);
+        double* XPc = XPb[cur];
+        double* XPn = XPb[cur ^ 1];
+
+        // ============ round A: first force evaluation at time t, head p(t) ============
+        double hA[NT][2];
+        zero_acc<NT>(hA);
+        matvec1<NT>(aM, ks, XPc, LD, hA, lr, lc);
+        if (HASCON) {
+            double fc[NT][2], uc[NT][2];
+            zero_acc<NT>(fc);
+            zero_acc<NT>(uc);
+            if (HASQ) matvec2<NT>(aD, aQ, ks, XQ, LD, fc, uc, lr, lc);
+            else matvec1<NT>(aD, ks, XQ, LD, fc, lr, lc);
+            __syncthreads();        // every warp has read q(t) from XQ before any warp overwrites it with q'
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int n = 8 * j + 2 * lc + e;
+                    double m = 0.0;
+#pragma unroll
+                    for (int ww = 0; ww < FW; ++ww) m = fmax(m, MAXP[ww * N + n]);
+                    if (!(m < 10e-10)) fpot[j][e] = -fc[j][e];      // md.sameq miss -> fresh force
+                    uq[j][e] = uc[j][e];
+                }
+        }
+        // ---- elementwise part on the rows this thread owns
+        double cpart[PYMD_MAX_BATHS];
+#pragma unroll
+        for (int b = 0; b < PYMD_MAX_BATHS; ++b) cpart[b] = 0.0;
+        double epart = 0.0;
+        // per-column partial sums are accumulated per n-tile below
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int n = 8 * j + 2 * lc;
+            double ce[PYMD_MAX_BATHS][2];
+#pragma unroll
+            for (int b = 0; b < PYMD_MAX_BATHS; ++b) ce[b][0] = ce[b][1] = 0.0;
+            double ee[2] = {0.0, 0.0};
+            if (row < nd) {
+                const double2 pv = *reinterpret_cast<const double2*>(&XPc[row * LD + n]);
+                const double2 qv = *reinterpret_cast<const double2*>(&XQ[row * LD + n]);
+                double f0 = fpot[j][0] + uq[j][0] - hA[j][0];
+                double f1 = fpot[j][1] + uq[j][1] - hA[j][1];
+#pragma unroll
+                for (int b = 0; b < PYMD_MAX_BATHS; ++b) {
+                    if (b >= nb) break;
+                    const int ip = INV[b * NDP + row];
+                    if (ip < 0) continue;
+                    const FusedBath& B = P.b[b];
+                    const double2 nv = *reinterpret_cast<const double2*>(&sm[B.off_nb + nbuf * B.ncp * LD + ip * LD + n]);
+                    f0 += nv.x;
+                    f1 += nv.y;
+                    double c0 = nv.x, c1 = nv.y;
+                    if (HASQ && b == P.aq) { c0 += uq[j][0]; c1 += uq[j][1]; }
+                    if (b == P.rem) { c0 -= hA[j][0]; c1 -= hA[j][1]; }
+                    ce[b][0] = pv.x * c0;
+                    ce[b][1] = pv.y * c1;
+                    if (B.nonlocal) {
+                        *reinterpret_cast<double2*>(&sm[B.off_hist + (s * B.ncp + ip) * LD + n]) = pv;
+                        const int slot = (B.slot0 + s) % B.R;
+                        *reinterpret_cast<double2*>(&B.ring[((size_t)slot * B.ncp + ip) * ldb + col0 + n]) = pv;
+                    }
+                }
+                ee[0] = pv.x * pv.x;
+                ee[1] = pv.y * pv.y;
+                const double2 ph = make_double2(pv.x + f0 * dt / 2.0, pv.y + f1 * dt / 2.0);
+                const double2 qn = make_double2(qv.x + pv.x * dt + f0 * dt2 / 2.0, qv.y + pv.y * dt + f1 * dt2 / 2.0);
+                *reinterpret_cast<double2*>(&XPn[row * LD + n]) = ph;
+                *reinterpret_cast<double2*>(&PH[row * LD + n]) = ph;
+                *reinterpret_cast<double2*>(&XQ[row * LD + n]) = qn;
+                if (P.ps) *reinterpret_cast<double2*>(&P.ps[((size_t)tn * nd + row) * ldb + col0 + n]) = pv;
+                if (P.qs) *reinterpret_cast<double2*>(&P.qs[((size_t)tn * nd + row) * ldb + col0 + n]) = qv;
+            }
+            // column sums over this warp's 8 rows -> per-warp slots
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double es = colsum8(ee[e]);
+                if (lr == 0) CURP[(nb * FW + w) * N + n + e] = es;
+            }
+#pragma unroll
+            for (int b = 0; b < PYMD_MAX_BATHS; ++b) {
+                if (b >= nb) break;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double cs = colsum8(ce[b][e]);
+                    if (lr == 0) CURP[(b * FW + w) * N + n + e] = cs;
+                }
+            }
+        }
+        (void)cpart; (void)epart;
+        __syncwarp();
+        // ---- work items: heads of the small baths (scalars p.g_b only) ...
+        {
+            int item = 0;
+            for (int b = 0; b < nb; ++b) {
+                if (b == P.rem) continue;
+                const FusedBath& B = P.b[b];
+                const int mts = B.ncp / 8;
+                const int* CIDS = reinterpret_cast<const int*>(sm + B.off_cids);
+                const int* INREM = reinterpret_cast<const int*>(sm + B.off_inrem);
+                const double* HD = sm + B.off_hd;
+                for (int mt = 0; mt < mts; ++mt)
+                    for (int j = 0; j < NT; ++j, ++item) {
+                        if (item % FW != w) continue;
+                        double g0 = 0.0, g1 = 0.0;
+                        for (int kk = 0; kk < B.ncp; kk += 4)
+                            dmma884(g0, g1, HD[(mt * 8 + lr) * B.ldk + kk + lc], XPc[CIDS[kk + lc] * LD + 8 * j + lr]);
+                        const int rr = mt * 8 + lr, n = 8 * j + 2 * lc;
+                        double s0 = 0.0, s1 = 0.0, r0 = 0.0, r1 = 0.0;
+                        if (rr < B.nc) {
+                            const double2 pv = *reinterpret_cast<const double2*>(&XPc[CIDS[rr] * LD + n]);
+                            s0 = pv.x * g0;
+                            s1 = pv.y * g1;
+                            if (INREM[rr]) { r0 = s0; r1 = s1; }
+                        }
+                        s0 = colsum8(s0); s1 = colsum8(s1);
+                        r0 = colsum8(r0); r1 = colsum8(r1);
+                        if (lr == 0) {
+                            CURP[(b * FW + w) * N + n] -= s0;
+                            CURP[(b * FW + w) * N + n + 1] -= s1;
+                            if (P.rem >= 0) {
+                                CURP[(P.rem * FW + w) * N + n] += r0;
+                                CURP[(P.rem * FW + w) * N + n + 1] += r1;
+                            }
+                        }
+                        __syncwarp();
+                    }
+            }
+            // ... and noise minus memory-kernel tail at time t+1 for every bath
+            item = 0;
+            for (int b = 0; b < nb; ++b) {
+                const FusedBath& B = P.b[b];
+                const int mts = B.ncp / 8;
+                const int* CIDS = reinterpret_cast<const int*>(sm + B.off_cids);
+                for (int mt = 0; mt < mts; ++mt)
+                    for (int j = 0; j < NT; ++j, ++item) {
+                        if (item % FW != w) continue;
+                        const int rr = mt * 8 + lr, n = 8 * j + 2 * lc;
+                        double2 xi = make_double2(0.0, 0.0), pt = make_double2(0.0, 0.0);
+                        if (rr < B.nc) {
+                            xi = *reinterpret_cast<const double2*>(&B.noise[((size_t)tn1 * B.nc + rr) * ldb + col0 + n]);
+                            if (B.nonlocal)
+                                pt = *reinterpret_cast<const double2*>(&B.P[((size_t)s * B.nc + rr) * ldb + col0 + n]);
+                        }
+                        double a0 = 0.0, a1 = 0.0;
+                        if (B.nonlocal) {
+                            const double* KIN = sm + B.off_kin;
+                            const int ntap = min(s + 1, B.ntap);
+                            for (int k = 1; k <= ntap; ++k) {
+                                const double* A = KIN + ((k - 1) * B.ncp + mt * 8 + lr) * B.ldk + lc;
+                                if (k == 1) {
+                                    for (int kk = 0; kk < B.ncp; kk += 4)
+                                        dmma884(a0, a1, A[kk], XPc[CIDS[kk + lc] * LD + 8 * j + lr]);
+                                } else {
+                                    const double* H = sm + B.off_hist + ((s + 1 - k) * B.ncp + lc) * LD + 8 * j + lr;
+                                    for (int kk = 0; kk < B.ncp; kk += 4) dmma884(a0, a1, A[kk], H[kk * LD]);
+                                }
+                            }
+                        }
+                        const double t0v = pt.x + a0, t1v = pt.y + a1;
+                        if (rr < B.nc) {
+                            *reinterpret_cast<double2*>(&sm[B.off_nb + (nbuf ^ 1) * B.ncp * LD + rr * LD + n]) =
+                                make_double2(xi.x - t0v, xi.y - t1v);
+                            if (B.nonlocal && s == P.nsteps - 1)
+                                *reinterpret_cast<double2*>(&B.tail_cur[(size_t)rr * ldb + col0 + n]) = make_double2(t0v, t1v);
+                        }
+                    }
+            }
+        }
+        __syncthreads();                                                        // ---- S2
+        // currents and kinetic energy of time t: fixed-order sum of the per-warp slots
+        for (int e = tid; e < (nb + 1) * N; e += FW * 32) {
+            const int b = e / N, n = e % N;
+            double sum = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < FW; ++ww) sum += CURP[(b * FW + ww) * N + n];
+            if (b < nb) P.b[b].cur[(size_t)tn * ldb + col0 + n] = sum;
+            else P.etot[(size_t)tn * ldb + col0 + n] = 0.5 * sum;
+        }
+        nbuf ^= 1;
+        cur ^= 1;
+
+        // ============ round B: second evaluation at time t+1, head p(t+1/2) ============
+        XPc = XPb[cur];
+        XPn = XPb[cur ^ 1];
+        {
+            double aDq[NT][2], aQq[NT][2], hB[NT][2];
+            zero_acc<NT>(aDq);
+            zero_acc<NT>(aQq);
+            zero_acc<NT>(hB);
+            if (HASQ) matvec2<NT>(aD, aQ, ks, XQ, LD, aDq, aQq, lr, lc);
+            else matvec1<NT>(aD, ks, XQ, LD, aDq, lr, lc);
+            matvec1<NT>(aM, ks, XPc, LD, hB, lr, lc);
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int n = 8 * j + 2 * lc;
+                fpot[j][0] = -aDq[j][0];
+                fpot[j][1] = -aDq[j][1];
+                if (!HASCON) { uq[j][0] = aQq[j][0]; uq[j][1] = aQq[j][1]; }
+                if (row < nd) {
+                    double f0 = fpot[j][0] + aQq[j][0], f1 = fpot[j][1] + aQq[j][1];
+#pragma unroll
+                    for (int b = 0; b < PYMD_MAX_BATHS; ++b) {
+                        if (b >= nb) break;
+                        const int ip = INV[b * NDP + row];
+                        if (ip < 0) continue;
+                        const double2 nv = *reinterpret_cast<const double2*>(&sm[P.b[b].off_nb + nbuf * P.b[b].ncp * LD + ip * LD + n]);
+                        f0 += nv.x;
+                        f1 += nv.y;
+                    }
+                    const double2 ph = *reinterpret_cast<const double2*>(&PH[row * LD + n]);
+                    *reinterpret_cast<double2*>(&FB[row * LD + n]) = make_double2(f0, f1);
+                    *reinterpret_cast<double2*>(&XPn[row * LD + n]) =
+                        make_double2(ph.x + dt * (f0 - hB[j][0]) / 2.0, ph.y + dt * (f1 - hB[j][1]) / 2.0);
+                }
+            }
+        }
+        __syncthreads();                                                        // ---- S3
+        cur ^= 1;
+
+        // ============ round C: third evaluation, head p1 -> p(t+1), constraints ============
+        XPc = XPb[cur];
+        XPn = XPb[cur ^ 1];
+        {
+            double hC[NT][2];
+            zero_acc<NT>(hC);
+            matvec1<NT>(aM, ks, XPc, LD, hC, lr, lc);
+            double pn[NT][2];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int n = 8 * j + 2 * lc;
+                pn[j][0] = pn[j][1] = 0.0;
+                if (row < nd) {
+                    const double2 ph = *reinterpret_cast<const double2*>(&PH[row * LD + n]);
+                    const double2 fb = *reinterpret_cast<const double2*>(&FB[row * LD + n]);
+                    pn[j][0] = ph.x + dt * (fb.x - hC[j][0]) / 2.0;
+                    pn[j][1] = ph.y + dt * (fb.y - hC[j][1]) / 2.0;
+                }
+            }
+            if (!HASCON) {
+                if (row < nd) {
+#pragma unroll
+                    for (int j = 0; j < NT; ++j)
+                        *reinterpret_cast<double2*>(&XPn[row * LD + 8 * j + 2 * lc]) = make_double2(pn[j][0], pn[j][1]);
+                }
+            } else {
+                // md.ApplyConstraint (md.py:739-762): all dots with the unprojected vectors
+                for (int c = 0; c < P.ncon; ++c) {
+                    const double cv = row < nd ? CONV[c * NDP + row] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const int n = 8 * j + 2 * lc;
+                        const double2 qv = *reinterpret_cast<const double2*>(&XQ[row * LD + n]);
+                        const double d0 = colsum8(pn[j][0] * cv), d1 = colsum8(pn[j][1] * cv);
+                        const double e0 = colsum8(qv.x * cv), e1 = colsum8(qv.y * cv);
+                        if (lr == 0) {
+                            CONP[((c * 2 + 0) * FW + w) * N + n] = d0;
+                            CONP[((c * 2 + 0) * FW + w) * N + n + 1] = d1;
+                            CONP[((c * 2 + 1) * FW + w) * N + n] = e0;
+                            CONP[((c * 2 + 1) * FW + w) * N + n + 1] = e1;
+                        }
+                    }
+                }
+                __syncthreads();                                                // ---- S4
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const int n = 8 * j + 2 * lc;
+                    const double2 q0 = *reinterpret_cast<const double2*>(&XQ[row * LD + n]);
+                    double p0 = pn[j][0], p1 = pn[j][1], qa = q0.x, qb = q0.y;
+                    for (int c = 0; c < P.ncon; ++c) {
+                        const double cv = row < nd ? CONV[c * NDP + row] : 0.0;
+                        double dp0 = 0.0, dp1 = 0.0, dq0 = 0.0, dq1 = 0.0;
+#pragma unroll
+                        for (int ww = 0; ww < FW; ++ww) {
+                            dp0 += CONP[((c * 2 + 0) * FW + ww) * N + n];
+                            dp1 += CONP[((c * 2 + 0) * FW + ww) * N + n + 1];
+                            dq0 += CONP[((c * 2 + 1) * FW + ww) * N + n];
+                            dq1 += CONP[((c * 2 + 1) * FW + ww) * N + n + 1];
+                        }
+                        p0 -= dp0 * cv; p1 -= dp1 * cv;
+                        qa -= dq0 * cv; qb -= dq1 * cv;
+                    }
+                    const double m0 = colmax8(row < nd ? fabs(qa - q0.x) : 0.0);
+                    const double m1 = colmax8(row < nd ? fabs(qb - q0.y) : 0.0);
+                    if (lr == 0) { MAXP[w * N + n] = m0; MAXP[w * N + n + 1] = m1; }
+                    if (row < nd) {
+                        *reinterpret_cast<double2*>(&XPn[row * LD + n]) = make_double2(p0, p1);
+                        *reinterpret_cast<double2*>(&XQ[row * LD + n]) = make_double2(qa, qb);
+                    }
+                }
+            }
+        }
+        __syncthreads();                                                        // ---- S1
+        cur ^= 1;
+    }
+
+    // ------------------------------------------------------------------ epilogue
+    if (row < nd) {
+        const double* XPc = XPb[cur];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int n = 8 * j + 2 * lc;
+            *reinterpret_cast<double2*>(&P.p[(size_t)row * ldb + col0 + n]) = *reinterpret_cast<const double2*>(&XPc[row * LD + n]);
+            *reinterpret_cast<double2*>(&P.q[(size_t)row * ldb + col0 + n]) = *reinterpret_cast<const double2*>(&XQ[row * LD + n]);
+            *reinterpret_cast<double2*>(&P.fpotn[(size_t)row * ldb + col0 + n]) = make_double2(fpot[j][0], fpot[j][1]);
+        }
+    }
+    for (int n = tid; n < N; n += FW * 32) {
+        int same = 1;
+        if (HASCON) {
+            double m = 0.0;
+            for (int ww = 0; ww < FW; ++ww) m = fmax(m, MAXP[ww * N + n]);
+            same = m < 10e-10;
+        }
+        P.samef[col0 + n] = same;
+    }
+}
+
+struct Layout {
+    FusedParams fp;
+    size_t smem_bytes;
+};
+
+// shared-memory plan for NT n-tiles; returns bytes
+size_t plan(const pymd_ctx* c, int NT, FusedParams& fp) {
+    const int N = 8 * NT, LD = N + 4;
+    int off = 0;
+    auto take = [&](int n) { int o = off; off += (n + 1) / 2 * 2; return o; };
+    fp.off_xp0 = take(NDP * LD);
+    fp.off_xp1 = take(NDP * LD);
+    fp.off_xq = take(NDP * LD);
+    fp.off_ph = take(NDP * LD);
+    fp.off_fb = take(NDP * LD);
+    fp.off_curp = take((c->nbath + 1) * FW * N);
+    fp.off_conp = take(std::max(1, c->ncon) * 2 * FW * N);
+    fp.off_maxp = take(FW * N);
+    fp.off_conv = take(std::max(1, c->ncon) * NDP);
+    fp.off_inv = take((c->nbath * NDP + 1) / 2 + 1);
+    for (int b = 0; b < c->nbath; ++b) {
+        const BathHost& H = c->bath[b];
+        FusedBath& B = fp.b[b];
+        B.nc = H.nc; B.ncp = H.ncp; B.ml = H.ml; B.nonlocal = H.ml > 1;
+        B.ldk = H.ncp + 4;
+        B.ntap = H.ml > 1 ? std::min(FT, H.ml - 1) : 0;
+        B.off_cids = take(H.ncp / 2 + 1);
+        B.off_inrem = take(H.ncp / 2 + 1);
+        B.off_hd = (b != fp.rem) ? take(H.ncp * B.ldk) : 0;
+        B.off_nb = take(2 * H.ncp * LD);
+        if (H.ml > 1) {
+            B.off_kin = take(B.ntap * H.ncp * B.ldk);
+            B.off_hist = take(FT * H.ncp * LD);
+        } else {
+            B.off_kin = B.off_hist = 0;
+        }
+    }
+    fp.smem_doubles = off;
+    return (size_t)off * sizeof(double);
+}
+
+int pick_nt(const pymd_ctx* c, FusedParams& fp) {
+    // largest trajectory tile that fits in 227 KB and divides the ensemble
+    for (int NT : {4, 2, 1}) {
+        if (c->ldb % (8 * NT)) continue;
+        if (plan(c, NT, fp) <= 227 * 1024) return NT;
+    }
+    return 0;
+}
+
+void choose_roles(const pymd_ctx* c, FusedParams& fp) {
+    fp.rem = -1;
+    fp.aq = -1;
+    int best = -1;
+    for (int b = 0; b < c->nbath; ++b) {
+        if (c->bath[b].nc > best) { best = c->bath[b].nc; fp.rem = b; }
+        if (c->bath[b].has_aq) fp.aq = b;
+    }
+}
+
+template <int NT>
+int launch_nt(const FusedParams& fp, size_t smem, int grid, bool hasq, bool hascon, cudaStream_t st) {
+#define PYMD_FUSED_CASE(Q, C)                                                                              \
+    {                                                                                                      \
+        static bool cfg = false;                                                                           \
+        if (!cfg) {                                                                                        \
+            PYMD_CUDA_CHECK(cudaFuncSetAttribute(fused_kernel<NT, Q, C>,                                   \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+            cfg = true;                                                                                    \
+        }                                                                                                  \
+        fused_kernel<NT, Q, C><<<grid, FW * 32, smem, st>>>(fp);                                           \
+    }
+    if (hasq && hascon) PYMD_FUSED_CASE(true, true)
+    else if (hasq) PYMD_FUSED_CASE(true, false)
+    else if (hascon) PYMD_FUSED_CASE(false, true)
+    else PYMD_FUSED_CASE(false, false)
+#undef PYMD_FUSED_CASE
+    PYMD_CUDA_CHECK(cudaGetLastError());
+    return PYMD_OK;
+}
+
+}  // namespace
+
+int fused_supported(const pymd_ctx* c) {
+    if (c->nd > NDP || c->ncon > 4) return 0;
+    int naq = 0;
+    for (int b = 0; b < c->nbath; ++b) {
+        naq += c->bath[b].has_aq;
+        if (c->sd.b[b].fhis) return 0;
+        if (c->bath[b].ncp > NDP) return 0;
+    }
+    if (naq > 1) return 0;
+    FusedParams fp{};
+    choose_roles(c, fp);
+    return pick_nt(c, fp) > 0;
+}
+
+int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
+    StepDev& d = c->sd;
+    FusedParams fp{};
+    choose_roles(c, fp);
+    const int NT = pick_nt(c, fp);
+    PYMD_REQUIRE(NT > 0, "fused: configuration does not fit in shared memory");
+    const size_t smem = plan(c, NT, fp);
+    fp.nd = c->nd; fp.ks = (c->nd + 3) / 4; fp.ldb = c->ldb; fp.ldn = c->ldn; fp.nbath = c->nbath;
+    fp.nmd = c->nmd; fp.ncon = c->ncon; fp.dt = c->dt;
+    fp.p = d.p; fp.q = d.q; fp.ps = d.ps; fp.qs = d.qs; fp.etot = d.etot; fp.fpotn = d.fpotn; fp.samef = d.samef;
+    fp.dyn = c->d_dyn; fp.mp = c->d_mp; fp.con = c->d_con;
+    // q-coupled operator scattered to nd x nd (built once)
+    bool hasq = fp.aq >= 0;
+    if (hasq && !c->d_aqT) {
+        const BathHost& H = c->bath[fp.aq];
+        std::vector<double> aqT((size_t)c->nd * c->ldn, 0.0);
+        for (int i = 0; i < H.nc; ++i)
+            for (int j = 0; j < H.nc; ++j) aqT[(size_t)H.cids[i] * c->ldn + H.cids[j]] = H.aq[(size_t)i * H.nc + j];
+        PYMD_CUDA_CHECK(cudaMalloc(&c->d_aqT, aqT.size() * sizeof(double)));
+        PYMD_CUDA_CHECK(cudaMemcpy(c->d_aqT, aqT.data(), aqT.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    fp.aqT = c->d_aqT;
+    for (int b = 0; b < c->nbath; ++b) {
+        BathHost& H = c->bath[b];
+        FusedBath& B = fp.b[b];
+        B.noise = d.b[b].noise; B.cur = d.b[b].cur; B.ring = d.b[b].ring; B.R = H.R > 0 ? H.R : 1;
+        B.tail_cur = d.b[b].tail_cur; B.P = d.b[b].tail_next;
+        B.head_g = H.d_head; B.lda = H.lda; B.kin_g = H.d_kintra; B.cids_g = H.d_cids; B.inv_g = H.d_inv;
+    }
+    int rc;
+    if (!c->tail_valid) {
+        for (int b = 0; b < c->nbath; ++b)
+            if (c->bath[b].ml > 1 && (rc = launch_tail(c, b, 1, 1, d.b[b].tail_cur, st))) return rc;
+        c->tail_valid = true;
+    }
+    const int grid = c->ldb / (8 * NT);
+    for (int done = 0; done < nsteps; done += FT) {
+        const int ns = std::min(FT, nsteps - done);
+        for (int b = 0; b < c->nbath; ++b) {
+            BathHost& H = c->bath[b];
+            if (H.ml > 1) {
+                // pre-block part: history older than this block, read once for ns steps
+                if ((rc = launch_tail(c, b, ns, 2, d.b[b].tail_next, st))) return rc;
+                fp.b[b].slot0 = (int)(H.hcount % H.R);
+            }
+        }
+        fp.t0 = t0 + done;
+        fp.nsteps = ns;
+        fp.carry_valid = c->fpot_valid ? 1 : 0;
+        switch (NT) {
+            case 4: rc = launch_nt<4>(fp, smem, grid, hasq, c->ncon > 0, st); break;
+            case 2: rc = launch_nt<2>(fp, smem, grid, hasq, c->ncon > 0, st); break;
+            default: rc = launch_nt<1>(fp, smem, grid, hasq, c->ncon > 0, st);
+        }
+        if (rc) return rc;
+        c->launches++;
+        for (int b = 0; b < c->nbath; ++b)
+            if (c->bath[b].ml > 1) c->bath[b].hcount += ns;
+        c->fpot_valid = true;
+        c->fpotc_valid = false;
+    }
+    return PYMD_OK;
+}
+
 }  // namespace pymd

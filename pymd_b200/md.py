@@ -272,23 +272,22 @@ class md(object):
             self._ps.zero_()
             self._qs.zero_()
 
-    def _host(self, t, lead):
-        """device [..., ldb] -> host; trajectory axis first for an ensemble, dropped for batch 1."""
+    def _host(self, t, lead=True):
+        """device [..., ldb] -> host array in the reference's shape, with a trailing ensemble
+        axis when batch > 1."""
         a = t[..., :self.batch].cpu().numpy()
-        if self.batch == 1:
-            return a[..., 0]
-        return N.moveaxis(a, -1, 0)
+        return a[..., 0] if self.batch == 1 else a
 
     def _upload(self, dst, value):
+        """host array in the reference's shape (broadcast over the ensemble) or with a trailing
+        ensemble axis -> device [..., ldb]."""
         import torch
         a = N.asarray(value, dtype=N.float64)
         want = tuple(dst.shape[:-1])
         if a.shape == want:
             a = N.broadcast_to(a[..., None], want + (self.batch,))
-        elif a.shape == (self.batch,) + want:
-            a = N.moveaxis(a, 0, -1)
-        else:
-            raise ValueError("expected shape %s or %s" % (want, (self.batch,) + want))
+        elif a.shape != want + (self.batch,):
+            raise ValueError("expected shape %s or %s, got %s" % (want, want + (self.batch,), a.shape))
         dst.zero_()
         dst[..., :self.batch] = torch.as_tensor(N.array(a, dtype=N.float64, order='C'), dtype=torch.float64).to(dst.device)
 
@@ -334,9 +333,9 @@ class md(object):
             if b not in self._fhis:
                 out.append(None)
                 continue
-            loc = self._host(self._fhis[b], True)
-            full = N.zeros(loc.shape[:-1] + (self.nph,))
-            full[..., bath.cids] = loc
+            loc = self._host(self._fhis[b])
+            full = N.zeros((self.nmd, self.nph) + loc.shape[2:])
+            full[:, bath.cids] = loc
             out.append(full)
         return out
 
@@ -351,27 +350,26 @@ class md(object):
         return self._history()
 
     def _history(self):
-        import torch
         self._ensure()
-        out = N.zeros(((self.batch,) if self.batch > 1 else ()) + (self.ml, self.nph))
+        out = N.zeros((self.ml, self.nph) + ((self.batch,) if self.batch > 1 else ()))
         for b, bath in enumerate(self.baths):
             if bath.ml <= 1:
                 continue
             buf = self._zeros(bath.ml, bath.nc, self.ldb)
             _lib.call("pymd_history_get", self._ctx, b, buf.data_ptr(), int(bath.ml), _lib.stream_ptr())
-            out[..., :bath.ml, bath.cids] = self._host(buf, True)
+            out[:bath.ml, bath.cids] = self._host(buf)
         return out
 
     def set_history(self, phis):
-        """Restore the velocity history (resume path, md.py:550-551/576-582)."""
-        import torch
+        """Restore the velocity history (resume path, md.py:550-551/576-582); phis has the
+        reference's shape (ml, nph) [+ trailing ensemble axis]."""
         self._ensure()
         phis = N.asarray(phis, dtype=N.float64)
         for b, bath in enumerate(self.baths):
             if bath.ml <= 1:
                 continue
             buf = self._zeros(bath.ml, bath.nc, self.ldb)
-            self._upload(buf, phis[..., :bath.ml, :][..., bath.cids])
+            self._upload(buf, phis[:bath.ml][:, bath.cids])
             _lib.call("pymd_history_set", self._ctx, b, buf.data_ptr(), int(bath.ml), _lib.stream_ptr())
 
     # ------------------------------------------------------------------ the reference's methods
@@ -383,7 +381,7 @@ class md(object):
 
     def initialise(self, r=None):
         """Quantum initial displacements/velocities from the eigenmodes (md.py:253-290).
-        ``r``: optional uniforms in [0,1), shape (nph,) or (nph, batch) / (batch, nph); by
+        ``r``: optional uniforms in [0,1), shape (nph,) or (nph, batch); by
         default one Philox stream per trajectory."""
         import torch
         self._ensure()
@@ -408,10 +406,8 @@ class md(object):
             ra = N.asarray(r, dtype=N.float64)
             if ra.shape == (nd,):
                 ra = N.broadcast_to(ra[:, None], (nd, self.batch))
-            elif ra.shape == (self.batch, nd):
-                ra = ra.T
             elif ra.shape != (nd, self.batch):
-                raise ValueError("r must have shape (nph,), (nph, batch) or (batch, nph)")
+                raise ValueError("r must have shape (nph,) or (nph, batch)")
             rdev[:, :self.batch] = torch.as_tensor(N.ascontiguousarray(ra)).to(rdev.device)
         Um = N.ascontiguousarray(self.U, dtype=N.float64)
         _lib.call("pymd_init_state", self._ctx, Um.ctypes.data, hw.ctypes.data, am.ctypes.data,
@@ -450,7 +446,7 @@ class md(object):
     def force(self, t, p, q, id=0):
         """Potential + bath forces for ONE host state (md.py:360-383), using the current device
         history; diagnostic helper (the time loop never calls it)."""
-        phis = self._history() if self.batch == 1 else self._history()[0]
+        phis = self._history() if self.batch == 1 else self._history()[..., 0]
         qhis = N.zeros_like(phis)
         if id == 0:
             phis[0], qhis[0] = p, q
@@ -572,7 +568,7 @@ class md(object):
             d = N.load(fnm)
             self.p, self.q = d["p"], d["q"]
             self.t = int(d["t"][0])
-            if d["phis"].shape[-2:] == (self.ml, self.nph):
+            if d["phis"].shape[:2] == (self.ml, self.nph):
                 self.set_history(d["phis"])
         return None
 

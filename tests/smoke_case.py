@@ -32,8 +32,8 @@ def run(verbose=True):
     for n in range(B):
         om, recs = T.run_oracle(c, j, m, xi, r, n, c["nmd"])
         rec = recs[0]
-        worst = max(worst, T.relerr(m.ps[n], rec["ps"]), T.relerr(m.qs[n], rec["qs"]),
-                    T.relerr(m.etot[n], rec["etot"]))
+        worst = max(worst, T.relerr(m.ps[..., n], rec["ps"]), T.relerr(m.qs[..., n], rec["qs"]),
+                    T.relerr(m.etot[..., n], rec["etot"]))
         for b in range(len(m.baths)):
             worst = max(worst, T.relerr(m.baths[b].cur[:, n], rec["cur"][b]))
         om.GetPower()

@@ -176,11 +176,11 @@ def test_initial_condition_matches_oracle(cuda, case):
     for n in range(B):
         om = T.oracle_md(c, j)
         om.initialise(r=r[:, n])
-        assert T.relerr(m.p[n], om.p) < 1e-13 and T.relerr(m.q[n], om.q) < 1e-13
+        assert T.relerr(m.p[:, n], om.p) < 1e-13 and T.relerr(m.q[:, n], om.q) < 1e-13
     m2, _ = T.device_md(c, 64, seed=42)
     m2.initialise()
     p = m2.p
-    assert np.isfinite(p).all() and np.abs(p[0] - p[1]).max() > 0      # distinct trajectories
+    assert np.isfinite(p).all() and np.abs(p[:, 0] - p[:, 1]).max() > 0      # distinct trajectories
     m3, _ = T.device_md(c, 32, seed=42, traj0=32)
     m3.initialise()
-    assert np.array_equal(m3.p, p[32:64])                             # shard invariance
+    assert np.array_equal(m3.p, p[:, 32:64])                             # shard invariance

@@ -18,12 +18,12 @@ TOL = 1e-11
 
 def compare(m, rec, n, tol=TOL):
     B = m.batch
-    ps = m.ps if B > 1 else m.ps[None]
-    qs = m.qs if B > 1 else m.qs[None]
-    et = m.etot if B > 1 else m.etot[None]
-    assert T.relerr(ps[n], rec["ps"]) < tol
-    assert T.relerr(qs[n], rec["qs"]) < tol
-    assert T.relerr(et[n], rec["etot"]) < tol
+    ps = m.ps if B > 1 else m.ps[..., None]
+    qs = m.qs if B > 1 else m.qs[..., None]
+    et = m.etot if B > 1 else m.etot[..., None]
+    assert T.relerr(ps[..., n], rec["ps"]) < tol
+    assert T.relerr(qs[..., n], rec["qs"]) < tol
+    assert T.relerr(et[..., n], rec["etot"]) < tol
     for b, bath in enumerate(m.baths):
         cur = bath.cur if B > 1 else bath.cur[:, None]
         scale = max(np.abs(rec["cur"][b]).max(), 1e-300)
@@ -31,7 +31,9 @@ def compare(m, rec, n, tol=TOL):
 
 
 @pytest.mark.parametrize("case,batch,mode", [("ph2", 1, 1), ("ph2", 3, 1), ("eph", 3, 1), ("chain39", 2, 1),
-                                               ("aubz", 2, 1), ("ragged", 33, 1)])
+                                               ("aubz", 2, 1), ("ragged", 33, 1),
+                                               ("ph2", 1, 2), ("ph2", 3, 2), ("eph", 3, 2), ("chain39", 2, 2),
+                                               ("aubz", 2, 2), ("ragged", 33, 2), ("aubz", 40, 0)])
 def test_short_horizon_parity(cuda, case, batch, mode):
     c = T.CASES[case]
     m, j = T.device_md(c, batch, step_mode=mode)
@@ -48,13 +50,13 @@ def test_short_horizon_parity(cuda, case, batch, mode):
     for n in sorted(set([0, batch - 1, batch // 2])):
         om, recs = T.run_oracle(c, j, m, xi, r, n, c["nmd"])
         compare(m, recs[0], n)
-        pn = m.p if batch > 1 else m.p[None]
-        qn = m.q if batch > 1 else m.q[None]
-        assert T.relerr(pn[n], om.p) < TOL and T.relerr(qn[n], om.q) < TOL
-        hist = m.phis if batch > 1 else m.phis[None]
+        pn = m.p if batch > 1 else m.p[..., None]
+        qn = m.q if batch > 1 else m.q[..., None]
+        assert T.relerr(pn[..., n], om.p) < TOL and T.relerr(qn[..., n], om.q) < TOL
+        hist = m.phis if batch > 1 else m.phis[..., None]
         for bath in m.baths:
             if bath.ml > 1:
-                assert T.relerr(hist[n][:bath.ml][:, bath.cids], om.phis[:bath.ml][:, bath.cids]) < TOL
+                assert T.relerr(hist[..., n][:bath.ml][:, bath.cids], om.phis[:bath.ml][:, bath.cids]) < TOL
 
 
 def test_two_segments_carry_state_and_wrap_noise(cuda):
@@ -77,14 +79,15 @@ def test_two_segments_carry_state_and_wrap_noise(cuda):
     for n in range(B):
         om, recs = T.run_oracle(c, j, m, xi, r, n, c["nmd"], nrep=2)
         for rep in range(2):
-            assert T.relerr(recs_dev[rep][0][n], recs[rep]["ps"]) < TOL
-            assert T.relerr(recs_dev[rep][1][n], recs[rep]["qs"]) < TOL
+            assert T.relerr(recs_dev[rep][0][..., n], recs[rep]["ps"]) < TOL
+            assert T.relerr(recs_dev[rep][1][..., n], recs[rep]["qs"]) < TOL
             for b in range(2):
                 assert np.abs(recs_dev[rep][2][b][:, n] - recs[rep]["cur"][b]).max() < 10 * TOL * np.abs(recs[rep]["cur"][b]).max()
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name", ["ph2", "eph", "debye"])
-def test_against_reference_golden_trajectories(cuda, golden, name):
+def test_against_reference_golden_trajectories(cuda, golden, name, mode):
     """The REFERENCE's own trajectories (golden *.npz): feed its noise and initial state to the
     device path and reproduce ps, qs, currents, kinetic energy and the final history."""
     from pymd_b200 import synth
@@ -110,7 +113,7 @@ def test_against_reference_golden_trajectories(cuda, golden, name):
                  ebath(j.cats_e, c["T"], c["dt"], c["nmd"], wmax=c["ewmax"], nw=c["enw"], bias=c["bias"], efric=j.efric,
                        exim=j.exim, exip=j.exip)]
         constr = None
-    m = md(c["dt"], c["nmd"], c["T"], axyz=j.axyz, harmonic=True, dyn=j.DynMat, constr=constr)
+    m = md(c["dt"], c["nmd"], c["T"], axyz=j.axyz, harmonic=True, dyn=j.DynMat, constr=constr, step_mode=mode)
     m.write_files = False
     for b in baths:
         if hasattr(b, "gmem"):
@@ -134,6 +137,33 @@ def test_against_reference_golden_trajectories(cuda, golden, name):
             assert T.relerr(m.phis[:, b.cids], g["phis_end"][:, b.cids]) < TOL
 
 
+@pytest.mark.parametrize("case", ["ph2", "eph", "aubz"])
+def test_switching_between_step_modes(cuda, case):
+    """The per-step pipeline (mode 1) and the fused kernel (mode 2) share all carried state
+    (p, q, history ring, tail, cached potential force): alternating between them mid-run, with
+    odd step counts that straddle the fused time blocks, still follows the oracle."""
+    c = T.CASES[case]
+    B = 3
+    m, j = T.device_md(c, B)
+    xi, r = T.draw(c, m, B, seed=23)
+    m.initialise(r=r); m.ResetHis()
+    for b, bath in enumerate(m.baths):
+        bath.gnoi(xi=xi[0][b])
+    m.ResetSavepq()
+    plan = [(2, 3), (1, 2), (2, 11), (1, 1), (2, 8), (2, 1), (1, 5)]
+    done = 0
+    for mode, n in plan:
+        m.step_mode = mode
+        m.steps(n)
+        done += n
+    m.step_mode = 2
+    m.steps(c["nmd"] - done)
+    for n in range(B):
+        om, recs = T.run_oracle(c, j, m, xi, r, n, c["nmd"])
+        compare(m, recs[0], n)
+        assert T.relerr(m.p[..., n], om.p) < TOL and T.relerr(m.q[..., n], om.q) < TOL
+
+
 def test_fhis_recording(cuda, golden):
     """md.fhis (bath forces of the first evaluation, md.py:343) when asked for."""
     c = T.CASES["ph2"]
@@ -150,7 +180,7 @@ def test_fhis_recording(cuda, golden):
     for _ in range(16):
         om.vv()
     for b in range(2):
-        assert T.relerr(m.fhis[b][1][:16], om.fhis[b][:16]) < TOL
+        assert T.relerr(m.fhis[b][:16, :, 1], om.fhis[b][:16]) < TOL
 
 
 def test_history_roundtrip_and_resume(cuda, tmp_path):
@@ -239,7 +269,7 @@ def test_size_independent_properties_at_scale(cuda):
     for b in small.baths:
         b.gnoi()
     small.steps(48)
-    assert np.array_equal(small.p, pb[64:96]) and np.array_equal(small.q, qb[64:96])
+    assert np.array_equal(small.p, pb[:, 64:96]) and np.array_equal(small.q, qb[:, 64:96])
     dbl, _ = T.device_md(c, 32, savepq=False, seed=9, traj0=64)
     dbl.initialise(); dbl.ResetHis()
     dbl.p, dbl.q = 2.0 * np.asarray(dbl.p), 2.0 * np.asarray(dbl.q)
