@@ -214,8 +214,10 @@ def test_history_roundtrip_and_resume(cuda, tmp_path):
     del b
     r = fresh()
     r.Run()                               # finds MD0.npz with ipie=1, resumes pieces 2,3
-    assert np.array_equal(r.p, ref_p) and np.array_equal(r.q, ref_q)
-    assert np.array_equal(r.power2, ref_pow) and np.array_equal(r.curmean, ref_cur)
+    # on resume the memory-kernel tail and the cached force are recomputed from the restored
+    # history (different summation order than the carried values): equal to rounding, not bitwise
+    assert T.relerr(r.p, ref_p) < 1e-12 and T.relerr(r.q, ref_q) < 1e-12
+    assert T.relerr(r.power2, ref_pow) < 1e-12 and T.relerr(r.curmean, ref_cur) < 1e-10
     assert os.path.exists(os.path.join(tmp_path, "kappa.300.0.bath0.run0.dat"))
     assert os.path.exists(os.path.join(tmp_path, "power2.300.0.run0.dat"))
 
