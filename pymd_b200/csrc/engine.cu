@@ -308,6 +308,7 @@ int finalize(pymd_ctx* c) {
     d.con = c->d_con;
     d.nd = nd; d.ldb = ldb; d.nbath = c->nbath; d.nmd = c->nmd; d.ncon = c->ncon; d.dt = c->dt;
     if (c->d_aqT) { cudaFree(c->d_aqT); c->d_aqT = nullptr; }
+    if (c->d_con3) { cudaFree(c->d_con3); c->d_con3 = nullptr; }
     c->finalized = true;
     c->fpot_valid = false;
     c->fpotc_valid = false;
@@ -462,7 +463,7 @@ int pymd_ctx_destroy(pymd_ctx* c) {
         cudaFree(H.d_cids); cudaFree(H.d_inv); cudaFree(H.d_head); cudaFree(H.d_aq);
         cudaFree(H.d_krev); cudaFree(H.d_kintra);
     }
-    cudaFree(c->d_dyn); cudaFree(c->d_mp); cudaFree(c->d_con); cudaFree(c->d_aqT); cudaFree(c->ws);
+    cudaFree(c->d_dyn); cudaFree(c->d_mp); cudaFree(c->d_con); cudaFree(c->d_aqT); cudaFree(c->d_con3); cudaFree(c->ws);
     delete c;
     return PYMD_OK;
 }

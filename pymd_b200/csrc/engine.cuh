@@ -67,6 +67,7 @@ struct pymd_ctx {
     double* d_mp = nullptr;            // [nd][ldn]  sum_b scatter(alpha_b kernel_b[0])
     double* d_con = nullptr;           // [ncon][nd]
     double* d_aqT = nullptr;           // [nd][ldn]  q-coupled operator scattered to nd x nd (fused path)
+    double* d_con3 = nullptr;          // [3][ncon][nd]  c, D c, AqT c (fused path, constraints by linearity)
     void* ws = nullptr;                // workspace
     size_t ws_bytes = 0;
     pymd::StepDev sd{};

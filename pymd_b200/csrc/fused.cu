@@ -33,10 +33,12 @@ constexpr int FW = 8;        // warps per CTA
 constexpr int NDP = 64;      // padded rows (8 per warp)
 constexpr int FT = 8;        // steps per block
 constexpr int MAXKS = 16;    // k-steps of the nd x nd operators (nd <= 64)
+constexpr int FB_MAX = 4;    // baths supported by the fused path
 
 struct FusedBath {
-    int nc, ncp, ml, nonlocal, R, slot0, ntap, ldk;
-    int off_hd, off_kin, off_hist, off_nb, off_cids, off_inrem;   // smem offsets (doubles / ints)
+    int nc, ncp, ml, nonlocal, R, slot0, ntap, ldk, direct;       // direct: local remainder bath, noise read straight from HBM
+    int off_hd, off_kin, off_hist, off_nb, off_cids, off_inrem;   // smem offsets (doubles)
+    int lda;
     const double* noise;
     const double* P;          // [FT][nc][ldb] pre-block tail
     double* tail_cur;         // [nc][ldb] tail(t) carried between launches
@@ -46,7 +48,6 @@ struct FusedBath {
     const double* kin_g;      // [kBlockT][nc][nc]
     const int* cids_g;
     const int* inv_g;
-    int lda;
 };
 
 struct FusedParams {
@@ -55,10 +56,10 @@ struct FusedParams {
     double dt;
     double *p, *q, *ps, *qs, *etot, *fpotn;
     int* samef;
-    const double *dyn, *mp, *aqT, *con;
-    int off_xp0, off_xp1, off_xq, off_ph, off_fb, off_curp, off_conp, off_maxp, off_conv, off_inv;
+    const double *dyn, *mp, *aqT, *con3;      // con3: [3][ncon][nd] = c, D c, AqT c
+    int off_xp0, off_xp1, off_xq, off_curp, off_conp, off_maxp, off_conv;
     int smem_doubles;
-    FusedBath b[PYMD_MAX_BATHS];
+    FusedBath b[FB_MAX];
 };
 
 __device__ __forceinline__ double colsum8(double v) {     // sum over the 8 lanes sharing lane%4
@@ -73,6 +74,8 @@ __device__ __forceinline__ double colmax8(double v) {
     v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 16));
     return v;
 }
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 
 template <int NT>
 __device__ __forceinline__ void zero_acc(double (&a)[NT][2]) {
@@ -122,23 +125,15 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
     const int nd = P.nd, ks = P.ks, nb = P.nbath;
     const size_t ldb = P.ldb;
     const double dt = P.dt, dt2 = P.dt * P.dt;
-
-    double* XPb[2] = {sm + P.off_xp0, sm + P.off_xp1};
-    double* XQ = sm + P.off_xq;
-    double* PH = sm + P.off_ph;
-    double* FB = sm + P.off_fb;
-    double* CURP = sm + P.off_curp;             // [(nb+1)][FW][N]
-    double* CONP = sm + P.off_conp;             // [ncon][2][FW][N]
-    double* MAXP = sm + P.off_maxp;             // [FW][N]
-    double* CONV = sm + P.off_conv;             // [ncon][NDP]
-    int* INV = reinterpret_cast<int*>(sm + P.off_inv);   // [nb][NDP]
+    const bool live = row < nd;
+    const int own = row * LD + 2 * lc;          // this thread's entries: own + 8 j (+0,+1)
 
     // ------------------------------------------------------------------ prologue
     for (int i = tid; i < P.smem_doubles; i += FW * 32) sm[i] = 0.0;
     __syncthreads();
     for (int b = 0; b < nb; ++b) {
         const FusedBath& B = P.b[b];
-        for (int i = tid; i < NDP; i += FW * 32) INV[b * NDP + i] = i < nd ? B.inv_g[i] : -1;
+        if (B.direct) continue;
         int* CIDS = reinterpret_cast<int*>(sm + B.off_cids);
         int* INREM = reinterpret_cast<int*>(sm + B.off_inrem);
         for (int i = tid; i < B.ncp; i += FW * 32) {
@@ -158,33 +153,51 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
             }
         }
     }
-    for (int e = tid; e < P.ncon * nd; e += FW * 32) CONV[(e / nd) * NDP + e % nd] = P.con[e];
+    if (HASCON)
+        for (int e = tid; e < 3 * P.ncon * nd; e += FW * 32) sm[P.off_conv + (e / nd) * NDP + e % nd] = P.con3[e];
 
     double aD[MAXKS], aM[MAXKS], aQ[MAXKS];
 #pragma unroll
     for (int k = 0; k < MAXKS; ++k) {
-        const bool ok = k < ks && row < nd;
+        const bool ok = k < ks && live;
         aD[k] = ok ? P.dyn[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
         aM[k] = ok ? P.mp[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
         aQ[k] = (HASQ && ok) ? P.aqT[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
     }
-    // state of this CTA's trajectories
-    int cur = 0;
-    if (row < nd) {
+    // per-thread bath membership of the owned row: index into the bath's dofs or -1
+    int ip[FB_MAX];
+#pragma unroll
+    for (int b = 0; b < FB_MAX; ++b) ip[b] = (b < nb && live) ? P.b[b].inv_g[row] : -1;
+
+    int xpc = P.off_xp0, xpn = P.off_xp1;      // current / next head buffer (offsets into sm)
+    const int xq = P.off_xq;
+    if (live) {
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             const int n = 8 * j + 2 * lc;
-            *reinterpret_cast<double2*>(&XPb[0][row * LD + n]) =
-                *reinterpret_cast<const double2*>(&P.p[(size_t)row * ldb + col0 + n]);
-            *reinterpret_cast<double2*>(&XQ[row * LD + n]) =
-                *reinterpret_cast<const double2*>(&P.q[(size_t)row * ldb + col0 + n]);
+            const double2 pv = ld2(&P.p[(size_t)row * ldb + col0 + n]);
+            const double2 qv = ld2(&P.q[(size_t)row * ldb + col0 + n]);
+            st2(&sm[xpc + own + 8 * j], pv.x, pv.y);
+            st2(&sm[xq + own + 8 * j], qv.x, qv.y);
         }
     }
-    // noise minus tail at time t0 for every bath
+    // noise minus tail at time t0: in smem for every bath but a local remainder bath (registers)
+    double nzr[NT][2];
+    zero_acc<NT>(nzr);
     {
         const int tn0 = (int)(P.t0 % P.nmd);
         for (int b = 0; b < nb; ++b) {
             const FusedBath& B = P.b[b];
+            if (B.direct) {
+                if (ip[b] >= 0) {
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const double2 v = ld2(&B.noise[((size_t)tn0 * B.nc + ip[b]) * ldb + col0 + 8 * j + 2 * lc]);
+                        nzr[j][0] = v.x; nzr[j][1] = v.y;
+                    }
+                }
+                continue;
+            }
             double* NB = sm + B.off_nb;                 // buffer 0
             for (int e = tid; e < B.nc * N; e += FW * 32) {
                 const int r = e / N, n = e % N;
@@ -196,27 +209,24 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
     }
     __syncthreads();
 
-    double fpot[NT][2], uq[NT][2];          // potential force / q-coupled bath force at q(t), own rows
+    double fpot[NT][2], uq[NT][2], fcor[NT][2];   // -D q, AqT q at the current q; pending constraint correction
     zero_acc<NT>(fpot);
     zero_acc<NT>(uq);
-    if (!HASCON) {
-        if (HASQ) matvec2<NT>(aD, aQ, ks, XQ, LD, fpot, uq, lr, lc);
-        else matvec1<NT>(aD, ks, XQ, LD, fpot, lr, lc);
+    zero_acc<NT>(fcor);
+    if (HASQ) matvec2<NT>(aD, aQ, ks, sm + xq, LD, fpot, uq, lr, lc);
+    else matvec1<NT>(aD, ks, sm + xq, LD, fpot, lr, lc);
 #pragma unroll
-        for (int j = 0; j < NT; ++j) { fpot[j][0] = -fpot[j][0]; fpot[j][1] = -fpot[j][1]; }
-    } else {
+    for (int j = 0; j < NT; ++j) { fpot[j][0] = -fpot[j][0]; fpot[j][1] = -fpot[j][1]; }
+    if (HASCON) {
         // constrained runs carry md.potforce's cache (md.py:456-457) across launches
+        if (P.carry_valid && live) {
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            const int n = 8 * j + 2 * lc;
-            if (P.carry_valid && row < nd) {
-                fpot[j][0] = P.fpotn[(size_t)row * ldb + col0 + n];
-                fpot[j][1] = P.fpotn[(size_t)row * ldb + col0 + n + 1];
+            for (int j = 0; j < NT; ++j) {
+                const int n = col0 + 8 * j + 2 * lc;
+                if (P.samef[n]) fpot[j][0] = P.fpotn[(size_t)row * ldb + n];
+                if (P.samef[n + 1]) fpot[j][1] = P.fpotn[(size_t)row * ldb + n + 1];
             }
         }
-        for (int e = tid; e < FW * N; e += FW * 32)
-            MAXP[e] = (P.carry_valid && P.samef[col0 + e % N]) ? 0.0 : 1.0;
-        __syncthreads();
     }
     int nbuf = 0;                           // NB buffer holding noise-minus-tail at time t
 
@@ -224,20 +234,14 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
     for (int s = 0; s < P.nsteps; ++s) {
         const long long t = P.t0 + s;
         const int tn = (int)(t % P.nmd), tn1 = (int)((t + 1) % P.nmd);
-        double* XPc = XPb[cur];
-        double* XPn = XPb[cur ^ 1];
 
         // ============ round A: first force evaluation at time t, head p(t) ============
         double hA[NT][2];
         zero_acc<NT>(hA);
-        matvec1<NT>(aM, ks, XPc, LD, hA, lr, lc);
-        if (HASCON) {
-            double fc[NT][2], uc[NT][2];
-            zero_acc<NT>(fc);
-            zero_acc<NT>(uc);
-            if (HASQ) matvec2<NT>(aD, aQ, ks, XQ, LD, fc, uc, lr, lc);
-            else matvec1<NT>(aD, ks, XQ, LD, fc, lr, lc);
-            __syncthreads();        // every warp has read q(t) from XQ before any warp overwrites it with q'
+        matvec1<NT>(aM, ks, sm + xpc, LD, hA, lr, lc);
+        if (HASCON && s > 0) {
+            // md.sameq (md.py:724-736): a constraint projection that moved q by >= 1e-9 invalidates the
+            // cached potential force; -D q(t) = -D q' + sum_c dq_c (D c_c) by linearity
 #pragma unroll
             for (int j = 0; j < NT; ++j)
 #pragma unroll
@@ -245,36 +249,29 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                     const int n = 8 * j + 2 * lc + e;
                     double m = 0.0;
 #pragma unroll
-                    for (int ww = 0; ww < FW; ++ww) m = fmax(m, MAXP[ww * N + n]);
-                    if (!(m < 10e-10)) fpot[j][e] = -fc[j][e];      // md.sameq miss -> fresh force
-                    uq[j][e] = uc[j][e];
+                    for (int ww = 0; ww < FW; ++ww) m = fmax(m, sm[P.off_maxp + ww * N + n]);
+                    if (!(m < 10e-10)) fpot[j][e] += fcor[j][e];
                 }
         }
-        // ---- elementwise part on the rows this thread owns
-        double cpart[PYMD_MAX_BATHS];
-#pragma unroll
-        for (int b = 0; b < PYMD_MAX_BATHS; ++b) cpart[b] = 0.0;
-        double epart = 0.0;
-        // per-column partial sums are accumulated per n-tile below
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             const int n = 8 * j + 2 * lc;
-            double ce[PYMD_MAX_BATHS][2];
+            double ce[FB_MAX][2];
 #pragma unroll
-            for (int b = 0; b < PYMD_MAX_BATHS; ++b) ce[b][0] = ce[b][1] = 0.0;
-            double ee[2] = {0.0, 0.0};
-            if (row < nd) {
-                const double2 pv = *reinterpret_cast<const double2*>(&XPc[row * LD + n]);
-                const double2 qv = *reinterpret_cast<const double2*>(&XQ[row * LD + n]);
+            for (int b = 0; b < FB_MAX; ++b) ce[b][0] = ce[b][1] = 0.0;
+            double e0 = 0.0, e1 = 0.0;
+            if (live) {
+                const double2 pv = ld2(&sm[xpc + own + 8 * j]);
+                const double2 qv = ld2(&sm[xq + own + 8 * j]);
                 double f0 = fpot[j][0] + uq[j][0] - hA[j][0];
                 double f1 = fpot[j][1] + uq[j][1] - hA[j][1];
 #pragma unroll
-                for (int b = 0; b < PYMD_MAX_BATHS; ++b) {
-                    if (b >= nb) break;
-                    const int ip = INV[b * NDP + row];
-                    if (ip < 0) continue;
+                for (int b = 0; b < FB_MAX; ++b) {
+                    if (ip[b] < 0) continue;
                     const FusedBath& B = P.b[b];
-                    const double2 nv = *reinterpret_cast<const double2*>(&sm[B.off_nb + nbuf * B.ncp * LD + ip * LD + n]);
+                    double2 nv;
+                    if (B.direct) nv = make_double2(nzr[j][0], nzr[j][1]);
+                    else nv = ld2(&sm[B.off_nb + (nbuf * B.ncp + ip[b]) * LD + n]);
                     f0 += nv.x;
                     f1 += nv.y;
                     double c0 = nv.x, c1 = nv.y;
@@ -283,59 +280,62 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                     ce[b][0] = pv.x * c0;
                     ce[b][1] = pv.y * c1;
                     if (B.nonlocal) {
-                        *reinterpret_cast<double2*>(&sm[B.off_hist + (s * B.ncp + ip) * LD + n]) = pv;
+                        st2(&sm[B.off_hist + (s * B.ncp + ip[b]) * LD + n], pv.x, pv.y);
                         const int slot = (B.slot0 + s) % B.R;
-                        *reinterpret_cast<double2*>(&B.ring[((size_t)slot * B.ncp + ip) * ldb + col0 + n]) = pv;
+                        st2(&B.ring[((size_t)slot * B.ncp + ip[b]) * ldb + col0 + n], pv.x, pv.y);
                     }
                 }
-                ee[0] = pv.x * pv.x;
-                ee[1] = pv.y * pv.y;
-                const double2 ph = make_double2(pv.x + f0 * dt / 2.0, pv.y + f1 * dt / 2.0);
-                const double2 qn = make_double2(qv.x + pv.x * dt + f0 * dt2 / 2.0, qv.y + pv.y * dt + f1 * dt2 / 2.0);
-                *reinterpret_cast<double2*>(&XPn[row * LD + n]) = ph;
-                *reinterpret_cast<double2*>(&PH[row * LD + n]) = ph;
-                *reinterpret_cast<double2*>(&XQ[row * LD + n]) = qn;
-                if (P.ps) *reinterpret_cast<double2*>(&P.ps[((size_t)tn * nd + row) * ldb + col0 + n]) = pv;
-                if (P.qs) *reinterpret_cast<double2*>(&P.qs[((size_t)tn * nd + row) * ldb + col0 + n]) = qv;
+                e0 = pv.x * pv.x;
+                e1 = pv.y * pv.y;
+                st2(&sm[xpn + own + 8 * j], pv.x + f0 * dt / 2.0, pv.y + f1 * dt / 2.0);
+                st2(&sm[xq + own + 8 * j], qv.x + pv.x * dt + f0 * dt2 / 2.0, qv.y + pv.y * dt + f1 * dt2 / 2.0);
+                if (P.ps) st2(&P.ps[((size_t)tn * nd + row) * ldb + col0 + n], pv.x, pv.y);
+                if (P.qs) st2(&P.qs[((size_t)tn * nd + row) * ldb + col0 + n], qv.x, qv.y);
             }
             // column sums over this warp's 8 rows -> per-warp slots
+            e0 = colsum8(e0);
+            e1 = colsum8(e1);
+            if (lr == 0) st2(&sm[P.off_curp + (nb * FW + w) * N + n], e0, e1);
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const double es = colsum8(ee[e]);
-                if (lr == 0) CURP[(nb * FW + w) * N + n + e] = es;
-            }
-#pragma unroll
-            for (int b = 0; b < PYMD_MAX_BATHS; ++b) {
+            for (int b = 0; b < FB_MAX; ++b) {
                 if (b >= nb) break;
+                const double c0 = colsum8(ce[b][0]), c1 = colsum8(ce[b][1]);
+                if (lr == 0) st2(&sm[P.off_curp + (b * FW + w) * N + n], c0, c1);
+            }
+        }
+        // noise of the direct bath at time t+1 (used from round B on)
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const double cs = colsum8(ce[b][e]);
-                    if (lr == 0) CURP[(b * FW + w) * N + n + e] = cs;
+        for (int b = 0; b < FB_MAX; ++b) {
+            if (b < nb && P.b[b].direct && ip[b] >= 0) {
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const double2 v = ld2(&P.b[b].noise[((size_t)tn1 * P.b[b].nc + ip[b]) * ldb + col0 + 8 * j + 2 * lc]);
+                    nzr[j][0] = v.x; nzr[j][1] = v.y;
                 }
             }
         }
-        (void)cpart; (void)epart;
         __syncwarp();
-        // ---- work items: heads of the small baths (scalars p.g_b only) ...
+        // ---- work items, dealt round-robin to the warps ----
         {
             int item = 0;
+            // (1) heads of the small baths: only the scalars p.g_b are needed (currents)
             for (int b = 0; b < nb; ++b) {
                 if (b == P.rem) continue;
                 const FusedBath& B = P.b[b];
                 const int mts = B.ncp / 8;
                 const int* CIDS = reinterpret_cast<const int*>(sm + B.off_cids);
                 const int* INREM = reinterpret_cast<const int*>(sm + B.off_inrem);
-                const double* HD = sm + B.off_hd;
                 for (int mt = 0; mt < mts; ++mt)
                     for (int j = 0; j < NT; ++j, ++item) {
                         if (item % FW != w) continue;
                         double g0 = 0.0, g1 = 0.0;
+                        const double* A = sm + B.off_hd + (mt * 8 + lr) * B.ldk + lc;
                         for (int kk = 0; kk < B.ncp; kk += 4)
-                            dmma884(g0, g1, HD[(mt * 8 + lr) * B.ldk + kk + lc], XPc[CIDS[kk + lc] * LD + 8 * j + lr]);
+                            dmma884(g0, g1, A[kk], sm[xpc + CIDS[kk + lc] * LD + 8 * j + lr]);
                         const int rr = mt * 8 + lr, n = 8 * j + 2 * lc;
                         double s0 = 0.0, s1 = 0.0, r0 = 0.0, r1 = 0.0;
                         if (rr < B.nc) {
-                            const double2 pv = *reinterpret_cast<const double2*>(&XPc[CIDS[rr] * LD + n]);
+                            const double2 pv = ld2(&sm[xpc + CIDS[rr] * LD + n]);
                             s0 = pv.x * g0;
                             s1 = pv.y * g1;
                             if (INREM[rr]) { r0 = s0; r1 = s1; }
@@ -343,20 +343,22 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                         s0 = colsum8(s0); s1 = colsum8(s1);
                         r0 = colsum8(r0); r1 = colsum8(r1);
                         if (lr == 0) {
-                            CURP[(b * FW + w) * N + n] -= s0;
-                            CURP[(b * FW + w) * N + n + 1] -= s1;
+                            double* cb = &sm[P.off_curp + (b * FW + w) * N + n];
+                            cb[0] -= s0;
+                            cb[1] -= s1;
                             if (P.rem >= 0) {
-                                CURP[(P.rem * FW + w) * N + n] += r0;
-                                CURP[(P.rem * FW + w) * N + n + 1] += r1;
+                                double* cr = &sm[P.off_curp + (P.rem * FW + w) * N + n];
+                                cr[0] += r0;
+                                cr[1] += r1;
                             }
                         }
                         __syncwarp();
                     }
             }
-            // ... and noise minus memory-kernel tail at time t+1 for every bath
-            item = 0;
+            // (2) noise minus memory-kernel tail at time t+1
             for (int b = 0; b < nb; ++b) {
                 const FusedBath& B = P.b[b];
+                if (B.direct) continue;
                 const int mts = B.ncp / 8;
                 const int* CIDS = reinterpret_cast<const int*>(sm + B.off_cids);
                 for (int mt = 0; mt < mts; ++mt)
@@ -365,19 +367,17 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                         const int rr = mt * 8 + lr, n = 8 * j + 2 * lc;
                         double2 xi = make_double2(0.0, 0.0), pt = make_double2(0.0, 0.0);
                         if (rr < B.nc) {
-                            xi = *reinterpret_cast<const double2*>(&B.noise[((size_t)tn1 * B.nc + rr) * ldb + col0 + n]);
-                            if (B.nonlocal)
-                                pt = *reinterpret_cast<const double2*>(&B.P[((size_t)s * B.nc + rr) * ldb + col0 + n]);
+                            xi = ld2(&B.noise[((size_t)tn1 * B.nc + rr) * ldb + col0 + n]);
+                            if (B.nonlocal) pt = ld2(&B.P[((size_t)s * B.nc + rr) * ldb + col0 + n]);
                         }
                         double a0 = 0.0, a1 = 0.0;
                         if (B.nonlocal) {
-                            const double* KIN = sm + B.off_kin;
                             const int ntap = min(s + 1, B.ntap);
                             for (int k = 1; k <= ntap; ++k) {
-                                const double* A = KIN + ((k - 1) * B.ncp + mt * 8 + lr) * B.ldk + lc;
+                                const double* A = sm + B.off_kin + ((k - 1) * B.ncp + mt * 8 + lr) * B.ldk + lc;
                                 if (k == 1) {
                                     for (int kk = 0; kk < B.ncp; kk += 4)
-                                        dmma884(a0, a1, A[kk], XPc[CIDS[kk + lc] * LD + 8 * j + lr]);
+                                        dmma884(a0, a1, A[kk], sm[xpc + CIDS[kk + lc] * LD + 8 * j + lr]);
                                 } else {
                                     const double* H = sm + B.off_hist + ((s + 1 - k) * B.ncp + lc) * LD + 8 * j + lr;
                                     for (int kk = 0; kk < B.ncp; kk += 4) dmma884(a0, a1, A[kk], H[kk * LD]);
@@ -386,10 +386,9 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                         }
                         const double t0v = pt.x + a0, t1v = pt.y + a1;
                         if (rr < B.nc) {
-                            *reinterpret_cast<double2*>(&sm[B.off_nb + (nbuf ^ 1) * B.ncp * LD + rr * LD + n]) =
-                                make_double2(xi.x - t0v, xi.y - t1v);
+                            st2(&sm[B.off_nb + ((nbuf ^ 1) * B.ncp + rr) * LD + n], xi.x - t0v, xi.y - t1v);
                             if (B.nonlocal && s == P.nsteps - 1)
-                                *reinterpret_cast<double2*>(&B.tail_cur[(size_t)rr * ldb + col0 + n]) = make_double2(t0v, t1v);
+                                st2(&B.tail_cur[(size_t)rr * ldb + col0 + n], t0v, t1v);
                         }
                     }
             }
@@ -400,91 +399,84 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
             const int b = e / N, n = e % N;
             double sum = 0.0;
 #pragma unroll
-            for (int ww = 0; ww < FW; ++ww) sum += CURP[(b * FW + ww) * N + n];
+            for (int ww = 0; ww < FW; ++ww) sum += sm[P.off_curp + (b * FW + ww) * N + n];
             if (b < nb) P.b[b].cur[(size_t)tn * ldb + col0 + n] = sum;
             else P.etot[(size_t)tn * ldb + col0 + n] = 0.5 * sum;
         }
         nbuf ^= 1;
-        cur ^= 1;
+        { const int tmp = xpc; xpc = xpn; xpn = tmp; }      // xpc: p(t+1/2), xpn: free (held p(t))
 
         // ============ round B: second evaluation at time t+1, head p(t+1/2) ============
-        XPc = XPb[cur];
-        XPn = XPb[cur ^ 1];
+        double fb[NT][2];
         {
-            double aDq[NT][2], aQq[NT][2], hB[NT][2];
+            double aDq[NT][2], hB[NT][2];
             zero_acc<NT>(aDq);
-            zero_acc<NT>(aQq);
             zero_acc<NT>(hB);
-            if (HASQ) matvec2<NT>(aD, aQ, ks, XQ, LD, aDq, aQq, lr, lc);
-            else matvec1<NT>(aD, ks, XQ, LD, aDq, lr, lc);
-            matvec1<NT>(aM, ks, XPc, LD, hB, lr, lc);
+            zero_acc<NT>(uq);
+            if (HASQ) matvec2<NT>(aD, aQ, ks, sm + xq, LD, aDq, uq, lr, lc);
+            else matvec1<NT>(aD, ks, sm + xq, LD, aDq, lr, lc);
+            matvec1<NT>(aM, ks, sm + xpc, LD, hB, lr, lc);
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 const int n = 8 * j + 2 * lc;
                 fpot[j][0] = -aDq[j][0];
                 fpot[j][1] = -aDq[j][1];
-                if (!HASCON) { uq[j][0] = aQq[j][0]; uq[j][1] = aQq[j][1]; }
-                if (row < nd) {
-                    double f0 = fpot[j][0] + aQq[j][0], f1 = fpot[j][1] + aQq[j][1];
+                double f0 = fpot[j][0] + uq[j][0], f1 = fpot[j][1] + uq[j][1];
 #pragma unroll
-                    for (int b = 0; b < PYMD_MAX_BATHS; ++b) {
-                        if (b >= nb) break;
-                        const int ip = INV[b * NDP + row];
-                        if (ip < 0) continue;
-                        const double2 nv = *reinterpret_cast<const double2*>(&sm[P.b[b].off_nb + nbuf * P.b[b].ncp * LD + ip * LD + n]);
+                for (int b = 0; b < FB_MAX; ++b) {
+                    if (ip[b] < 0) continue;
+                    const FusedBath& B = P.b[b];
+                    if (B.direct) { f0 += nzr[j][0]; f1 += nzr[j][1]; }
+                    else {
+                        const double2 nv = ld2(&sm[B.off_nb + (nbuf * B.ncp + ip[b]) * LD + n]);
                         f0 += nv.x;
                         f1 += nv.y;
                     }
-                    const double2 ph = *reinterpret_cast<const double2*>(&PH[row * LD + n]);
-                    *reinterpret_cast<double2*>(&FB[row * LD + n]) = make_double2(f0, f1);
-                    *reinterpret_cast<double2*>(&XPn[row * LD + n]) =
-                        make_double2(ph.x + dt * (f0 - hB[j][0]) / 2.0, ph.y + dt * (f1 - hB[j][1]) / 2.0);
+                }
+                fb[j][0] = f0;
+                fb[j][1] = f1;
+                if (live) {
+                    const double2 ph = ld2(&sm[xpc + own + 8 * j]);
+                    st2(&sm[xpn + own + 8 * j], ph.x + dt * (f0 - hB[j][0]) / 2.0, ph.y + dt * (f1 - hB[j][1]) / 2.0);
                 }
             }
         }
         __syncthreads();                                                        // ---- S3
-        cur ^= 1;
+        { const int tmp = xpc; xpc = xpn; xpn = tmp; }      // xpc: p1, xpn: still holds p(t+1/2)
 
         // ============ round C: third evaluation, head p1 -> p(t+1), constraints ============
-        XPc = XPb[cur];
-        XPn = XPb[cur ^ 1];
         {
             double hC[NT][2];
             zero_acc<NT>(hC);
-            matvec1<NT>(aM, ks, XPc, LD, hC, lr, lc);
+            matvec1<NT>(aM, ks, sm + xpc, LD, hC, lr, lc);
             double pn[NT][2];
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
-                const int n = 8 * j + 2 * lc;
                 pn[j][0] = pn[j][1] = 0.0;
-                if (row < nd) {
-                    const double2 ph = *reinterpret_cast<const double2*>(&PH[row * LD + n]);
-                    const double2 fb = *reinterpret_cast<const double2*>(&FB[row * LD + n]);
-                    pn[j][0] = ph.x + dt * (fb.x - hC[j][0]) / 2.0;
-                    pn[j][1] = ph.y + dt * (fb.y - hC[j][1]) / 2.0;
+                if (live) {
+                    const double2 ph = ld2(&sm[xpn + own + 8 * j]);
+                    pn[j][0] = ph.x + dt * (fb[j][0] - hC[j][0]) / 2.0;
+                    pn[j][1] = ph.y + dt * (fb[j][1] - hC[j][1]) / 2.0;
                 }
             }
             if (!HASCON) {
-                if (row < nd) {
+                if (live) {
 #pragma unroll
-                    for (int j = 0; j < NT; ++j)
-                        *reinterpret_cast<double2*>(&XPn[row * LD + 8 * j + 2 * lc]) = make_double2(pn[j][0], pn[j][1]);
+                    for (int j = 0; j < NT; ++j) st2(&sm[xpn + own + 8 * j], pn[j][0], pn[j][1]);
                 }
             } else {
                 // md.ApplyConstraint (md.py:739-762): all dots with the unprojected vectors
                 for (int c = 0; c < P.ncon; ++c) {
-                    const double cv = row < nd ? CONV[c * NDP + row] : 0.0;
+                    const double cv = sm[P.off_conv + c * NDP + row];
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
                         const int n = 8 * j + 2 * lc;
-                        const double2 qv = *reinterpret_cast<const double2*>(&XQ[row * LD + n]);
+                        const double2 qv = ld2(&sm[xq + own + 8 * j]);
                         const double d0 = colsum8(pn[j][0] * cv), d1 = colsum8(pn[j][1] * cv);
-                        const double e0 = colsum8(qv.x * cv), e1 = colsum8(qv.y * cv);
+                        const double g0 = colsum8(qv.x * cv), g1 = colsum8(qv.y * cv);
                         if (lr == 0) {
-                            CONP[((c * 2 + 0) * FW + w) * N + n] = d0;
-                            CONP[((c * 2 + 0) * FW + w) * N + n + 1] = d1;
-                            CONP[((c * 2 + 1) * FW + w) * N + n] = e0;
-                            CONP[((c * 2 + 1) * FW + w) * N + n + 1] = e1;
+                            st2(&sm[P.off_conp + ((c * 2 + 0) * FW + w) * N + n], d0, d1);
+                            st2(&sm[P.off_conp + ((c * 2 + 1) * FW + w) * N + n], g0, g1);
                         }
                     }
                 }
@@ -492,51 +484,59 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
                     const int n = 8 * j + 2 * lc;
-                    const double2 q0 = *reinterpret_cast<const double2*>(&XQ[row * LD + n]);
+                    const double2 q0 = ld2(&sm[xq + own + 8 * j]);
                     double p0 = pn[j][0], p1 = pn[j][1], qa = q0.x, qb = q0.y;
+                    double fc0 = 0.0, fc1 = 0.0;
                     for (int c = 0; c < P.ncon; ++c) {
-                        const double cv = row < nd ? CONV[c * NDP + row] : 0.0;
+                        const double cv = sm[P.off_conv + c * NDP + row];
+                        const double dv = sm[P.off_conv + (P.ncon + c) * NDP + row];
+                        const double av = HASQ ? sm[P.off_conv + (2 * P.ncon + c) * NDP + row] : 0.0;
                         double dp0 = 0.0, dp1 = 0.0, dq0 = 0.0, dq1 = 0.0;
 #pragma unroll
                         for (int ww = 0; ww < FW; ++ww) {
-                            dp0 += CONP[((c * 2 + 0) * FW + ww) * N + n];
-                            dp1 += CONP[((c * 2 + 0) * FW + ww) * N + n + 1];
-                            dq0 += CONP[((c * 2 + 1) * FW + ww) * N + n];
-                            dq1 += CONP[((c * 2 + 1) * FW + ww) * N + n + 1];
+                            const double2 a = ld2(&sm[P.off_conp + ((c * 2 + 0) * FW + ww) * N + n]);
+                            const double2 bq = ld2(&sm[P.off_conp + ((c * 2 + 1) * FW + ww) * N + n]);
+                            dp0 += a.x; dp1 += a.y;
+                            dq0 += bq.x; dq1 += bq.y;
                         }
                         p0 -= dp0 * cv; p1 -= dp1 * cv;
                         qa -= dq0 * cv; qb -= dq1 * cv;
+                        fc0 += dq0 * dv; fc1 += dq1 * dv;                  // -D q(t+1) = -D q' + sum dq_c (D c)
+                        if (HASQ) { uq[j][0] -= dq0 * av; uq[j][1] -= dq1 * av; }   // AqT q(t+1)
                     }
-                    const double m0 = colmax8(row < nd ? fabs(qa - q0.x) : 0.0);
-                    const double m1 = colmax8(row < nd ? fabs(qb - q0.y) : 0.0);
-                    if (lr == 0) { MAXP[w * N + n] = m0; MAXP[w * N + n + 1] = m1; }
-                    if (row < nd) {
-                        *reinterpret_cast<double2*>(&XPn[row * LD + n]) = make_double2(p0, p1);
-                        *reinterpret_cast<double2*>(&XQ[row * LD + n]) = make_double2(qa, qb);
+                    fcor[j][0] = fc0;
+                    fcor[j][1] = fc1;
+                    const double m0 = colmax8(live ? fabs(qa - q0.x) : 0.0);
+                    const double m1 = colmax8(live ? fabs(qb - q0.y) : 0.0);
+                    if (lr == 0) st2(&sm[P.off_maxp + w * N + n], m0, m1);
+                    if (live) {
+                        st2(&sm[xpn + own + 8 * j], p0, p1);
+                        st2(&sm[xq + own + 8 * j], qa, qb);
                     }
                 }
             }
         }
         __syncthreads();                                                        // ---- S1
-        cur ^= 1;
+        { const int tmp = xpc; xpc = xpn; xpn = tmp; }      // xpc: p(t+1)
     }
 
     // ------------------------------------------------------------------ epilogue
-    if (row < nd) {
-        const double* XPc = XPb[cur];
+    if (live) {
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             const int n = 8 * j + 2 * lc;
-            *reinterpret_cast<double2*>(&P.p[(size_t)row * ldb + col0 + n]) = *reinterpret_cast<const double2*>(&XPc[row * LD + n]);
-            *reinterpret_cast<double2*>(&P.q[(size_t)row * ldb + col0 + n]) = *reinterpret_cast<const double2*>(&XQ[row * LD + n]);
-            *reinterpret_cast<double2*>(&P.fpotn[(size_t)row * ldb + col0 + n]) = make_double2(fpot[j][0], fpot[j][1]);
+            const double2 pv = ld2(&sm[xpc + own + 8 * j]);
+            const double2 qv = ld2(&sm[xq + own + 8 * j]);
+            st2(&P.p[(size_t)row * ldb + col0 + n], pv.x, pv.y);
+            st2(&P.q[(size_t)row * ldb + col0 + n], qv.x, qv.y);
+            st2(&P.fpotn[(size_t)row * ldb + col0 + n], fpot[j][0], fpot[j][1]);
         }
     }
     for (int n = tid; n < N; n += FW * 32) {
         int same = 1;
         if (HASCON) {
             double m = 0.0;
-            for (int ww = 0; ww < FW; ++ww) m = fmax(m, MAXP[ww * N + n]);
+            for (int ww = 0; ww < FW; ++ww) m = fmax(m, sm[P.off_maxp + ww * N + n]);
             same = m < 10e-10;
         }
         P.samef[col0 + n] = same;
@@ -556,28 +556,26 @@ size_t plan(const pymd_ctx* c, int NT, FusedParams& fp) {
     fp.off_xp0 = take(NDP * LD);
     fp.off_xp1 = take(NDP * LD);
     fp.off_xq = take(NDP * LD);
-    fp.off_ph = take(NDP * LD);
-    fp.off_fb = take(NDP * LD);
     fp.off_curp = take((c->nbath + 1) * FW * N);
     fp.off_conp = take(std::max(1, c->ncon) * 2 * FW * N);
     fp.off_maxp = take(FW * N);
-    fp.off_conv = take(std::max(1, c->ncon) * NDP);
-    fp.off_inv = take((c->nbath * NDP + 1) / 2 + 1);
+    fp.off_conv = take(std::max(1, 3 * c->ncon) * NDP);
     for (int b = 0; b < c->nbath; ++b) {
         const BathHost& H = c->bath[b];
         FusedBath& B = fp.b[b];
         B.nc = H.nc; B.ncp = H.ncp; B.ml = H.ml; B.nonlocal = H.ml > 1;
+        B.direct = (b == fp.rem && H.ml == 1) ? 1 : 0;
         B.ldk = H.ncp + 4;
         B.ntap = H.ml > 1 ? std::min(FT, H.ml - 1) : 0;
+        B.off_cids = B.off_inrem = B.off_hd = B.off_nb = B.off_kin = B.off_hist = 0;
+        if (B.direct) continue;
         B.off_cids = take(H.ncp / 2 + 1);
         B.off_inrem = take(H.ncp / 2 + 1);
-        B.off_hd = (b != fp.rem) ? take(H.ncp * B.ldk) : 0;
+        if (b != fp.rem) B.off_hd = take(H.ncp * B.ldk);
         B.off_nb = take(2 * H.ncp * LD);
         if (H.ml > 1) {
             B.off_kin = take(B.ntap * H.ncp * B.ldk);
             B.off_hist = take(FT * H.ncp * LD);
-        } else {
-            B.off_kin = B.off_hist = 0;
         }
     }
     fp.smem_doubles = off;
@@ -627,7 +625,7 @@ int launch_nt(const FusedParams& fp, size_t smem, int grid, bool hasq, bool hasc
 }  // namespace
 
 int fused_supported(const pymd_ctx* c) {
-    if (c->nd > NDP || c->ncon > 4) return 0;
+    if (c->nd > NDP || c->ncon > 4 || c->nbath > FB_MAX) return 0;
     int naq = 0;
     for (int b = 0; b < c->nbath; ++b) {
         naq += c->bath[b].has_aq;
@@ -650,7 +648,7 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
     fp.nd = c->nd; fp.ks = (c->nd + 3) / 4; fp.ldb = c->ldb; fp.ldn = c->ldn; fp.nbath = c->nbath;
     fp.nmd = c->nmd; fp.ncon = c->ncon; fp.dt = c->dt;
     fp.p = d.p; fp.q = d.q; fp.ps = d.ps; fp.qs = d.qs; fp.etot = d.etot; fp.fpotn = d.fpotn; fp.samef = d.samef;
-    fp.dyn = c->d_dyn; fp.mp = c->d_mp; fp.con = c->d_con;
+    fp.dyn = c->d_dyn; fp.mp = c->d_mp; fp.con3 = c->d_con3;
     // q-coupled operator scattered to nd x nd (built once)
     bool hasq = fp.aq >= 0;
     if (hasq && !c->d_aqT) {
@@ -662,6 +660,30 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
         PYMD_CUDA_CHECK(cudaMemcpy(c->d_aqT, aqT.data(), aqT.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
     fp.aqT = c->d_aqT;
+    if (c->ncon > 0 && !c->d_con3) {
+        // c, D c and AqT c for every constraint vector: -D q(t+1) and AqT q(t+1) follow from the
+        // projection coefficients by linearity, without another mat-vec
+        const int nd = c->nd, nc3 = c->ncon;
+        std::vector<double> c3((size_t)3 * nc3 * nd, 0.0);
+        for (int k = 0; k < nc3; ++k)
+            for (int i = 0; i < nd; ++i) {
+                c3[(size_t)k * nd + i] = c->con[(size_t)k * nd + i];
+                double sd = 0.0;
+                for (int j = 0; j < nd; ++j) sd += c->dyn[(size_t)i * nd + j] * c->con[(size_t)k * nd + j];
+                c3[(size_t)(nc3 + k) * nd + i] = sd;
+            }
+        if (hasq) {
+            const BathHost& H = c->bath[fp.aq];
+            for (int k = 0; k < nc3; ++k)
+                for (int i = 0; i < H.nc; ++i) {
+                    double sa = 0.0;
+                    for (int j = 0; j < H.nc; ++j) sa += H.aq[(size_t)i * H.nc + j] * c->con[(size_t)k * nd + H.cids[j]];
+                    c3[(size_t)(2 * nc3 + k) * nd + H.cids[i]] = sa;
+                }
+        }
+        PYMD_CUDA_CHECK(cudaMalloc(&c->d_con3, c3.size() * sizeof(double)));
+        PYMD_CUDA_CHECK(cudaMemcpy(c->d_con3, c3.data(), c3.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     for (int b = 0; b < c->nbath; ++b) {
         BathHost& H = c->bath[b];
         FusedBath& B = fp.b[b];

@@ -158,9 +158,18 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
         PYMD_REQUIRE(((a.seg_aoff[sg] + a.seg_lo[sg]) % 2) == 0 && (a.a_ld % 2) == 0 && (a.a_ls % 2) == 0,
                      "gemm: A rows must be 16-byte aligned");
     PYMD_REQUIRE((a.x_ld % 2) == 0 && (a.y_ld % 2) == 0, "gemm: X/Y leading dims must be even");
-    // Tile choice: fill the 148 SMs first, then grow the tile for operand reuse.
-    const long long ctas64 = (long long)((a.N + 63) / 64) * ((a.M + 63) / 64);
-    if (a.M > 32 && ctas64 >= 148) return launch_t<64, 64>(a, stream);
+    // Tile choice by estimated efficiency = SM fill x per-tile DMMA efficiency (measured: a 64x64 CTA
+    // tile with 32x32 warp tiles needs 1 LDS per 2 DMMA and sustains ~0.9 of the pipe; 32x32 ~0.45).
+    auto fill = [](long long ctas) {          // CTAs on one SM share its DMMA pipe
+        const long long per_sm = (ctas + 147) / 148;
+        return (double)ctas / (double)(per_sm * 148);
+    };
+    const long long c64 = (long long)((a.N + 63) / 64) * ((a.M + 63) / 64);
+    const long long c32 = (long long)((a.N + 31) / 32) * ((a.M + 31) / 32);
+    const double pad64 = (double)a.M / (double)(((a.M + 63) / 64) * 64);
+    const double pad32 = (double)a.M / (double)(((a.M + 31) / 32) * 32);
+    const double e64 = fill(c64) * 0.9 * pad64, e32 = fill(c32) * 0.45 * pad32;
+    if (a.M > 16 && e64 >= e32) return launch_t<64, 64>(a, stream);
     if (a.M > 16) return launch_t<32, 32>(a, stream);
     return launch_t<16, 32>(a, stream);
 }
