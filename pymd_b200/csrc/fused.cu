@@ -648,7 +648,7 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
     fp.nd = c->nd; fp.ks = (c->nd + 3) / 4; fp.ldb = c->ldb; fp.ldn = c->ldn; fp.nbath = c->nbath;
     fp.nmd = c->nmd; fp.ncon = c->ncon; fp.dt = c->dt;
     fp.p = d.p; fp.q = d.q; fp.ps = d.ps; fp.qs = d.qs; fp.etot = d.etot; fp.fpotn = d.fpotn; fp.samef = d.samef;
-    fp.dyn = c->d_dyn; fp.mp = c->d_mp; fp.con3 = c->d_con3;
+    fp.dyn = c->d_dyn; fp.mp = c->d_mp;
     // q-coupled operator scattered to nd x nd (built once)
     bool hasq = fp.aq >= 0;
     if (hasq && !c->d_aqT) {
@@ -684,6 +684,7 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
         PYMD_CUDA_CHECK(cudaMalloc(&c->d_con3, c3.size() * sizeof(double)));
         PYMD_CUDA_CHECK(cudaMemcpy(c->d_con3, c3.data(), c3.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
+    fp.con3 = c->d_con3;
     for (int b = 0; b < c->nbath; ++b) {
         BathHost& H = c->bath[b];
         FusedBath& B = fp.b[b];
