@@ -7,10 +7,9 @@ namespace {
 
 constexpr int BK = 32;         // K rows per pipeline stage
 constexpr int LDA = BK + 4;    // padded so the A-fragment LDS is bank-conflict free (ld % 16 == 4)
-constexpr int STAGES = 3;
 constexpr int NCOMPUTE = 4;    // DMMA warps, arranged 2 (M) x 2 (N)
 
-template <int BM, int BN>
+template <int BM, int BN, int STAGES>
 struct __align__(16) Smem {
     double A[STAGES][BM][LDA];
     double B[STAGES][BK][BN + 4];
@@ -18,10 +17,10 @@ struct __align__(16) Smem {
     uint64_t empty[STAGES];
 };
 
-template <int BM, int BN>
+template <int BM, int BN, int STAGES>
 __global__ void __launch_bounds__((NCOMPUTE + 1) * 32) gemm_kernel(const GemmArgs g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem<BM, BN>& s = *reinterpret_cast<Smem<BM, BN>*>(smem_raw);
+    Smem<BM, BN, STAGES>& s = *reinterpret_cast<Smem<BM, BN, STAGES>*>(smem_raw);
     constexpr int LDB = BN + 4;
     constexpr int WTM = BM / 2, WTN = BN / 2, MT = WTM / 8, NT = WTN / 8;
     static_assert(MT >= 1 && NT >= 1, "tile too small");
@@ -134,17 +133,17 @@ __global__ void __launch_bounds__((NCOMPUTE + 1) * 32) gemm_kernel(const GemmArg
     }
 }
 
-template <int BM, int BN>
+template <int BM, int BN, int STAGES>
 int launch_t(const GemmArgs& a, cudaStream_t stream) {
     static bool configured = false;
-    const int smem = static_cast<int>(sizeof(Smem<BM, BN>));
+    const int smem = static_cast<int>(sizeof(Smem<BM, BN, STAGES>));
     if (!configured) {
-        PYMD_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BM, BN>,
+        PYMD_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BM, BN, STAGES>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM);
-    gemm_kernel<BM, BN><<<grid, (NCOMPUTE + 1) * 32, smem, stream>>>(a);
+    gemm_kernel<BM, BN, STAGES><<<grid, (NCOMPUTE + 1) * 32, smem, stream>>>(a);
     PYMD_CUDA_CHECK(cudaGetLastError());
     return PYMD_OK;
 }
@@ -169,9 +168,9 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     const double pad64 = (double)a.M / (double)(((a.M + 63) / 64) * 64);
     const double pad32 = (double)a.M / (double)(((a.M + 31) / 32) * 32);
     const double e64 = fill(c64) * 0.9 * pad64, e32 = fill(c32) * 0.45 * pad32;
-    if (a.M > 16 && e64 >= e32) return launch_t<64, 64>(a, stream);
-    if (a.M > 16) return launch_t<32, 32>(a, stream);
-    return launch_t<16, 32>(a, stream);
+    if (a.M > 16 && e64 >= e32) return launch_t<64, 64, 6>(a, stream);   // one CTA per SM: deep pipeline hides the TMA latency
+    if (a.M > 16) return launch_t<32, 32, 3>(a, stream);
+    return launch_t<16, 32, 3>(a, stream);
 }
 
 }  // namespace pymd
