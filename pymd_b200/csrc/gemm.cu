@@ -1,4 +1,4 @@
-// See gemm.cuh.  One producer warp (TMA bulk row copies) + four DMMA warps per CTA.
+// See gemm.cuh.  Producer warps (TMA bulk row copies) + DMMA warps per CTA, mbarrier pipeline.
 #include "gemm.cuh"
 
 namespace pymd {
@@ -7,8 +7,11 @@ namespace {
 
 constexpr int BK = 32;         // K rows per pipeline stage
 constexpr int LDA = BK + 4;    // padded so the A-fragment LDS is bank-conflict free (ld % 16 == 4)
-constexpr int NCOMPUTE = 4;    // DMMA warps, arranged 2 (M) x 2 (N)
 
+// CTA tile BM x BN, compute warps arranged WM (M) x WN (N), NPROD producer warps.
+// cp.async.bulk is a uniform-datapath instruction: a warp whose lanes copy different rows issues
+// them one lane at a time (~65 clk each, measured), so the copies of a stage are spread over
+// NPROD producer warps to keep the issue time below the DMMA time of the stage.
 template <int BM, int BN, int STAGES>
 struct __align__(16) Smem {
     double A[STAGES][BM][LDA];
@@ -17,20 +20,21 @@ struct __align__(16) Smem {
     uint64_t empty[STAGES];
 };
 
-template <int BM, int BN, int STAGES>
-__global__ void __launch_bounds__((NCOMPUTE + 1) * 32) gemm_kernel(const GemmArgs g) {
+template <int BM, int BN, int STAGES, int WM, int WN, int NPROD>
+__global__ void __launch_bounds__((WM * WN + NPROD) * 32) gemm_kernel(const GemmArgs g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<BM, BN, STAGES>& s = *reinterpret_cast<Smem<BM, BN, STAGES>*>(smem_raw);
     constexpr int LDB = BN + 4;
-    constexpr int WTM = BM / 2, WTN = BN / 2, MT = WTM / 8, NT = WTN / 8;
-    static_assert(MT >= 1 && NT >= 1, "tile too small");
+    constexpr int NCOMPUTE = WM * WN;
+    constexpr int WTM = BM / WM, WTN = BN / WN, MT = WTM / 8, NT = WTN / 8;
+    static_assert(MT >= 1 && NT >= 1 && WTM % 8 == 0 && WTN % 8 == 0, "bad warp tile");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(&s.full[i], 1);
+            mbar_init(&s.full[i], NPROD);
             mbar_init(&s.empty[i], NCOMPUTE);
         }
         mbar_fence_init();
@@ -40,8 +44,9 @@ __global__ void __launch_bounds__((NCOMPUTE + 1) * 32) gemm_kernel(const GemmArg
     int ntiles = 0;
     for (int sg = 0; sg < g.nseg; ++sg) ntiles += (g.seg_hi[sg] - g.seg_lo[sg] + BK - 1) / BK;
 
-    if (warp == NCOMPUTE) {
-        // ------------------------------ producer ------------------------------
+    if (warp >= NCOMPUTE) {
+        // ------------------------------ producers ------------------------------
+        const int pw = warp - NCOMPUTE;
         const int ncols = min(BN, g.N - n0);
         const uint32_t xbytes = static_cast<uint32_t>(ncols) * 8u;
         int it = 0;
@@ -51,23 +56,26 @@ __global__ void __launch_bounds__((NCOMPUTE + 1) * 32) gemm_kernel(const GemmArg
                 if (it >= STAGES) mbar_wait(&s.empty[st], ((it / STAGES) - 1) & 1);
                 const int kvalid = min(BK, g.seg_hi[sg] - k0);
                 uint32_t mybytes = 0;
-                // X rows: one bulk copy per valid row, zero fill for the rest of the tile.
-                if (lane < kvalid) {
-                    const int k = k0 + lane;
-                    const long long row = g.x_idx ? g.x_idx[k] : k;
-                    bulk_g2s(&s.B[st][lane][0], g.x_base + row * g.x_ld + n0, xbytes, &s.full[st]);
-                    mybytes += xbytes;
-                } else {
-                    for (int c = 0; c < BN; ++c) s.B[st][lane][c] = 0.0;
-                }
-                // A rows: BK contiguous doubles each.
-                for (int r = lane; r < BM; r += 32) {
-                    const int m = m0 + r;
-                    if (m < g.M) {
-                        const double* src = g.a_base + (long long)(m % g.a_mod) * g.a_ld +
-                                            (long long)(m / g.a_mod) * g.a_ls + g.seg_aoff[sg] + k0;
-                        bulk_g2s(&s.A[st][r][0], src, BK * 8, &s.full[st]);
-                        mybytes += BK * 8;
+                // rows of the stage: [0, BK) are X rows, [BK, BK + BM) are A rows; dealt to the
+                // producer lanes round-robin
+                for (int e = pw * 32 + lane; e < BK + BM; e += NPROD * 32) {
+                    if (e < BK) {
+                        if (e < kvalid) {
+                            const int k = k0 + e;
+                            const long long row = g.x_idx ? g.x_idx[k] : k;
+                            bulk_g2s(&s.B[st][e][0], g.x_base + row * g.x_ld + n0, xbytes, &s.full[st]);
+                            mybytes += xbytes;
+                        } else {
+                            for (int c = 0; c < BN; ++c) s.B[st][e][c] = 0.0;   // rows past the K range are zero
+                        }
+                    } else {
+                        const int r = e - BK, m = m0 + r;
+                        if (m < g.M) {
+                            const double* src = g.a_base + (long long)(m % g.a_mod) * g.a_ld +
+                                                (long long)(m / g.a_mod) * g.a_ls + g.seg_aoff[sg] + k0;
+                            bulk_g2s(&s.A[st][r][0], src, BK * 8, &s.full[st]);
+                            mybytes += BK * 8;
+                        }
                     }
                 }
                 uint32_t total = mybytes;
@@ -81,7 +89,7 @@ __global__ void __launch_bounds__((NCOMPUTE + 1) * 32) gemm_kernel(const GemmArg
     }
 
     // ------------------------------ DMMA warps ------------------------------
-    const int wm = warp >> 1, wn = warp & 1;
+    const int wm = warp / WN, wn = warp % WN;
     const int lr = lane >> 2, lc = lane & 3;
     double acc[MT][NT][2];
 #pragma unroll
@@ -133,17 +141,17 @@ __global__ void __launch_bounds__((NCOMPUTE + 1) * 32) gemm_kernel(const GemmArg
     }
 }
 
-template <int BM, int BN, int STAGES>
+template <int BM, int BN, int STAGES, int WM, int WN, int NPROD>
 int launch_t(const GemmArgs& a, cudaStream_t stream) {
     static bool configured = false;
     const int smem = static_cast<int>(sizeof(Smem<BM, BN, STAGES>));
     if (!configured) {
-        PYMD_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BM, BN, STAGES>,
+        PYMD_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BM, BN, STAGES, WM, WN, NPROD>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM);
-    gemm_kernel<BM, BN, STAGES><<<grid, (NCOMPUTE + 1) * 32, smem, stream>>>(a);
+    gemm_kernel<BM, BN, STAGES, WM, WN, NPROD><<<grid, (WM * WN + NPROD) * 32, smem, stream>>>(a);
     PYMD_CUDA_CHECK(cudaGetLastError());
     return PYMD_OK;
 }
@@ -168,9 +176,9 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     const double pad64 = (double)a.M / (double)(((a.M + 63) / 64) * 64);
     const double pad32 = (double)a.M / (double)(((a.M + 31) / 32) * 32);
     const double e64 = fill(c64) * 0.9 * pad64, e32 = fill(c32) * 0.45 * pad32;
-    if (a.M > 16 && e64 >= e32) return launch_t<64, 64, 6>(a, stream);   // one CTA per SM: deep pipeline hides the TMA latency
-    if (a.M > 16) return launch_t<32, 32, 3>(a, stream);
-    return launch_t<16, 32, 3>(a, stream);
+    if (a.M > 16 && e64 >= e32) return launch_t<64, 64, 5, 2, 4, 4>(a, stream);   // one CTA per SM: 8 DMMA warps + 4 producer warps
+    if (a.M > 16) return launch_t<32, 32, 3, 2, 2, 1>(a, stream);
+    return launch_t<16, 32, 3, 2, 2, 1>(a, stream);
 }
 
 }  // namespace pymd
