@@ -1,0 +1,381 @@
+#!/usr/bin/env python3
+"""Benchmark of the generalized-Langevin stepping path (BASELINE.json metric: trajectory-steps/s).
+
+  python bench.py --gpus N --steps K --warmup W              # our CUDA path, one rank per GPU
+  python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path on host cores
+
+Workload (configs[1] of BASELINE.json, "cfg2"): AuBZ-like junction, nd = 60 system dofs, electron
+bath on all 60 dofs at finite bias (all five coupling matrices), left/right phonon baths on 15 dofs
+each with a 100-step memory kernel, one constraint vector, dt = 1, nmd = 2^15, an ensemble of 4096
+trajectories per GPU (weak scaling).  Synthetic junction (pymd_b200/synth.py): the reference's
+inputs (EPH.nc, ...) do not ship.
+
+One bench "step" = one piece of 256 md.vv steps for the whole resident ensemble (md.Run advances in
+pieces of nmd/npie steps, npie = 128, reference md.py:595-598).  `value` = trajectory-steps/s with
+the coloured noise already resident in HBM; `e2e` = the same metric through the md/phbath/ebath
+class API from host inputs: upload of the spectral factors, noise generation, 2^15 steps with
+trajectories saved, power spectra, device->host read of spectra and currents, (+ NCCL all-reduce).
+"""
+import os
+
+for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+    os.environ.setdefault(_v, "1")
+
+import argparse
+import json
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(nd=60, ncl=15, ncr=15, seed=4, dt=1.0, T=300.0, dT=10.0, ml=100, nw=200, hwcut=0.03, bias=0.5)
+PIECE = 256
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def _cpu_modules():
+    """The reference itself (oracle/_ref, built from /root/reference by oracle/build_ref.py) when
+    it travelled with the snapshot, else the oracle port."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    warnings.filterwarnings("ignore", category=SyntaxWarning)
+    os.environ["PYMD_REF_QUIET"] = "1"
+    if os.path.exists(os.path.join(ref, "md.py")):
+        sys.path.insert(0, ref)
+        import md as rmd, phbath as rph, ebath as reb   # noqa: E401
+        return "reference", rmd.md, rph.phbath, reb.ebath
+    from oracle import pymd_oracle as O
+    return "port", O.md, O.phbath, O.ebath
+
+
+def _cpu_system(nmd_cpu, seed):
+    from pymd_b200 import synth
+    kind, MD, PH, EB = _cpu_modules()
+    c = CFG
+    j = synth.synth(c["nd"], c["ncl"], c["ncr"], seed=c["seed"], constraint=True)
+    m = MD(c["dt"], nmd_cpu, c["T"], axyz=j.axyz, harmonic=True, dyn=j.DynMat, savepq=False, constr=j.constr.copy())
+    eb = EB(j.cats_e, c["T"], c["dt"], nmd_cpu, wmax=1.0, nw=500, bias=c["bias"], efric=j.efric, exim=j.exim,
+            exip=j.exip, zeta1=j.zeta1, zeta2=j.zeta2)
+    pl = PH(c["T"] + c["dT"] / 2, j.cats_l, c["hwcut"], c["nw"], c["dt"], nmd_cpu, ml=c["ml"], sig=j.SigL, gwl=j.wl)
+    pr = PH(c["T"] - c["dT"] / 2, j.cats_r, c["hwcut"], c["nw"], c["dt"], nmd_cpu, ml=c["ml"], sig=j.SigR, gwl=j.wl)
+    pl.gmem(); pr.gmem()
+    for b in (eb, pl, pr):
+        m.AddBath(b)
+    np.random.seed(seed)
+    for b in m.baths:
+        b.gnoi()
+    m.initialise()
+    m.ResetHis()
+    return kind, m
+
+
+def _cpu_worker(args):
+    """One host core: `warm` untimed then `nsteps` timed md.vv steps of ONE trajectory."""
+    nsteps, warm, nmd_cpu, seed = args
+    kind, m = _cpu_system(nmd_cpu, seed)
+    for _ in range(warm):
+        m.vv()
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        m.vv()
+    return kind, nsteps, time.perf_counter() - t0
+
+
+def cpu_throughput(nsteps, warm, cores=None, nmd_cpu=256):
+    """Aggregate trajectory-steps/s of one reference process per host core."""
+    import multiprocessing as mp
+    cores = cores or min(os.cpu_count() or 1, 64)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(nsteps, warm, nmd_cpu, 1000 + i) for i in range(cores)])
+    kind = res[0][0]
+    tmax = max(r[2] for r in res)
+    return dict(value=sum(r[1] for r in res) / tmax, cores=cores, kind=kind, seconds=tmax,
+                per_core=float(np.mean([r[1] / r[2] for r in res])))
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = a.steps + a.warmup
+    piece = max(8, min(64, 3000 // max(total, 1)))
+    r = cpu_throughput(a.steps * piece, a.warmup * piece)
+    sample = ("%d md.vv steps of one trajectory per core after %d warm-up steps, cfg2 shape, noise table nmd=256 "
+              "(the loop cost does not depend on nmd)" % (a.steps * piece, a.warmup * piece))
+    out = dict(impl="reference", metric="trajectory_steps_per_s", value=r["value"], unit="trajectory-steps/s",
+               n_gpus=a.gpus, steps=a.steps, warmup=a.warmup, ms_per_step=r["seconds"] * 1e3 / max(a.steps, 1),
+               higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+               config=workload_config(a), gpu_launches=0,
+               cpu_baseline=dict(value=r["value"], unit="trajectory-steps/s", cores=r["cores"], kind=r["kind"],
+                                 sample=sample, per_core=r["per_core"]),
+               e2e=dict(value=r["value"], unit="trajectory-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def workload_config(a):
+    return dict(workload="cfg2 AuBZ-like junction: nd=60, electron bath nc=60 at bias 0.5 eV (5 matrices), "
+                         "2 phonon baths nc=15 ml=100, 1 constraint, dt=1, nmd=%d" % a.nmd,
+                batch_per_gpu=a.batch, md_steps_per_step=PIECE, nmd=a.nmd,
+                l2="inputs exceed L2: each step streams %d MB of noise rows (%.0f GB resident), 126 MB L2"
+                   % (PIECE * 90 * a.batch * 8 // 2 ** 20, a.nmd * 90 * a.batch * 8 / 2 ** 30))
+
+
+def build(batch, nmd, traj0, savepq, seed, mode=0):
+    from pymd_b200 import synth
+    from pymd_b200.ebath import ebath
+    from pymd_b200.md import md
+    from pymd_b200.phbath import phbath
+    c = CFG
+    j = synth.synth(c["nd"], c["ncl"], c["ncr"], seed=c["seed"], constraint=True)
+    m = md(c["dt"], nmd, c["T"], axyz=j.axyz, harmonic=True, dyn=j.DynMat, savepq=savepq, constr=j.constr.copy(),
+           batch=batch, seed=seed, traj0=traj0, step_mode=mode, npie=nmd // PIECE)
+    m.write_files = False
+    eb = ebath(j.cats_e, c["T"], c["dt"], nmd, wmax=1.0, nw=500, bias=c["bias"], efric=j.efric, exim=j.exim,
+               exip=j.exip, zeta1=j.zeta1, zeta2=j.zeta2)
+    pl = phbath(c["T"] + c["dT"] / 2, j.cats_l, c["hwcut"], c["nw"], c["dt"], nmd, ml=c["ml"], sig=j.SigL, gwl=j.wl)
+    pr = phbath(c["T"] - c["dT"] / 2, j.cats_r, c["hwcut"], c["nw"], c["dt"], nmd, ml=c["ml"], sig=j.SigR, gwl=j.wl)
+    pl.gmem(); pr.gmem()
+    for b in (eb, pl, pr):
+        m.AddBath(b)
+    return m
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 7]
+        if not rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(rows[0][1]), reasons=reasons, samples=len(rows))
+
+
+def algorithmic_flops():
+    """flops per trajectory-step, split by the kernel that executes them."""
+    c = CFG
+    nd, nc, ml, nce = c["nd"], 15, c["ml"], c["nd"]
+    intra = (8 + 1) / 2.0                                  # in-block taps handled by the fused kernel (block of 8)
+    tail = 2 * (2 * nc * nc * (ml - 1 - intra))            # two phonon baths, pre-block taps
+    fused = 2 * nd * nd + 6 * 2 * nce * nce + 2 * (3 * 2 * nc * nc + 2 * nc * nc * intra)
+    total = 2 * nd * nd + 2 * (2 * (ml + 2) * nc * nc) + 6 * 2 * nce * nce
+    return dict(total=total, tail=tail, fused=fused)
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if local == 0:
+        ge.build()                      # no-op when the in-tree library is current
+    else:
+        for _ in range(600):
+            if os.path.exists(ge.LIB) and not ge._stale():
+                break
+            time.sleep(0.5)
+    from pymd_b200 import _lib, ensemble
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    B, nmd = a.batch, a.nmd
+    peaks = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peaks.json"))) if os.path.exists(
+        os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")) else None
+    p64 = max(r["tflops"] for r in peaks["dmma"]) if peaks else 37.0
+
+    # ------------------------------------------------------------ resident-ensemble throughput
+    t_setup = time.time()
+    m = build(B, nmd, rank * B, False, a.seed, a.mode)
+    m.initialise()
+    m.ResetHis()
+    for b in m.baths:
+        b.gnoi()
+    torch.cuda.synchronize()
+    t_setup = time.time() - t_setup
+    for _ in range(a.warmup):
+        m.steps(PIECE)
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    l0 = _lib.load().pymd_launch_count(m._ctx)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        m.steps(PIECE)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = _lib.load().pymd_launch_count(m._ctx) - l0
+    clocks = sampler.finish()
+    finite = bool(torch.isfinite(m._p).all().item())
+    value = B * world * PIECE * a.steps / (ms * 1e-3)
+
+    # per-kernel device time of the same loop, CUDA events on the launching stream
+    import ctypes
+    _lib.call("pymd_profile_enable", m._ctx, 1)
+    m.steps(PIECE)
+    ms4 = (ctypes.c_double * 4)()
+    cnt4 = (ctypes.c_longlong * 4)()
+    _lib.call("pymd_profile_read", m._ctx, ctypes.addressof(ms4), ctypes.addressof(cnt4))
+    _lib.call("pymd_profile_enable", m._ctx, 0)
+    names = ["tail_gemm", "fused_step", "other_gemm", "stage_kernels"]
+    kern = {names[i]: dict(ms=ms4[i], launches=int(cnt4[i])) for i in range(4) if cnt4[i]}
+    fl = algorithmic_flops()
+    tot_ms = sum(v["ms"] for v in kern.values())
+    roof = None
+    per_kernel = {}
+    for key, fkey in (("fused_step", "fused"), ("tail_gemm", "tail")):
+        if key in kern:
+            k = kern[key]
+            ach = fl[fkey] * B * PIECE / (k["ms"] * 1e-3) / 1e12
+            per_kernel[key] = dict(achieved=ach, frac=ach / p64, share_of_step=k["ms"] / tot_ms,
+                                   us_per_launch=1e3 * k["ms"] / k["launches"], launches_per_step=k["launches"])
+    if per_kernel:
+        dom = max(per_kernel, key=lambda n: per_kernel[n]["share_of_step"])
+        roof = dict(bound="tensor", kernel=dom, achieved=per_kernel[dom]["achieved"], peak=p64, unit="TFLOP/s",
+                    frac=per_kernel[dom]["frac"], traffic=None,
+                    peak_source="FP64 DMMA.8x8x4 peak measured on this pool (profiles/r01_fp64_peaks.json); "
+                                "MEASURED_PEAKS.json has no FP64 entry (cuBLAS DGEMM 8192^3: 35.45 TFLOP/s)",
+                    kernels=per_kernel,
+                    whole_step_frac=(value / world) * fl["total"] / (p64 * 1e12),
+                    flops_per_trajectory_step=fl)
+    del m
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------ end to end through the class API
+    e2e = None
+    if not a.no_e2e:
+        Be = min(a.e2e_batch, B)
+        nsub = B // Be
+        me = build(Be, nmd, rank * B, True, a.seed + 1, a.mode)
+        for b in me.baths:
+            b.spectral_factors()                       # host setup (eigh per frequency), as the reference does once
+        h2d = sum(b.spectral_factors().L.nbytes for b in me.baths)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        psum = np.zeros(nmd); p2sum = np.zeros(nmd); cur = np.zeros(len(me.baths)); ek = 0.0
+        for sub in range(nsub):
+            me.traj0 = rank * B + sub * Be
+            for b in me.baths:
+                b._traj0 = me.traj0
+            me.initialise()
+            me.ResetHis()
+            for b in me.baths:
+                b.gnoi()
+            me.ResetSavepq(True)
+            me.steps(nmd)
+            me.GetPower()
+            psum += me.power_sum; p2sum += me.power2_sum
+            cur += np.array([float(b._cur_dev[:, :Be].mean().item()) * Be for b in me.baths])
+            ek += float(me._etot[:, :Be].mean().item()) * Be
+        res = ensemble.allreduce_sums([psum, p2sum, cur, np.array([ek])])
+        torch.cuda.synchronize()
+        barrier()
+        sec = max_over_ranks(time.perf_counter() - t0)
+        d2h = 2 * nmd * 8 + (len(me.baths) + 1) * 8
+        e2e = dict(value=B * world * nmd / sec, unit="trajectory-steps/s", h2d_bytes_per_step=int(h2d),
+                   d2h_bytes_per_step=int(d2h), seconds=sec, sub_ensembles=nsub, sub_batch=Be,
+                   step="one sub-ensemble Run segment: factors H2D + noise generation + %d md steps with savepq + "
+                        "power spectra + D2H" % nmd,
+                   mean_current_nW=[float(x) * 243414. / (B * world) for x in res[2]],
+                   finite=bool(np.isfinite(res[0]).all() and np.isfinite(res[1]).all()))
+        del me
+        torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------ CPU baseline (rank 0, N == 1)
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        r = cpu_throughput(a.cpu_steps, 8)
+        cpu = dict(value=r["value"], unit="trajectory-steps/s", cores=r["cores"], kind=r["kind"],
+                   per_core=r["per_core"],
+                   sample="%d md.vv steps of one trajectory per core (one process per core), cfg2 shape, "
+                          "noise table nmd=256" % a.cpu_steps)
+
+    if rank == 0:
+        out = dict(metric="trajectory_steps_per_s", value=value, unit="trajectory-steps/s", n_gpus=world,
+                   steps=a.steps, warmup=a.warmup, ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak",
+                   vs_baseline=None, dtype="f64", data="synthetic", config=workload_config(a), clocks=clocks,
+                   gpu_launches=int(launches), e2e=e2e, roofline=roof, cpu_baseline=cpu,
+                   setup_s=t_setup, finite=finite, step_mode=a.mode)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="trajectories per GPU")
+    ap.add_argument("--nmd", type=int, default=2 ** 15)
+    ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 per-step pipeline, 2 fused")
+    ap.add_argument("--seed", type=int, default=20240)
+    ap.add_argument("--e2e-batch", type=int, default=2048)
+    ap.add_argument("--cpu-steps", type=int, default=1024)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    if a.warmup < 3:
+        a.warmup = 3
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

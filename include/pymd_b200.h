@@ -92,17 +92,25 @@ int pymd_history_set(pymd_ctx* ctx, int b, const double* in_dev, int nrows, void
 int pymd_step(pymd_ctx* ctx, long long t0, int nsteps, int mode, void* stream);
 /* number of kernel launches issued by this ctx so far */
 long long pymd_launch_count(const pymd_ctx* ctx);
+/* Per-kernel-class device timing with CUDA events on the launching stream (measurement aid for
+ * bench.py's roofline; adds an event pair per launch while enabled).  Classes: 0 = memory-kernel
+ * tail GEMM, 1 = fused step kernel, 2 = other tensor-core GEMMs, 3 = elementwise stage kernels.
+ * pymd_profile_read synchronises, writes the accumulated milliseconds and launch counts of the 4
+ * classes and clears them. */
+int pymd_profile_enable(pymd_ctx* ctx, int on);
+int pymd_profile_read(pymd_ctx* ctx, double* ms4, long long* count4);
 
 /* ---- noise generation: noise.phnoise / noise.enoise (noise.py:38-88, 135-190) --------
  * factors: L[f] = U_f diag(sqrt(max(lambda_f,0))) for f = 0..nmd/2, dev [nf][nc][nc]
  * (real part; imaginary part NULL for phonon baths).  xi: standard normals dev
  * [nf][nc][ldb].  Computes X_f = L_f xi_f, the Hermitian mirror (noise.py:74-81), the
  * w->t transform myfft.iFourier1D (myfft.py:35-52: fft/(nmd*dt)) and keeps the real part.
- * out: dev [nmd][nc][ldb].  work: dev scratch of pymd_noise_work_bytes(). */
-size_t pymd_noise_work_bytes(int nmd, int nc, int ldb);
+ * out: dev [nmd][nc][ldb]; only the component rows i0 <= i < i1 are produced by one call, so the
+ * FFT scratch (pymd_noise_work_bytes(nmd, i1-i0, ldb)) can be kept small for large ensembles. */
+size_t pymd_noise_work_bytes(int nmd, int nrows, int ldb);
 int pymd_noise_generate(const double* lre_dev, const double* lim_dev, const double* xi_dev,
-                        int nmd, int nc, int ldb, double dt, double* out_dev, void* work_dev,
-                        void* stream);
+                        int nmd, int nc, int ldb, int i0, int i1, double dt, double* out_dev,
+                        void* work_dev, void* stream);
 
 /* N.random.normal replacement (noise.py:282): counter-based Philox4x32-10 + Box-Muller.
  * Element (row r, trajectory n) depends only on (seed, stream_id, r, traj0+n): results do

@@ -327,7 +327,10 @@ static int gemm_plain(pymd_ctx* c, const double* A, int lda, int M, int K, const
     g.nseg = 1; g.seg_lo[0] = 0; g.seg_hi[0] = K; g.seg_aoff[0] = 0;
     g.alpha = alpha; g.accumulate = accumulate;
     c->launches++;
-    return launch_gemm(g, st);
+    prof_begin(c, 2, st);
+    const int rc = launch_gemm(g, st);
+    prof_end(c, st);
+    return rc;
 }
 
 // out[s][i][n] = dt * sum_{lag>=0} K[s + koff + lag][i][:] . ring(newest - lag)[:][n],  s < T
@@ -359,7 +362,10 @@ int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t s
     }
     g.alpha = c->dt; g.accumulate = 0;
     c->launches++;
-    return launch_gemm(g, st);
+    prof_begin(c, 0, st);
+    const int rc = launch_gemm(g, st);
+    prof_end(c, st);
+    return rc;
 }
 
 static int compute_fpotc(pymd_ctx* c, cudaStream_t st) {
@@ -399,7 +405,9 @@ static int generic_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) 
                 return rc;
             slots.s[b] = H.ml > 1 ? (int)(H.hcount % H.R) : 0;
         }
+        prof_begin(c, 3, st);
         stage_a_kernel<<<grd, blk, 0, st>>>(d, tn, slots);
+        prof_end(c, st);
         c->launches++;
         for (int b = 0; b < c->nbath; ++b)
             if (c->bath[b].ml > 1) c->bath[b].hcount++;
@@ -415,9 +423,13 @@ static int generic_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) 
                 return rc;
         }
         if ((rc = gemm_plain(c, c->d_mp, c->ldn, c->nd, c->nd, d.ph, nullptr, d.h, 1.0, 0, st))) return rc;
+        prof_begin(c, 3, st);
         stage_b_kernel<<<grd, blk, 0, st>>>(d, tn1);
+        prof_end(c, st);
         if ((rc = gemm_plain(c, c->d_mp, c->ldn, c->nd, c->nd, d.p1, nullptr, d.h, 1.0, 0, st))) return rc;
+        prof_begin(c, 3, st);
         stage_c_kernel<<<grd, blk, 0, st>>>(d);
+        prof_end(c, st);
         c->launches += 2;
         if (c->ncon > 0 && (rc = compute_fpotc(c, st))) return rc;
         for (int b = 0; b < c->nbath; ++b) std::swap(d.b[b].tail_cur, d.b[b].tail_next);
@@ -610,6 +622,29 @@ int pymd_step(pymd_ctx* c, long long t0, int nsteps, int mode, void* stream) {
 }
 
 long long pymd_launch_count(const pymd_ctx* c) { return c ? c->launches : 0; }
+
+int pymd_profile_enable(pymd_ctx* c, int on) {
+    PYMD_REQUIRE(c, "profile_enable: null ctx");
+    c->prof = on != 0;
+    return PYMD_OK;
+}
+
+int pymd_profile_read(pymd_ctx* c, double* ms4, long long* count4) {
+    PYMD_REQUIRE(c && ms4 && count4, "profile_read: null argument");
+    PYMD_CUDA_CHECK(cudaDeviceSynchronize());
+    for (int i = 0; i < 4; ++i) { ms4[i] = 0.0; count4[i] = 0; }
+    for (auto& r : c->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && r.cls >= 0 && r.cls < 4) {
+            ms4[r.cls] += ms;
+            count4[r.cls]++;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    c->prof_recs.clear();
+    return PYMD_OK;
+}
 
 int pymd_gemm(const double* a, int lda, const double* x, double* y, int M, int K, int ldb, double alpha,
               int accumulate, void* stream) {

@@ -73,4 +73,23 @@ struct pymd_ctx {
     pymd::StepDev sd{};
     bool finalized = false, fpot_valid = false, tail_valid = false, fpotc_valid = false;
     long long launches = 0;
+    // optional per-launch CUDA-event timing (pymd_profile_enable)
+    struct ProfRec { int cls; cudaEvent_t e0, e1; };
+    bool prof = false;
+    std::vector<ProfRec> prof_recs;
 };
+
+namespace pymd {
+inline void prof_begin(pymd_ctx* c, int cls, cudaStream_t st) {
+    if (!c->prof) return;
+    pymd_ctx::ProfRec r;
+    r.cls = cls;
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+    c->prof_recs.push_back(r);
+}
+inline void prof_end(pymd_ctx* c, cudaStream_t st) {
+    if (c->prof && !c->prof_recs.empty()) cudaEventRecord(c->prof_recs.back().e1, st);
+}
+}  // namespace pymd

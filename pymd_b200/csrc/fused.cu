@@ -583,12 +583,21 @@ size_t plan(const pymd_ctx* c, int NT, FusedParams& fp) {
 }
 
 int pick_nt(const pymd_ctx* c, FusedParams& fp) {
-    // largest trajectory tile that fits in 227 KB and divides the ensemble
+    // trajectory tile 8*NT per CTA: trade SM fill (one CTA per SM) against per-CTA efficiency
+    // (larger tiles amortise barriers and give the DMMA pipe more independent chains)
+    int best = 0;
+    double best_score = -1.0;
     for (int NT : {4, 2, 1}) {
         if (c->ldb % (8 * NT)) continue;
-        if (plan(c, NT, fp) <= 227 * 1024) return NT;
+        if (plan(c, NT, fp) > 227 * 1024) continue;
+        const long long ctas = c->ldb / (8 * NT);
+        const long long waves = (ctas + 147) / 148;
+        const double fill = (double)ctas / (double)(waves * 148);
+        const double eff = NT == 4 ? 1.0 : (NT == 2 ? 0.75 : 0.5);
+        if (fill * eff > best_score) { best_score = fill * eff; best = NT; }
     }
-    return 0;
+    if (best) plan(c, best, fp);
+    return best;
 }
 
 void choose_roles(const pymd_ctx* c, FusedParams& fp) {
@@ -712,11 +721,13 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
         fp.t0 = t0 + done;
         fp.nsteps = ns;
         fp.carry_valid = c->fpot_valid ? 1 : 0;
+        prof_begin(c, 1, st);
         switch (NT) {
             case 4: rc = launch_nt<4>(fp, smem, grid, hasq, c->ncon > 0, st); break;
             case 2: rc = launch_nt<2>(fp, smem, grid, hasq, c->ncon > 0, st); break;
             default: rc = launch_nt<1>(fp, smem, grid, hasq, c->ncon > 0, st);
         }
+        prof_end(c, st);
         if (rc) return rc;
         c->launches++;
         for (int b = 0; b < c->nbath; ++b)

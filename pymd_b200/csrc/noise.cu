@@ -149,35 +149,32 @@ using namespace pymd;
 
 extern "C" {
 
-size_t pymd_noise_work_bytes(int nmd, int nc, int ldb) {
-    return (size_t)(nmd / 2) * nc * ldb * sizeof(double2);
+size_t pymd_noise_work_bytes(int nmd, int nrows, int ldb) {
+    return 2 * (size_t)(nmd / 2) * nrows * ldb * sizeof(double2);
 }
 
 int pymd_noise_generate(const double* lre, const double* lim, const double* xi, int nmd, int nc, int ldb,
-                        double dt, double* out, void* work, void* stream) {
+                        int i0, int i1, double dt, double* out, void* work, void* stream) {
     PYMD_REQUIRE(lre && xi && out && work, "noise_generate: null argument");
     PYMD_REQUIRE(nmd >= 4 && (nmd & (nmd - 1)) == 0, "noise_generate: nmd=%d must be a power of two >= 4", nmd);
     PYMD_REQUIRE(nc > 0 && ldb > 0 && ldb % 32 == 0, "noise_generate: nc=%d ldb=%d", nc, ldb);
+    PYMD_REQUIRE(0 <= i0 && i0 < i1 && i1 <= nc, "noise_generate: row range [%d, %d) of %d", i0, i1, nc);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int half = nmd / 2;
+    const int half = nmd / 2, rows = i1 - i0;
     const double2* twN = twiddle_table(nmd);
     PYMD_REQUIRE(twN, "noise_generate: twiddle table allocation failed");
-    // buffer choreography: the last pass must read `work` and write `out` (see fft.cuh)
-    const int np = fft_num_passes(half);
-    double2* W = static_cast<double2*>(work);
-    double2* O = reinterpret_cast<double2*>(out);
-    double2* zbuf = (np % 2) ? W : O;
-    double2* bufA = (np % 2) ? O : W;
-    double2* bufB = (np % 2) ? W : O;
+    // Z goes to W0; the passes ping-pong W1, W0, W1, ...; the last one writes the real rows of `out`
+    double2* W0 = static_cast<double2*>(work);
+    double2* W1 = W0 + (size_t)half * rows * ldb;
     dim3 grid(half / 2 + 1, ldb / SX), blk(SX, SY);
-    shape_kernel<<<grid, blk, 0, st>>>(lre, lim, xi, nmd, nc, ldb, 0, nc, twN, zbuf);
+    shape_kernel<<<grid, blk, 0, st>>>(lre, lim, xi, nmd, nc, ldb, i0, i1, twN, W0);
     PYMD_CUDA_CHECK(cudaGetLastError());
     FftPlan p{};
-    p.n = half; p.cols = (long long)nc * ldb; p.sign = -1;
+    p.n = half; p.cols = (long long)rows * ldb; p.sign = -1;
     p.load = LOAD_C; p.store = STORE_REAL_ROWS;
-    p.src_ld = p.cols; p.dst_ld = p.cols;
+    p.src_ld = p.cols; p.dst_ld = (long long)nc * ldb;
     p.scale = 1.0 / ((double)nmd * dt);
-    return fft_columns(zbuf, out, bufA, bufB, p, st, nullptr);
+    return fft_columns(W0, out + (size_t)i0 * ldb, W1, W0, p, st, nullptr);
 }
 
 int pymd_philox_normal(double* out, long long rows, int ldb, uint64_t seed, uint32_t stream_id,

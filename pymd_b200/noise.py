@@ -90,6 +90,8 @@ def electron_factors(efric, exim, exip, bias, T, ecut, dt, nmd, classical=False,
 
 
 # ------------------------------------------------------------------ device pipeline
+MAX_WORK_BYTES = 8 << 30     # FFT scratch bound for noise generation
+
 def white_noise(nf, nc, ldb, seed, stream_id, traj0=0, device=None):
     """Standard normals [nf][nc][ldb] from the library's Philox generator (replaces the
     sequential N.random.normal draws of noise.vargau, noise.py:282)."""
@@ -112,9 +114,14 @@ def generate(factors, xi, dt, nmd, out=None):
         if factors.complex else None
     if out is None:
         out = torch.empty((nmd, nc, ldb), dtype=torch.float64, device=dev)
-    work = torch.empty(_lib.load().pymd_noise_work_bytes(nmd, nc, ldb), dtype=torch.uint8, device=dev)
-    _lib.call("pymd_noise_generate", lre.data_ptr(), _lib.ptr(lim), xi.data_ptr(), nmd, nc, ldb, float(dt),
-              out.data_ptr(), work.data_ptr(), _lib.stream_ptr())
+    # component rows are transformed in chunks so that the FFT scratch stays below MAX_WORK_BYTES
+    per_row = _lib.load().pymd_noise_work_bytes(nmd, 1, ldb)
+    rows = max(1, min(nc, MAX_WORK_BYTES // per_row))
+    work = torch.empty(per_row * rows, dtype=torch.uint8, device=dev)
+    for i0 in range(0, nc, rows):
+        i1 = min(nc, i0 + rows)
+        _lib.call("pymd_noise_generate", lre.data_ptr(), _lib.ptr(lim), xi.data_ptr(), nmd, nc, ldb, i0, i1,
+                  float(dt), out.data_ptr(), work.data_ptr(), _lib.stream_ptr())
     return out
 
 
