@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpymd_b200.so")
+LIB_PATH = os.environ.get("PYMD_B200_LIB", os.path.join(_HERE, "libpymd_b200.so"))   # override: debug builds only
 
 _lib = None
 

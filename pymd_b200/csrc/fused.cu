@@ -19,6 +19,8 @@
 //     p.g_b; they are produced as warp-shuffle column reductions into per-warp slots and summed
 //     in a fixed order (deterministic, no atomics).
 #include <algorithm>
+#include <cmath>
+#include <cstdio>
 #include <vector>
 
 #include "engine.cuh"
@@ -34,6 +36,7 @@ constexpr int NDP = 64;      // padded rows (8 per warp)
 constexpr int FT = 8;        // steps per block
 constexpr int MAXKS = 16;    // k-steps of the nd x nd operators (nd <= 64)
 constexpr int FB_MAX = 4;    // baths supported by the fused path
+constexpr int MAXIT = 4;     // work items of each kind per warp
 
 struct FusedBath {
     int nc, ncp, ml, nonlocal, R, slot0, ntap, ldk, direct;       // direct: local remainder bath, noise read straight from HBM
@@ -57,8 +60,10 @@ struct FusedParams {
     double *p, *q, *ps, *qs, *etot, *fpotn;
     int* samef;
     const double *dyn, *mp, *aqT, *con3;      // con3: [3][ncon][nd] = c, D c, AqT c
-    int off_xp0, off_xp1, off_xq, off_curp, off_conp, off_maxp, off_conv;
+    int off_xp0, off_xp1, off_xq, off_curp, off_conp, off_zero, off_conv;
+    double cmax;              // max_i |c_i| of the (single) constraint vector
     int smem_doubles;
+    long long* timing;        // debug: [grid][8] accumulated clock64 deltas per phase (PYMD_FUSED_TIMING)
     FusedBath b[FB_MAX];
 };
 
@@ -68,11 +73,36 @@ __device__ __forceinline__ double colsum8(double v) {     // sum over the 8 lane
     v += __shfl_xor_sync(0xffffffffu, v, 16);
     return v;
 }
-__device__ __forceinline__ double colmax8(double v) {
-    v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 4));
-    v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 8));
-    v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 16));
-    return v;
+// Reduce-scatter over the 8 lanes sharing lane%4 (lr = lane>>2): lane lr returns sum_lanes v[lr].
+// 7 shuffles for 8 column sums instead of 24.
+__device__ __forceinline__ double rs8(const double (&v)[8], int lr) {
+    const bool h4 = lr & 4, h2 = lr & 2, h1 = lr & 1;
+    double k[4], m[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double keep = h4 ? v[i + 4] : v[i], send = h4 ? v[i] : v[i + 4];
+        k[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double keep = h2 ? k[i + 2] : k[i], send = h2 ? k[i] : k[i + 2];
+        m[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const double keep = h1 ? m[1] : m[0], send = h1 ? m[0] : m[1];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 4);
+}
+// 4 values: lanes with (lr>>1) == i return sum_lanes v[i] (both lanes of a pair hold it)
+__device__ __forceinline__ double rs4(const double (&v)[4], int lr) {
+    const bool h4 = lr & 4, h2 = lr & 2;
+    double k[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double keep = h4 ? v[i + 2] : v[i], send = h4 ? v[i] : v[i + 2];
+        k[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    const double keep = h2 ? k[1] : k[0], send = h2 ? k[0] : k[1];
+    double r = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    return r + __shfl_xor_sync(0xffffffffu, r, 4);
 }
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
@@ -164,10 +194,34 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
         aM[k] = ok ? P.mp[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
         aQ[k] = (HASQ && ok) ? P.aqT[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
     }
-    // per-thread bath membership of the owned row: index into the bath's dofs or -1
-    int ip[FB_MAX];
+    // per-thread bath membership of the owned row: index into the bath's dofs or -1; smem offset of
+    // the row's noise-minus-tail entry (a zero row when the dof is not coupled to the bath)
+    int ip[FB_MAX], nbo[FB_MAX];
+    double mrem = 0.0, maq = 0.0;               // 1.0 when the row belongs to the remainder / q-coupled bath
 #pragma unroll
-    for (int b = 0; b < FB_MAX; ++b) ip[b] = (b < nb && live) ? P.b[b].inv_g[row] : -1;
+    for (int b = 0; b < FB_MAX; ++b) {
+        ip[b] = (b < nb && live) ? P.b[b].inv_g[row] : -1;
+        nbo[b] = (ip[b] >= 0 && !P.b[b].direct) ? P.b[b].off_nb + ip[b] * LD + 2 * lc : P.off_zero + 2 * lc;
+        if (ip[b] >= 0 && b == P.rem) mrem = 1.0;
+        if (ip[b] >= 0 && b == P.aq) maq = 1.0;
+    }
+    // static work-item list of this warp: code = b | mt << 4 | j << 8 (heads of the small baths, taps)
+    int hitem[MAXIT], titem[MAXIT], nh = 0, nt = 0;
+    {
+        int item = 0;
+        for (int b = 0; b < nb; ++b) {
+            if (b == P.rem) continue;
+            for (int mt = 0; mt < P.b[b].ncp / 8; ++mt)
+                for (int j = 0; j < NT; ++j, ++item)
+                    if (item % FW == w && nh < MAXIT) hitem[nh++] = b | (mt << 4) | (j << 8);
+        }
+        for (int b = 0; b < nb; ++b) {
+            if (P.b[b].direct) continue;
+            for (int mt = 0; mt < P.b[b].ncp / 8; ++mt)
+                for (int j = 0; j < NT; ++j, ++item)
+                    if (item % FW == w && nt < MAXIT) titem[nt++] = b | (mt << 4) | (j << 8);
+        }
+    }
 
     int xpc = P.off_xp0, xpn = P.off_xp1;      // current / next head buffer (offsets into sm)
     const int xq = P.off_xq;
@@ -179,6 +233,14 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
             const double2 qv = ld2(&P.q[(size_t)row * ldb + col0 + n]);
             st2(&sm[xpc + own + 8 * j], pv.x, pv.y);
             st2(&sm[xq + own + 8 * j], qv.x, qv.y);
+            // p_c(t0) opens the block history and is appended to the HBM ring (functions.rpadleft)
+#pragma unroll
+            for (int b = 0; b < FB_MAX; ++b) {
+                if (ip[b] < 0 || P.b[b].direct) continue;
+                const FusedBath& B = P.b[b];
+                st2(&sm[B.off_hist + ip[b] * LD + n], pv.x, pv.y);
+                if (B.nonlocal) st2(&B.ring[((size_t)B.slot0 * B.ncp + ip[b]) * ldb + col0 + n], pv.x, pv.y);
+            }
         }
     }
     // noise minus tail at time t0: in smem for every bath but a local remainder bath (registers)
@@ -209,10 +271,9 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
     }
     __syncthreads();
 
-    double fpot[NT][2], uq[NT][2], fcor[NT][2];   // -D q, AqT q at the current q; pending constraint correction
+    double fpot[NT][2], uq[NT][2];              // -D q and AqT q at the current q, own rows
     zero_acc<NT>(fpot);
     zero_acc<NT>(uq);
-    zero_acc<NT>(fcor);
     if (HASQ) matvec2<NT>(aD, aQ, ks, sm + xq, LD, fpot, uq, lr, lc);
     else matvec1<NT>(aD, ks, sm + xq, LD, fpot, lr, lc);
 #pragma unroll
@@ -228,79 +289,78 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
             }
         }
     }
-    int nbuf = 0;                           // NB buffer holding noise-minus-tail at time t
+    int nbuf = 0;                               // NB buffer holding noise-minus-tail at time t
+#ifdef PYMD_FUSED_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#define TICK(i) { const long long _n = clock64(); tacc[i] += _n - tlast; tlast = _n; }
+#else
+#define TICK(i)
+#endif
 
     // ------------------------------------------------------------------ time loop
     for (int s = 0; s < P.nsteps; ++s) {
         const long long t = P.t0 + s;
         const int tn = (int)(t % P.nmd), tn1 = (int)((t + 1) % P.nmd);
 
+        // operands of this warp's first two tap items: issued now, consumed after the round-A mat-vec
+        double2 pxi[2], ppt[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            pxi[q] = make_double2(0.0, 0.0);
+            ppt[q] = make_double2(0.0, 0.0);
+            if (q < nt) {
+                const FusedBath& B = P.b[titem[q] & 15];
+                const int rr = ((titem[q] >> 4) & 15) * 8 + lr, n = 8 * (titem[q] >> 8) + 2 * lc;
+                if (rr < B.nc) {
+                    pxi[q] = ld2(&B.noise[((size_t)tn1 * B.nc + rr) * ldb + col0 + n]);
+                    if (B.nonlocal) ppt[q] = ld2(&B.P[((size_t)s * B.nc + rr) * ldb + col0 + n]);
+                }
+            }
+        }
+
         // ============ round A: first force evaluation at time t, head p(t) ============
         double hA[NT][2];
         zero_acc<NT>(hA);
         matvec1<NT>(aM, ks, sm + xpc, LD, hA, lr, lc);
-        if (HASCON && s > 0) {
-            // md.sameq (md.py:724-736): a constraint projection that moved q by >= 1e-9 invalidates the
-            // cached potential force; -D q(t) = -D q' + sum_c dq_c (D c_c) by linearity
-#pragma unroll
-            for (int j = 0; j < NT; ++j)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int n = 8 * j + 2 * lc + e;
-                    double m = 0.0;
-#pragma unroll
-                    for (int ww = 0; ww < FW; ++ww) m = fmax(m, sm[P.off_maxp + ww * N + n]);
-                    if (!(m < 10e-10)) fpot[j][e] += fcor[j][e];
-                }
-        }
+        TICK(0)
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             const int n = 8 * j + 2 * lc;
-            double ce[FB_MAX][2];
+            const double2 pv = ld2(&sm[xpc + own + 8 * j]);
+            const double2 qv = ld2(&sm[xq + own + 8 * j]);
+            double f0 = fpot[j][0] + uq[j][0] - hA[j][0];
+            double f1 = fpot[j][1] + uq[j][1] - hA[j][1];
+            double v[8];                         // kinetic energy and up to three bath currents, two columns each
+            v[0] = pv.x * pv.x;
+            v[1] = pv.y * pv.y;
+            double c3a = 0.0, c3b = 0.0;
 #pragma unroll
-            for (int b = 0; b < FB_MAX; ++b) ce[b][0] = ce[b][1] = 0.0;
-            double e0 = 0.0, e1 = 0.0;
+            for (int b = 0; b < FB_MAX; ++b) {
+                double2 nv = ld2(&sm[nbo[b] + nbuf * P.b[b].ncp * LD + 8 * j]);
+                if (b < nb && P.b[b].direct && ip[b] >= 0) nv = make_double2(nzr[j][0], nzr[j][1]);
+                f0 += nv.x;
+                f1 += nv.y;
+                double c0 = nv.x, c1 = nv.y;
+                if (HASQ && b == P.aq) { c0 += maq * uq[j][0]; c1 += maq * uq[j][1]; }
+                if (b == P.rem) { c0 -= mrem * hA[j][0]; c1 -= mrem * hA[j][1]; }
+                if (b < 3) { v[2 + 2 * b] = pv.x * c0; v[3 + 2 * b] = pv.y * c1; }
+                else { c3a = pv.x * c0; c3b = pv.y * c1; }
+            }
             if (live) {
-                const double2 pv = ld2(&sm[xpc + own + 8 * j]);
-                const double2 qv = ld2(&sm[xq + own + 8 * j]);
-                double f0 = fpot[j][0] + uq[j][0] - hA[j][0];
-                double f1 = fpot[j][1] + uq[j][1] - hA[j][1];
-#pragma unroll
-                for (int b = 0; b < FB_MAX; ++b) {
-                    if (ip[b] < 0) continue;
-                    const FusedBath& B = P.b[b];
-                    double2 nv;
-                    if (B.direct) nv = make_double2(nzr[j][0], nzr[j][1]);
-                    else nv = ld2(&sm[B.off_nb + (nbuf * B.ncp + ip[b]) * LD + n]);
-                    f0 += nv.x;
-                    f1 += nv.y;
-                    double c0 = nv.x, c1 = nv.y;
-                    if (HASQ && b == P.aq) { c0 += uq[j][0]; c1 += uq[j][1]; }
-                    if (b == P.rem) { c0 -= hA[j][0]; c1 -= hA[j][1]; }
-                    ce[b][0] = pv.x * c0;
-                    ce[b][1] = pv.y * c1;
-                    if (B.nonlocal) {
-                        st2(&sm[B.off_hist + (s * B.ncp + ip[b]) * LD + n], pv.x, pv.y);
-                        const int slot = (B.slot0 + s) % B.R;
-                        st2(&B.ring[((size_t)slot * B.ncp + ip[b]) * ldb + col0 + n], pv.x, pv.y);
-                    }
-                }
-                e0 = pv.x * pv.x;
-                e1 = pv.y * pv.y;
                 st2(&sm[xpn + own + 8 * j], pv.x + f0 * dt / 2.0, pv.y + f1 * dt / 2.0);
                 st2(&sm[xq + own + 8 * j], qv.x + pv.x * dt + f0 * dt2 / 2.0, qv.y + pv.y * dt + f1 * dt2 / 2.0);
                 if (P.ps) st2(&P.ps[((size_t)tn * nd + row) * ldb + col0 + n], pv.x, pv.y);
                 if (P.qs) st2(&P.qs[((size_t)tn * nd + row) * ldb + col0 + n], qv.x, qv.y);
             }
-            // column sums over this warp's 8 rows -> per-warp slots
-            e0 = colsum8(e0);
-            e1 = colsum8(e1);
-            if (lr == 0) st2(&sm[P.off_curp + (nb * FW + w) * N + n], e0, e1);
-#pragma unroll
-            for (int b = 0; b < FB_MAX; ++b) {
-                if (b >= nb) break;
-                const double c0 = colsum8(ce[b][0]), c1 = colsum8(ce[b][1]);
-                if (lr == 0) st2(&sm[P.off_curp + (b * FW + w) * N + n], c0, c1);
+            // column sums over this warp's 8 rows: reduce-scatter, lane lr ends with the sum of v[lr]
+            const double r = rs8(v, lr);
+            const int qn = lr >> 1;              // 0: kinetic energy, 1..3: bath qn-1
+            if (qn <= nb) sm[P.off_curp + (((qn == 0) ? nb : qn - 1) * FW + w) * N + n + (lr & 1)] = r;
+            if (nb > 3) {
+                c3a = colsum8(c3a);
+                c3b = colsum8(c3b);
+                if (lr == 0) st2(&sm[P.off_curp + (3 * FW + w) * N + n], c3a, c3b);
             }
         }
         // noise of the direct bath at time t+1 (used from round B on)
@@ -309,91 +369,80 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
             if (b < nb && P.b[b].direct && ip[b] >= 0) {
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
-                    const double2 v = ld2(&P.b[b].noise[((size_t)tn1 * P.b[b].nc + ip[b]) * ldb + col0 + 8 * j + 2 * lc]);
-                    nzr[j][0] = v.x; nzr[j][1] = v.y;
+                    const double2 vv = ld2(&P.b[b].noise[((size_t)tn1 * P.b[b].nc + ip[b]) * ldb + col0 + 8 * j + 2 * lc]);
+                    nzr[j][0] = vv.x; nzr[j][1] = vv.y;
                 }
             }
         }
         __syncwarp();
-        // ---- work items, dealt round-robin to the warps ----
-        {
-            int item = 0;
-            // (1) heads of the small baths: only the scalars p.g_b are needed (currents)
-            for (int b = 0; b < nb; ++b) {
-                if (b == P.rem) continue;
-                const FusedBath& B = P.b[b];
-                const int mts = B.ncp / 8;
-                const int* CIDS = reinterpret_cast<const int*>(sm + B.off_cids);
-                const int* INREM = reinterpret_cast<const int*>(sm + B.off_inrem);
-                for (int mt = 0; mt < mts; ++mt)
-                    for (int j = 0; j < NT; ++j, ++item) {
-                        if (item % FW != w) continue;
-                        double g0 = 0.0, g1 = 0.0;
-                        const double* A = sm + B.off_hd + (mt * 8 + lr) * B.ldk + lc;
-                        for (int kk = 0; kk < B.ncp; kk += 4)
-                            dmma884(g0, g1, A[kk], sm[xpc + CIDS[kk + lc] * LD + 8 * j + lr]);
-                        const int rr = mt * 8 + lr, n = 8 * j + 2 * lc;
-                        double s0 = 0.0, s1 = 0.0, r0 = 0.0, r1 = 0.0;
-                        if (rr < B.nc) {
-                            const double2 pv = ld2(&sm[xpc + CIDS[rr] * LD + n]);
-                            s0 = pv.x * g0;
-                            s1 = pv.y * g1;
-                            if (INREM[rr]) { r0 = s0; r1 = s1; }
-                        }
-                        s0 = colsum8(s0); s1 = colsum8(s1);
-                        r0 = colsum8(r0); r1 = colsum8(r1);
-                        if (lr == 0) {
-                            double* cb = &sm[P.off_curp + (b * FW + w) * N + n];
-                            cb[0] -= s0;
-                            cb[1] -= s1;
-                            if (P.rem >= 0) {
-                                double* cr = &sm[P.off_curp + (P.rem * FW + w) * N + n];
-                                cr[0] += r0;
-                                cr[1] += r1;
-                            }
-                        }
-                        __syncwarp();
-                    }
+        TICK(1)
+        // ---- work items ----
+        // (1) heads of the small baths: only the scalars p.g_b are needed (currents)
+        for (int q = 0; q < nh; ++q) {
+            const int b = hitem[q] & 15, mt = (hitem[q] >> 4) & 15, j = hitem[q] >> 8;
+            const FusedBath& B = P.b[b];
+            const int hs = B.nonlocal ? s : 0;
+            const int* INREM = reinterpret_cast<const int*>(sm + B.off_inrem);
+            double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
+            const double* A = sm + B.off_hd + (mt * 8 + lr) * B.ldk + lc;
+            const double* H = sm + B.off_hist + (hs * B.ncp + lc) * LD + 8 * j + lr;
+            for (int kk = 0; kk < B.ncp; kk += 8) {
+                dmma884(g0, g1, A[kk], H[kk * LD]);
+                dmma884(h0, h1, A[kk + 4], H[(kk + 4) * LD]);
             }
-            // (2) noise minus memory-kernel tail at time t+1
-            for (int b = 0; b < nb; ++b) {
-                const FusedBath& B = P.b[b];
-                if (B.direct) continue;
-                const int mts = B.ncp / 8;
-                const int* CIDS = reinterpret_cast<const int*>(sm + B.off_cids);
-                for (int mt = 0; mt < mts; ++mt)
-                    for (int j = 0; j < NT; ++j, ++item) {
-                        if (item % FW != w) continue;
-                        const int rr = mt * 8 + lr, n = 8 * j + 2 * lc;
-                        double2 xi = make_double2(0.0, 0.0), pt = make_double2(0.0, 0.0);
-                        if (rr < B.nc) {
-                            xi = ld2(&B.noise[((size_t)tn1 * B.nc + rr) * ldb + col0 + n]);
-                            if (B.nonlocal) pt = ld2(&B.P[((size_t)s * B.nc + rr) * ldb + col0 + n]);
-                        }
-                        double a0 = 0.0, a1 = 0.0;
-                        if (B.nonlocal) {
-                            const int ntap = min(s + 1, B.ntap);
-                            for (int k = 1; k <= ntap; ++k) {
-                                const double* A = sm + B.off_kin + ((k - 1) * B.ncp + mt * 8 + lr) * B.ldk + lc;
-                                if (k == 1) {
-                                    for (int kk = 0; kk < B.ncp; kk += 4)
-                                        dmma884(a0, a1, A[kk], sm[xpc + CIDS[kk + lc] * LD + 8 * j + lr]);
-                                } else {
-                                    const double* H = sm + B.off_hist + ((s + 1 - k) * B.ncp + lc) * LD + 8 * j + lr;
-                                    for (int kk = 0; kk < B.ncp; kk += 4) dmma884(a0, a1, A[kk], H[kk * LD]);
-                                }
-                            }
-                        }
-                        const double t0v = pt.x + a0, t1v = pt.y + a1;
-                        if (rr < B.nc) {
-                            st2(&sm[B.off_nb + ((nbuf ^ 1) * B.ncp + rr) * LD + n], xi.x - t0v, xi.y - t1v);
-                            if (B.nonlocal && s == P.nsteps - 1)
-                                st2(&B.tail_cur[(size_t)rr * ldb + col0 + n], t0v, t1v);
-                        }
+            g0 += h0; g1 += h1;
+            const int rr = mt * 8 + lr, n = 8 * j + 2 * lc;
+            double v4[4] = {0.0, 0.0, 0.0, 0.0};
+            if (rr < B.nc) {
+                const double2 pv = ld2(&sm[B.off_hist + (hs * B.ncp + rr) * LD + n]);
+                v4[0] = pv.x * g0;
+                v4[1] = pv.y * g1;
+                if (INREM[rr]) { v4[2] = v4[0]; v4[3] = v4[1]; }
+            }
+            const double r = rs4(v4, lr);        // lanes (lr>>1): 0 -> s0, 1 -> s1, 2 -> r0, 3 -> r1
+            if ((lr & 1) == 0) {
+                const int sel = lr >> 1;
+                if (sel < 2) sm[P.off_curp + (b * FW + w) * N + n + sel] -= r;
+                else if (P.rem >= 0) sm[P.off_curp + (P.rem * FW + w) * N + n + sel - 2] += r;
+            }
+            __syncwarp();
+        }
+        // (2) noise minus memory-kernel tail at time t+1
+        for (int q = 0; q < nt; ++q) {
+            const int b = titem[q] & 15, mt = (titem[q] >> 4) & 15, j = titem[q] >> 8;
+            const FusedBath& B = P.b[b];
+            const int rr = mt * 8 + lr, n = 8 * j + 2 * lc;
+            double2 xi, pt;
+            if (q == 0) { xi = pxi[0]; pt = ppt[0]; }
+            else if (q == 1) { xi = pxi[1]; pt = ppt[1]; }
+            else {
+                xi = make_double2(0.0, 0.0); pt = make_double2(0.0, 0.0);
+                if (rr < B.nc) {
+                    xi = ld2(&B.noise[((size_t)tn1 * B.nc + rr) * ldb + col0 + n]);
+                    if (B.nonlocal) pt = ld2(&B.P[((size_t)s * B.nc + rr) * ldb + col0 + n]);
+                }
+            }
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+            if (B.nonlocal) {
+                const int ntap = min(s + 1, B.ntap);
+                for (int k = 1; k <= ntap; ++k) {
+                    const double* A = sm + B.off_kin + ((k - 1) * B.ncp + mt * 8 + lr) * B.ldk + lc;
+                    const double* H = sm + B.off_hist + ((s + 1 - k) * B.ncp + lc) * LD + 8 * j + lr;
+                    for (int kk = 0; kk < B.ncp; kk += 8) {
+                        dmma884(a0, a1, A[kk], H[kk * LD]);
+                        dmma884(b0, b1, A[kk + 4], H[(kk + 4) * LD]);
                     }
+                }
+            }
+            const double t0v = pt.x + (a0 + b0), t1v = pt.y + (a1 + b1);
+            if (rr < B.nc) {
+                st2(&sm[B.off_nb + ((nbuf ^ 1) * B.ncp + rr) * LD + n], xi.x - t0v, xi.y - t1v);
+                if (B.nonlocal && s == P.nsteps - 1) st2(&B.tail_cur[(size_t)rr * ldb + col0 + n], t0v, t1v);
             }
         }
+        TICK(2)
         __syncthreads();                                                        // ---- S2
+        TICK(3)
         // currents and kinetic energy of time t: fixed-order sum of the per-warp slots
         for (int e = tid; e < (nb + 1) * N; e += FW * 32) {
             const int b = e / N, n = e % N;
@@ -416,22 +465,18 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
             if (HASQ) matvec2<NT>(aD, aQ, ks, sm + xq, LD, aDq, uq, lr, lc);
             else matvec1<NT>(aD, ks, sm + xq, LD, aDq, lr, lc);
             matvec1<NT>(aM, ks, sm + xpc, LD, hB, lr, lc);
+            TICK(4)
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
-                const int n = 8 * j + 2 * lc;
                 fpot[j][0] = -aDq[j][0];
                 fpot[j][1] = -aDq[j][1];
                 double f0 = fpot[j][0] + uq[j][0], f1 = fpot[j][1] + uq[j][1];
 #pragma unroll
                 for (int b = 0; b < FB_MAX; ++b) {
-                    if (ip[b] < 0) continue;
-                    const FusedBath& B = P.b[b];
-                    if (B.direct) { f0 += nzr[j][0]; f1 += nzr[j][1]; }
-                    else {
-                        const double2 nv = ld2(&sm[B.off_nb + (nbuf * B.ncp + ip[b]) * LD + n]);
-                        f0 += nv.x;
-                        f1 += nv.y;
-                    }
+                    double2 nv = ld2(&sm[nbo[b] + nbuf * P.b[b].ncp * LD + 8 * j]);
+                    if (b < nb && P.b[b].direct && ip[b] >= 0) nv = make_double2(nzr[j][0], nzr[j][1]);
+                    f0 += nv.x;
+                    f1 += nv.y;
                 }
                 fb[j][0] = f0;
                 fb[j][1] = f1;
@@ -441,86 +486,111 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                 }
             }
         }
+        TICK(5)
         __syncthreads();                                                        // ---- S3
+        TICK(3)
         { const int tmp = xpc; xpc = xpn; xpn = tmp; }      // xpc: p1, xpn: still holds p(t+1/2)
 
-        // ============ round C: third evaluation, head p1 -> p(t+1), constraints ============
+        // ============ round C: third evaluation, head p1 -> p(t+1), constraint ============
         {
             double hC[NT][2];
             zero_acc<NT>(hC);
             matvec1<NT>(aM, ks, sm + xpc, LD, hC, lr, lc);
-            double pn[NT][2];
+            TICK(6)
+            double pn[NT][2], qn[NT][2];
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
-                pn[j][0] = pn[j][1] = 0.0;
-                if (live) {
-                    const double2 ph = ld2(&sm[xpn + own + 8 * j]);
-                    pn[j][0] = ph.x + dt * (fb[j][0] - hC[j][0]) / 2.0;
-                    pn[j][1] = ph.y + dt * (fb[j][1] - hC[j][1]) / 2.0;
+                const double2 ph = ld2(&sm[xpn + own + 8 * j]);
+                pn[j][0] = live ? ph.x + dt * (fb[j][0] - hC[j][0]) / 2.0 : 0.0;
+                pn[j][1] = live ? ph.y + dt * (fb[j][1] - hC[j][1]) / 2.0 : 0.0;
+            }
+            if (HASCON) {
+                // md.ApplyConstraint (md.py:739-762) with one constraint vector: the dots c.p', c.q' are
+                // warp-reduced with a reduce-scatter, summed over the 8 warps after one barrier
+                const double cv = sm[P.off_conv + row];
+                const double dv = sm[P.off_conv + NDP + row];
+                const double av = HASQ ? sm[P.off_conv + 2 * NDP + row] : 0.0;
+                constexpr int NG = (4 * NT + 7) / 8;
+                double tot[NG];
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    double v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int vi = 8 * g + i, j = vi >> 2, kind = vi & 3;       // d0, d1, g0, g1 of n-tile j
+                        double x = 0.0;
+                        if (j < NT) {
+                            if (kind < 2) x = pn[j][kind] * cv;
+                            else x = (kind == 2 ? sm[xq + own + 8 * j] : sm[xq + own + 8 * j + 1]) * cv;
+                        }
+                        v[i] = x;
+                    }
+                    const double r = rs8(v, lr);
+                    sm[P.off_conp + ((8 * g + lr) * FW + w) * 4 + lc] = r;
+                }
+                TICK(7)
+                __syncthreads();                                                // ---- S4
+                TICK(3)
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int ww = 0; ww < FW; ++ww) sum += sm[P.off_conp + ((8 * g + lr) * FW + ww) * 4 + lc];
+                    tot[g] = sum;
+                }
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    // all-gather the four totals of n-tile j from the lanes that own them
+                    double d[4];
+#pragma unroll
+                    for (int kind = 0; kind < 4; ++kind) {
+                        const int vi = 4 * j + kind;
+                        d[kind] = __shfl_sync(0xffffffffu, tot[vi >> 3], ((vi & 7) << 2) | lc);
+                    }
+                    const double2 q0 = ld2(&sm[xq + own + 8 * j]);
+                    pn[j][0] -= d[0] * cv;
+                    pn[j][1] -= d[1] * cv;
+                    qn[j][0] = q0.x - d[2] * cv;
+                    qn[j][1] = q0.y - d[3] * cv;
+                    // md.sameq (md.py:724-736): max_i |q(t+1)_i - q'_i| = |dq| max_i |c_i|; when it reaches 1e-9
+                    // the cached force is dropped: -D q(t+1) = -D q' + dq (D c) by linearity
+                    if (!(fabs(d[2]) * P.cmax < 10e-10)) fpot[j][0] += d[2] * dv;
+                    if (!(fabs(d[3]) * P.cmax < 10e-10)) fpot[j][1] += d[3] * dv;
+                    if (HASQ) { uq[j][0] -= d[2] * av; uq[j][1] -= d[3] * av; }      // AqT q(t+1)
+                    if (live) st2(&sm[xq + own + 8 * j], qn[j][0], qn[j][1]);
                 }
             }
-            if (!HASCON) {
-                if (live) {
-#pragma unroll
-                    for (int j = 0; j < NT; ++j) st2(&sm[xpn + own + 8 * j], pn[j][0], pn[j][1]);
-                }
-            } else {
-                // md.ApplyConstraint (md.py:739-762): all dots with the unprojected vectors
-                for (int c = 0; c < P.ncon; ++c) {
-                    const double cv = sm[P.off_conv + c * NDP + row];
-#pragma unroll
-                    for (int j = 0; j < NT; ++j) {
-                        const int n = 8 * j + 2 * lc;
-                        const double2 qv = ld2(&sm[xq + own + 8 * j]);
-                        const double d0 = colsum8(pn[j][0] * cv), d1 = colsum8(pn[j][1] * cv);
-                        const double g0 = colsum8(qv.x * cv), g1 = colsum8(qv.y * cv);
-                        if (lr == 0) {
-                            st2(&sm[P.off_conp + ((c * 2 + 0) * FW + w) * N + n], d0, d1);
-                            st2(&sm[P.off_conp + ((c * 2 + 1) * FW + w) * N + n], g0, g1);
-                        }
-                    }
-                }
-                __syncthreads();                                                // ---- S4
+            if (live) {
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
                     const int n = 8 * j + 2 * lc;
-                    const double2 q0 = ld2(&sm[xq + own + 8 * j]);
-                    double p0 = pn[j][0], p1 = pn[j][1], qa = q0.x, qb = q0.y;
-                    double fc0 = 0.0, fc1 = 0.0;
-                    for (int c = 0; c < P.ncon; ++c) {
-                        const double cv = sm[P.off_conv + c * NDP + row];
-                        const double dv = sm[P.off_conv + (P.ncon + c) * NDP + row];
-                        const double av = HASQ ? sm[P.off_conv + (2 * P.ncon + c) * NDP + row] : 0.0;
-                        double dp0 = 0.0, dp1 = 0.0, dq0 = 0.0, dq1 = 0.0;
+                    st2(&sm[xpn + own + 8 * j], pn[j][0], pn[j][1]);
+                    // p_c(t+1) enters the block history / the HBM ring
 #pragma unroll
-                        for (int ww = 0; ww < FW; ++ww) {
-                            const double2 a = ld2(&sm[P.off_conp + ((c * 2 + 0) * FW + ww) * N + n]);
-                            const double2 bq = ld2(&sm[P.off_conp + ((c * 2 + 1) * FW + ww) * N + n]);
-                            dp0 += a.x; dp1 += a.y;
-                            dq0 += bq.x; dq1 += bq.y;
+                    for (int b = 0; b < FB_MAX; ++b) {
+                        if (ip[b] < 0 || P.b[b].direct) continue;
+                        const FusedBath& B = P.b[b];
+                        if (!B.nonlocal) st2(&sm[B.off_hist + ip[b] * LD + n], pn[j][0], pn[j][1]);
+                        else if (s + 1 < P.nsteps) {
+                            st2(&sm[B.off_hist + ((s + 1) * B.ncp + ip[b]) * LD + n], pn[j][0], pn[j][1]);
+                            const int slot = (B.slot0 + s + 1) % B.R;
+                            st2(&B.ring[((size_t)slot * B.ncp + ip[b]) * ldb + col0 + n], pn[j][0], pn[j][1]);
                         }
-                        p0 -= dp0 * cv; p1 -= dp1 * cv;
-                        qa -= dq0 * cv; qb -= dq1 * cv;
-                        fc0 += dq0 * dv; fc1 += dq1 * dv;                  // -D q(t+1) = -D q' + sum dq_c (D c)
-                        if (HASQ) { uq[j][0] -= dq0 * av; uq[j][1] -= dq1 * av; }   // AqT q(t+1)
-                    }
-                    fcor[j][0] = fc0;
-                    fcor[j][1] = fc1;
-                    const double m0 = colmax8(live ? fabs(qa - q0.x) : 0.0);
-                    const double m1 = colmax8(live ? fabs(qb - q0.y) : 0.0);
-                    if (lr == 0) st2(&sm[P.off_maxp + w * N + n], m0, m1);
-                    if (live) {
-                        st2(&sm[xpn + own + 8 * j], p0, p1);
-                        st2(&sm[xq + own + 8 * j], qa, qb);
                     }
                 }
             }
         }
+        TICK(7)
         __syncthreads();                                                        // ---- S1
+        TICK(3)
         { const int tmp = xpc; xpc = xpn; xpn = tmp; }      // xpc: p(t+1)
     }
 
     // ------------------------------------------------------------------ epilogue
+#ifdef PYMD_FUSED_TIMING
+    if (P.timing && lane == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(&P.timing[i]), (unsigned long long)tacc[i]);
+#endif
     if (live) {
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
@@ -532,15 +602,7 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
             st2(&P.fpotn[(size_t)row * ldb + col0 + n], fpot[j][0], fpot[j][1]);
         }
     }
-    for (int n = tid; n < N; n += FW * 32) {
-        int same = 1;
-        if (HASCON) {
-            double m = 0.0;
-            for (int ww = 0; ww < FW; ++ww) m = fmax(m, sm[P.off_maxp + ww * N + n]);
-            same = m < 10e-10;
-        }
-        P.samef[col0 + n] = same;
-    }
+    for (int n = tid; n < N; n += FW * 32) P.samef[col0 + n] = 1;     // the stored force is the force at q(t)
 }
 
 struct Layout {
@@ -548,7 +610,7 @@ struct Layout {
     size_t smem_bytes;
 };
 
-// shared-memory plan for NT n-tiles; returns bytes
+// shared-memory plan for NT n-tiles; returns bytes (0 if the work-item lists would overflow)
 size_t plan(const pymd_ctx* c, int NT, FusedParams& fp) {
     const int N = 8 * NT, LD = N + 4;
     int off = 0;
@@ -556,10 +618,11 @@ size_t plan(const pymd_ctx* c, int NT, FusedParams& fp) {
     fp.off_xp0 = take(NDP * LD);
     fp.off_xp1 = take(NDP * LD);
     fp.off_xq = take(NDP * LD);
+    fp.off_zero = take(LD);
     fp.off_curp = take((c->nbath + 1) * FW * N);
-    fp.off_conp = take(std::max(1, c->ncon) * 2 * FW * N);
-    fp.off_maxp = take(FW * N);
-    fp.off_conv = take(std::max(1, 3 * c->ncon) * NDP);
+    fp.off_conp = take(((4 * NT + 7) / 8) * 8 * FW * 4);
+    fp.off_conv = take(3 * NDP);
+    int nhead = 0, ntap = 0;
     for (int b = 0; b < c->nbath; ++b) {
         const BathHost& H = c->bath[b];
         FusedBath& B = fp.b[b];
@@ -569,16 +632,16 @@ size_t plan(const pymd_ctx* c, int NT, FusedParams& fp) {
         B.ntap = H.ml > 1 ? std::min(FT, H.ml - 1) : 0;
         B.off_cids = B.off_inrem = B.off_hd = B.off_nb = B.off_kin = B.off_hist = 0;
         if (B.direct) continue;
+        ntap += (H.ncp / 8) * NT;
         B.off_cids = take(H.ncp / 2 + 1);
         B.off_inrem = take(H.ncp / 2 + 1);
-        if (b != fp.rem) B.off_hd = take(H.ncp * B.ldk);
+        if (b != fp.rem) { B.off_hd = take(H.ncp * B.ldk); nhead += (H.ncp / 8) * NT; }
         B.off_nb = take(2 * H.ncp * LD);
-        if (H.ml > 1) {
-            B.off_kin = take(B.ntap * H.ncp * B.ldk);
-            B.off_hist = take(FT * H.ncp * LD);
-        }
+        B.off_hist = take((H.ml > 1 ? FT : 1) * H.ncp * LD);
+        if (H.ml > 1) B.off_kin = take(B.ntap * H.ncp * B.ldk);
     }
     fp.smem_doubles = off;
+    if (nhead > FW * MAXIT || ntap > FW * MAXIT) return (size_t)1 << 40;     // does not fit the item lists
     return (size_t)off * sizeof(double);
 }
 
@@ -634,7 +697,7 @@ int launch_nt(const FusedParams& fp, size_t smem, int grid, bool hasq, bool hasc
 }  // namespace
 
 int fused_supported(const pymd_ctx* c) {
-    if (c->nd > NDP || c->ncon > 4 || c->nbath > FB_MAX) return 0;
+    if (c->nd > NDP || c->ncon > 1 || c->nbath > FB_MAX) return 0;
     int naq = 0;
     for (int b = 0; b < c->nbath; ++b) {
         naq += c->bath[b].has_aq;
@@ -694,6 +757,8 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
         PYMD_CUDA_CHECK(cudaMemcpy(c->d_con3, c3.data(), c3.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
     fp.con3 = c->d_con3;
+    fp.cmax = 0.0;
+    for (int i = 0; i < (c->ncon > 0 ? c->nd : 0); ++i) fp.cmax = std::max(fp.cmax, std::fabs(c->con[i]));
     for (int b = 0; b < c->nbath; ++b) {
         BathHost& H = c->bath[b];
         FusedBath& B = fp.b[b];
@@ -708,6 +773,12 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
         c->tail_valid = true;
     }
     const int grid = c->ldb / (8 * NT);
+#ifdef PYMD_FUSED_TIMING
+    static long long* d_timing = nullptr;
+    if (!d_timing) { cudaMalloc(&d_timing, 8 * sizeof(long long)); }
+    cudaMemsetAsync(d_timing, 0, 8 * sizeof(long long), st);
+    fp.timing = d_timing;
+#endif
     for (int done = 0; done < nsteps; done += FT) {
         const int ns = std::min(FT, nsteps - done);
         for (int b = 0; b < c->nbath; ++b) {
@@ -735,6 +806,18 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
         c->fpot_valid = true;
         c->fpotc_valid = false;
     }
+#ifdef PYMD_FUSED_TIMING
+    {
+        long long h[8];
+        cudaMemcpy(h, fp.timing, sizeof(h), cudaMemcpyDeviceToHost);
+        const double nw = (double)grid * FW * nsteps;
+        const char* nm[8] = {"A.matvec", "A.elementwise", "A.items", "barrier-wait", "B.matvec", "B.elementwise", "C.matvec", "C.elementwise"};
+        double tot = 0; for (int i = 0; i < 8; ++i) tot += h[i] / nw;
+        fprintf(stderr, "[fused timing] cycles per warp-step (NT=%d):", NT);
+        for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.0f", nm[i], h[i] / nw);
+        fprintf(stderr, " total=%.0f\n", tot);
+    }
+#endif
     return PYMD_OK;
 }
 
