@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "engine.cuh"
@@ -196,12 +197,14 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
     }
     // per-thread bath membership of the owned row: index into the bath's dofs or -1; smem offset of
     // the row's noise-minus-tail entry (a zero row when the dof is not coupled to the bath)
-    int ip[FB_MAX], nbo[FB_MAX];
+    int ip[FB_MAX], nbo[FB_MAX], nbs[FB_MAX];      // nbs: double-buffer stride (0 for the zero row)
     double mrem = 0.0, maq = 0.0;               // 1.0 when the row belongs to the remainder / q-coupled bath
 #pragma unroll
     for (int b = 0; b < FB_MAX; ++b) {
         ip[b] = (b < nb && live) ? P.b[b].inv_g[row] : -1;
-        nbo[b] = (ip[b] >= 0 && !P.b[b].direct) ? P.b[b].off_nb + ip[b] * LD + 2 * lc : P.off_zero + 2 * lc;
+        const bool member = ip[b] >= 0 && !P.b[b].direct;
+        nbo[b] = member ? P.b[b].off_nb + ip[b] * LD + 2 * lc : P.off_zero + 2 * lc;
+        nbs[b] = member ? P.b[b].ncp * LD : 0;
         if (ip[b] >= 0 && b == P.rem) mrem = 1.0;
         if (ip[b] >= 0 && b == P.aq) maq = 1.0;
     }
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
             double c3a = 0.0, c3b = 0.0;
 #pragma unroll
             for (int b = 0; b < FB_MAX; ++b) {
-                double2 nv = ld2(&sm[nbo[b] + nbuf * P.b[b].ncp * LD + 8 * j]);
+                double2 nv = ld2(&sm[nbo[b] + nbuf * nbs[b] + 8 * j]);
                 if (b < nb && P.b[b].direct && ip[b] >= 0) nv = make_double2(nzr[j][0], nzr[j][1]);
                 f0 += nv.x;
                 f1 += nv.y;
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                 double f0 = fpot[j][0] + uq[j][0], f1 = fpot[j][1] + uq[j][1];
 #pragma unroll
                 for (int b = 0; b < FB_MAX; ++b) {
-                    double2 nv = ld2(&sm[nbo[b] + nbuf * P.b[b].ncp * LD + 8 * j]);
+                    double2 nv = ld2(&sm[nbo[b] + nbuf * nbs[b] + 8 * j]);
                     if (b < nb && P.b[b].direct && ip[b] >= 0) nv = make_double2(nzr[j][0], nzr[j][1]);
                     f0 += nv.x;
                     f1 += nv.y;
@@ -650,7 +653,9 @@ int pick_nt(const pymd_ctx* c, FusedParams& fp) {
     // (larger tiles amortise barriers and give the DMMA pipe more independent chains)
     int best = 0;
     double best_score = -1.0;
+    const char* force = getenv("PYMD_FUSED_NT");      // testing knob: force the trajectory tile
     for (int NT : {4, 2, 1}) {
+        if (force && atoi(force) != NT) continue;
         if (c->ldb % (8 * NT)) continue;
         if (plan(c, NT, fp) > 227 * 1024) continue;
         const long long ctas = c->ldb / (8 * NT);

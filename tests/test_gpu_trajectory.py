@@ -164,6 +164,27 @@ def test_switching_between_step_modes(cuda, case):
         assert T.relerr(m.p[..., n], om.p) < TOL and T.relerr(m.q[..., n], om.q) < TOL
 
 
+@pytest.mark.parametrize("nt", ["1", "2", "4"])
+@pytest.mark.parametrize("case", ["aubz", "chain39", "ragged"])
+def test_fused_tile_sizes(cuda, case, nt, monkeypatch):
+    """Every trajectory-tile size of the fused kernel (8, 16, 32 trajectories per CTA), forced
+    through the PYMD_FUSED_NT testing knob, against the oracle; 40 trajectories so that tiles are
+    partially padded and several CTAs run."""
+    monkeypatch.setenv("PYMD_FUSED_NT", nt)
+    c = T.CASES[case]
+    B = 40
+    m, j = T.device_md(c, B, step_mode=2)
+    xi, r = T.draw(c, m, B, seed=31)
+    m.initialise(r=r); m.ResetHis()
+    for b, bath in enumerate(m.baths):
+        bath.gnoi(xi=xi[0][b])
+    m.ResetSavepq()
+    m.steps(c["nmd"])
+    for n in (0, 17, 39):
+        om, recs = T.run_oracle(c, j, m, xi, r, n, c["nmd"])
+        compare(m, recs[0], n)
+
+
 def test_fhis_recording(cuda, golden):
     """md.fhis (bath forces of the first evaluation, md.py:343) when asked for."""
     c = T.CASES["ph2"]
