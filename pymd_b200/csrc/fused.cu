@@ -92,19 +92,6 @@ __device__ __forceinline__ double rs8(const double (&v)[8], int lr) {
     const double keep = h1 ? m[1] : m[0], send = h1 ? m[0] : m[1];
     return keep + __shfl_xor_sync(0xffffffffu, send, 4);
 }
-// 4 values: lanes with (lr>>1) == i return sum_lanes v[i] (both lanes of a pair hold it)
-__device__ __forceinline__ double rs4(const double (&v)[4], int lr) {
-    const bool h4 = lr & 4, h2 = lr & 2;
-    double k[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const double keep = h4 ? v[i + 2] : v[i], send = h4 ? v[i] : v[i + 2];
-        k[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-    const double keep = h2 ? k[1] : k[0], send = h2 ? k[0] : k[1];
-    double r = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    return r + __shfl_xor_sync(0xffffffffu, r, 4);
-}
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 
@@ -208,21 +195,21 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
         if (ip[b] >= 0 && b == P.rem) mrem = 1.0;
         if (ip[b] >= 0 && b == P.aq) maq = 1.0;
     }
-    // static work-item list of this warp: code = b | mt << 4 | j << 8 (heads of the small baths, taps)
-    int hitem[MAXIT], titem[MAXIT], nh = 0, nt = 0;
+    // static work-item list of this warp: code = b | mt << 4 | kind << 8.  An item covers one m8 tile of
+    // one bath for ALL n-tiles (A fragment loaded once per k-step, NT independent DMMA chains).  The
+    // heavier tap items (kind 1) are dealt first, then the heads of the small baths (kind 0).
+    int items[MAXIT], nit = 0;
     {
         int item = 0;
         for (int b = 0; b < nb; ++b) {
-            if (b == P.rem) continue;
-            for (int mt = 0; mt < P.b[b].ncp / 8; ++mt)
-                for (int j = 0; j < NT; ++j, ++item)
-                    if (item % FW == w && nh < MAXIT) hitem[nh++] = b | (mt << 4) | (j << 8);
+            if (P.b[b].direct) continue;
+            for (int mt = 0; mt < P.b[b].ncp / 8; ++mt, ++item)
+                if (item % FW == w && nit < MAXIT) items[nit++] = b | (mt << 4) | (1 << 8);
         }
         for (int b = 0; b < nb; ++b) {
-            if (P.b[b].direct) continue;
-            for (int mt = 0; mt < P.b[b].ncp / 8; ++mt)
-                for (int j = 0; j < NT; ++j, ++item)
-                    if (item % FW == w && nt < MAXIT) titem[nt++] = b | (mt << 4) | (j << 8);
+            if (b == P.rem) continue;
+            for (int mt = 0; mt < P.b[b].ncp / 8; ++mt, ++item)
+                if (item % FW == w && nit < MAXIT) items[nit++] = b | (mt << 4);
         }
     }
 
@@ -306,22 +293,6 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
         const long long t = P.t0 + s;
         const int tn = (int)(t % P.nmd), tn1 = (int)((t + 1) % P.nmd);
 
-        // operands of this warp's first two tap items: issued now, consumed after the round-A mat-vec
-        double2 pxi[2], ppt[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            pxi[q] = make_double2(0.0, 0.0);
-            ppt[q] = make_double2(0.0, 0.0);
-            if (q < nt) {
-                const FusedBath& B = P.b[titem[q] & 15];
-                const int rr = ((titem[q] >> 4) & 15) * 8 + lr, n = 8 * (titem[q] >> 8) + 2 * lc;
-                if (rr < B.nc) {
-                    pxi[q] = ld2(&B.noise[((size_t)tn1 * B.nc + rr) * ldb + col0 + n]);
-                    if (B.nonlocal) ppt[q] = ld2(&B.P[((size_t)s * B.nc + rr) * ldb + col0 + n]);
-                }
-            }
-        }
-
         // ============ round A: first force evaluation at time t, head p(t) ============
         double hA[NT][2];
         zero_acc<NT>(hA);
@@ -380,67 +351,82 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
         __syncwarp();
         TICK(1)
         // ---- work items ----
-        // (1) heads of the small baths: only the scalars p.g_b are needed (currents)
-        for (int q = 0; q < nh; ++q) {
-            const int b = hitem[q] & 15, mt = (hitem[q] >> 4) & 15, j = hitem[q] >> 8;
+        for (int q = 0; q < nit; ++q) {
+            const int b = items[q] & 15, mt = (items[q] >> 4) & 15;
             const FusedBath& B = P.b[b];
-            const int hs = B.nonlocal ? s : 0;
-            const int* INREM = reinterpret_cast<const int*>(sm + B.off_inrem);
-            double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
-            const double* A = sm + B.off_hd + (mt * 8 + lr) * B.ldk + lc;
-            const double* H = sm + B.off_hist + (hs * B.ncp + lc) * LD + 8 * j + lr;
-            for (int kk = 0; kk < B.ncp; kk += 8) {
-                dmma884(g0, g1, A[kk], H[kk * LD]);
-                dmma884(h0, h1, A[kk + 4], H[(kk + 4) * LD]);
-            }
-            g0 += h0; g1 += h1;
-            const int rr = mt * 8 + lr, n = 8 * j + 2 * lc;
-            double v4[4] = {0.0, 0.0, 0.0, 0.0};
-            if (rr < B.nc) {
-                const double2 pv = ld2(&sm[B.off_hist + (hs * B.ncp + rr) * LD + n]);
-                v4[0] = pv.x * g0;
-                v4[1] = pv.y * g1;
-                if (INREM[rr]) { v4[2] = v4[0]; v4[3] = v4[1]; }
-            }
-            const double r = rs4(v4, lr);        // lanes (lr>>1): 0 -> s0, 1 -> s1, 2 -> r0, 3 -> r1
-            if ((lr & 1) == 0) {
-                const int sel = lr >> 1;
-                if (sel < 2) sm[P.off_curp + (b * FW + w) * N + n + sel] -= r;
-                else if (P.rem >= 0) sm[P.off_curp + (P.rem * FW + w) * N + n + sel - 2] += r;
-            }
-            __syncwarp();
-        }
-        // (2) noise minus memory-kernel tail at time t+1
-        for (int q = 0; q < nt; ++q) {
-            const int b = titem[q] & 15, mt = (titem[q] >> 4) & 15, j = titem[q] >> 8;
-            const FusedBath& B = P.b[b];
-            const int rr = mt * 8 + lr, n = 8 * j + 2 * lc;
-            double2 xi, pt;
-            if (q == 0) { xi = pxi[0]; pt = ppt[0]; }
-            else if (q == 1) { xi = pxi[1]; pt = ppt[1]; }
-            else {
-                xi = make_double2(0.0, 0.0); pt = make_double2(0.0, 0.0);
-                if (rr < B.nc) {
-                    xi = ld2(&B.noise[((size_t)tn1 * B.nc + rr) * ldb + col0 + n]);
-                    if (B.nonlocal) pt = ld2(&B.P[((size_t)s * B.nc + rr) * ldb + col0 + n]);
-                }
-            }
-            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-            if (B.nonlocal) {
-                const int ntap = min(s + 1, B.ntap);
-                for (int k = 1; k <= ntap; ++k) {
-                    const double* A = sm + B.off_kin + ((k - 1) * B.ncp + mt * 8 + lr) * B.ldk + lc;
-                    const double* H = sm + B.off_hist + ((s + 1 - k) * B.ncp + lc) * LD + 8 * j + lr;
-                    for (int kk = 0; kk < B.ncp; kk += 8) {
-                        dmma884(a0, a1, A[kk], H[kk * LD]);
-                        dmma884(b0, b1, A[kk + 4], H[(kk + 4) * LD]);
+            const int rr = mt * 8 + lr;
+            const bool valid = rr < B.nc;
+            if (items[q] >> 8) {
+                // noise minus memory-kernel tail at time t+1: xi(t+1) - P[s] - sum_{k=1}^{s+1} dt K[k] p_c(t+1-k)
+                double2 xi[NT], pt[NT];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    xi[j] = make_double2(0.0, 0.0);
+                    pt[j] = make_double2(0.0, 0.0);
+                    if (valid) {
+                        xi[j] = ld2(&B.noise[((size_t)tn1 * B.nc + rr) * ldb + col0 + 8 * j + 2 * lc]);
+                        if (B.nonlocal) pt[j] = ld2(&B.P[((size_t)s * B.nc + rr) * ldb + col0 + 8 * j + 2 * lc]);
                     }
                 }
-            }
-            const double t0v = pt.x + (a0 + b0), t1v = pt.y + (a1 + b1);
-            if (rr < B.nc) {
-                st2(&sm[B.off_nb + ((nbuf ^ 1) * B.ncp + rr) * LD + n], xi.x - t0v, xi.y - t1v);
-                if (B.nonlocal && s == P.nsteps - 1) st2(&B.tail_cur[(size_t)rr * ldb + col0 + n], t0v, t1v);
+                double acc[NT][2];
+                zero_acc<NT>(acc);
+                if (B.nonlocal) {
+                    const int ntap = min(s + 1, B.ntap);
+                    for (int k = 1; k <= ntap; ++k) {
+                        const double* A = sm + B.off_kin + ((k - 1) * B.ncp + rr) * B.ldk + lc;
+                        const double* H = sm + B.off_hist + ((s + 1 - k) * B.ncp + lc) * LD + lr;
+                        for (int kk = 0; kk < B.ncp; kk += 4) {
+                            const double a = A[kk];
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) dmma884(acc[j][0], acc[j][1], a, H[kk * LD + 8 * j]);
+                        }
+                    }
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const double t0v = pt[j].x + acc[j][0], t1v = pt[j].y + acc[j][1];
+                        st2(&sm[B.off_nb + ((nbuf ^ 1) * B.ncp + rr) * LD + 8 * j + 2 * lc], xi[j].x - t0v, xi[j].y - t1v);
+                        if (B.nonlocal && s == P.nsteps - 1)
+                            st2(&B.tail_cur[(size_t)rr * ldb + col0 + 8 * j + 2 * lc], t0v, t1v);
+                    }
+                }
+            } else {
+                // head of a small bath: only the scalars p_c.g_b (currents) are needed
+                const int hs = B.nonlocal ? s : 0;
+                const int inrem = valid ? reinterpret_cast<const int*>(sm + B.off_inrem)[rr] : 0;
+                double g[NT][2];
+                zero_acc<NT>(g);
+                const double* A = sm + B.off_hd + rr * B.ldk + lc;
+                const double* H = sm + B.off_hist + (hs * B.ncp + lc) * LD + lr;
+                for (int kk = 0; kk < B.ncp; kk += 4) {
+                    const double a = A[kk];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) dmma884(g[j][0], g[j][1], a, H[kk * LD + 8 * j]);
+                }
+#pragma unroll
+                for (int j2 = 0; j2 < NT; j2 += 2) {
+                    double v[8];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int j = j2 + h;
+                        double s0 = 0.0, s1 = 0.0;
+                        if (j < NT && valid) {
+                            const double2 pv = ld2(&sm[B.off_hist + (hs * B.ncp + rr) * LD + 8 * j + 2 * lc]);
+                            s0 = pv.x * g[j < NT ? j : 0][0];
+                            s1 = pv.y * g[j < NT ? j : 0][1];
+                        }
+                        v[4 * h + 0] = s0; v[4 * h + 1] = s1;
+                        v[4 * h + 2] = inrem ? s0 : 0.0; v[4 * h + 3] = inrem ? s1 : 0.0;
+                    }
+                    const double r = rs8(v, lr);     // lane lr: n-tile j2 + (lr>>2), kind lr&3 (s0, s1, r0, r1)
+                    const int j = j2 + (lr >> 2), kind = lr & 3;
+                    if (j < NT) {
+                        if (kind < 2) sm[P.off_curp + (b * FW + w) * N + 8 * j + 2 * lc + kind] -= r;
+                        else if (P.rem >= 0) sm[P.off_curp + (P.rem * FW + w) * N + 8 * j + 2 * lc + kind - 2] += r;
+                    }
+                    __syncwarp();
+                }
             }
         }
         TICK(2)
@@ -635,16 +621,16 @@ size_t plan(const pymd_ctx* c, int NT, FusedParams& fp) {
         B.ntap = H.ml > 1 ? std::min(FT, H.ml - 1) : 0;
         B.off_cids = B.off_inrem = B.off_hd = B.off_nb = B.off_kin = B.off_hist = 0;
         if (B.direct) continue;
-        ntap += (H.ncp / 8) * NT;
+        ntap += H.ncp / 8;
         B.off_cids = take(H.ncp / 2 + 1);
         B.off_inrem = take(H.ncp / 2 + 1);
-        if (b != fp.rem) { B.off_hd = take(H.ncp * B.ldk); nhead += (H.ncp / 8) * NT; }
+        if (b != fp.rem) { B.off_hd = take(H.ncp * B.ldk); nhead += H.ncp / 8; }
         B.off_nb = take(2 * H.ncp * LD);
         B.off_hist = take((H.ml > 1 ? FT : 1) * H.ncp * LD);
         if (H.ml > 1) B.off_kin = take(B.ntap * H.ncp * B.ldk);
     }
     fp.smem_doubles = off;
-    if (nhead > FW * MAXIT || ntap > FW * MAXIT) return (size_t)1 << 40;     // does not fit the item lists
+    if (nhead + ntap > FW * MAXIT) return (size_t)1 << 40;     // does not fit the item lists
     return (size_t)off * sizeof(double);
 }
 

@@ -62,6 +62,18 @@ class SpectralFactors:
         self.lam, self.U = lam, vec
         self.L = vec * N.sqrt(N.maximum(lam, 0.0))[:, None, :]
         self.complex = N.iscomplexobj(vec)
+        self._dev = {}                      # device -> (lre, lim): uploaded once, reused by every gnoi()
+
+    def device_factors(self, dev):
+        """L on the device (real and imaginary parts as separate [nf][nc][nc] arrays)."""
+        import torch
+        key = str(dev)
+        if key not in self._dev:
+            lre = torch.as_tensor(N.ascontiguousarray(self.L.real), dtype=torch.float64).to(dev)
+            lim = torch.as_tensor(N.ascontiguousarray(self.L.imag), dtype=torch.float64).to(dev) \
+                if self.complex else None
+            self._dev[key] = (lre, lim)
+        return self._dev[key]
 
     def as_oracle(self):
         return self.lam, self.U
@@ -90,7 +102,7 @@ def electron_factors(efric, exim, exip, bias, T, ecut, dt, nmd, classical=False,
 
 
 # ------------------------------------------------------------------ device pipeline
-MAX_WORK_BYTES = 8 << 30     # FFT scratch bound for noise generation
+MAX_WORK_BYTES = 12 << 30    # FFT scratch bound for noise generation
 
 def white_noise(nf, nc, ldb, seed, stream_id, traj0=0, device=None):
     """Standard normals [nf][nc][ldb] from the library's Philox generator (replaces the
@@ -109,9 +121,7 @@ def generate(factors, xi, dt, nmd, out=None):
     if nf != int(nmd / 2) + 1 or factors.L.shape != (nf, nc, nc):
         raise ValueError("noise.generate: shape mismatch")
     dev = xi.device
-    lre = torch.as_tensor(N.ascontiguousarray(factors.L.real), dtype=torch.float64, device=dev)
-    lim = torch.as_tensor(N.ascontiguousarray(factors.L.imag), dtype=torch.float64, device=dev) \
-        if factors.complex else None
+    lre, lim = factors.device_factors(dev)
     if out is None:
         out = torch.empty((nmd, nc, ldb), dtype=torch.float64, device=dev)
     # component rows are transformed in chunks so that the FFT scratch stays below MAX_WORK_BYTES
