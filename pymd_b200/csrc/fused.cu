@@ -289,9 +289,10 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
 #endif
 
     // ------------------------------------------------------------------ time loop
+    int tn = (int)(P.t0 % P.nmd);               // noise row of time t (noise is periodic in nmd, phbath.py:196)
     for (int s = 0; s < P.nsteps; ++s) {
-        const long long t = P.t0 + s;
-        const int tn = (int)(t % P.nmd), tn1 = (int)((t + 1) % P.nmd);
+        const int tn_cur = tn;
+        const int tn1 = tn + 1 == P.nmd ? 0 : tn + 1;
 
         // ============ round A: first force evaluation at time t, head p(t) ============
         double hA[NT][2];
@@ -324,8 +325,8 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
             if (live) {
                 st2(&sm[xpn + own + 8 * j], pv.x + f0 * dt / 2.0, pv.y + f1 * dt / 2.0);
                 st2(&sm[xq + own + 8 * j], qv.x + pv.x * dt + f0 * dt2 / 2.0, qv.y + pv.y * dt + f1 * dt2 / 2.0);
-                if (P.ps) st2(&P.ps[((size_t)tn * nd + row) * ldb + col0 + n], pv.x, pv.y);
-                if (P.qs) st2(&P.qs[((size_t)tn * nd + row) * ldb + col0 + n], qv.x, qv.y);
+                if (P.ps) st2(&P.ps[((size_t)tn_cur * nd + row) * ldb + col0 + n], pv.x, pv.y);
+                if (P.qs) st2(&P.qs[((size_t)tn_cur * nd + row) * ldb + col0 + n], qv.x, qv.y);
             }
             // column sums over this warp's 8 rows: reduce-scatter, lane lr ends with the sum of v[lr]
             const double r = rs8(v, lr);
@@ -438,8 +439,8 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
             double sum = 0.0;
 #pragma unroll
             for (int ww = 0; ww < FW; ++ww) sum += sm[P.off_curp + (b * FW + ww) * N + n];
-            if (b < nb) P.b[b].cur[(size_t)tn * ldb + col0 + n] = sum;
-            else P.etot[(size_t)tn * ldb + col0 + n] = 0.5 * sum;
+            if (b < nb) P.b[b].cur[(size_t)tn_cur * ldb + col0 + n] = sum;
+            else P.etot[(size_t)tn_cur * ldb + col0 + n] = 0.5 * sum;
         }
         nbuf ^= 1;
         { const int tmp = xpc; xpc = xpn; xpn = tmp; }      // xpc: p(t+1/2), xpn: free (held p(t))
@@ -573,6 +574,7 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
         __syncthreads();                                                        // ---- S1
         TICK(3)
         { const int tmp = xpc; xpc = xpn; xpn = tmp; }      // xpc: p(t+1)
+        tn = tn1;
     }
 
     // ------------------------------------------------------------------ epilogue
