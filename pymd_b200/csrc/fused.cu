@@ -299,9 +299,11 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
         zero_acc<NT>(hA);
         matvec1<NT>(aM, ks, sm + xpc, LD, hA, lr, lc);
         TICK(0)
+        // stage 1: every shared-memory load and all arithmetic for all n-tiles (no stores in between, so
+        // the loads of different n-tiles overlap); stage 2: the stores
+        double phv[NT][2], qnv[NT][2], pvv[NT][2], qvv[NT][2], rsum[NT], c3a[NT], c3b[NT];
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
-            const int n = 8 * j + 2 * lc;
             const double2 pv = ld2(&sm[xpc + own + 8 * j]);
             const double2 qv = ld2(&sm[xq + own + 8 * j]);
             double f0 = fpot[j][0] + uq[j][0] - hA[j][0];
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
             double v[8];                         // kinetic energy and up to three bath currents, two columns each
             v[0] = pv.x * pv.x;
             v[1] = pv.y * pv.y;
-            double c3a = 0.0, c3b = 0.0;
+            c3a[j] = c3b[j] = 0.0;
 #pragma unroll
             for (int b = 0; b < FB_MAX; ++b) {
                 double2 nv = ld2(&sm[nbo[b] + nbuf * nbs[b] + 8 * j]);
@@ -320,23 +322,30 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                 if (HASQ && b == P.aq) { c0 += maq * uq[j][0]; c1 += maq * uq[j][1]; }
                 if (b == P.rem) { c0 -= mrem * hA[j][0]; c1 -= mrem * hA[j][1]; }
                 if (b < 3) { v[2 + 2 * b] = pv.x * c0; v[3 + 2 * b] = pv.y * c1; }
-                else { c3a = pv.x * c0; c3b = pv.y * c1; }
+                else { c3a[j] = pv.x * c0; c3b[j] = pv.y * c1; }
             }
-            if (live) {
-                st2(&sm[xpn + own + 8 * j], pv.x + f0 * dt / 2.0, pv.y + f1 * dt / 2.0);
-                st2(&sm[xq + own + 8 * j], qv.x + pv.x * dt + f0 * dt2 / 2.0, qv.y + pv.y * dt + f1 * dt2 / 2.0);
-                if (P.ps) st2(&P.ps[((size_t)tn_cur * nd + row) * ldb + col0 + n], pv.x, pv.y);
-                if (P.qs) st2(&P.qs[((size_t)tn_cur * nd + row) * ldb + col0 + n], qv.x, qv.y);
-            }
+            pvv[j][0] = pv.x; pvv[j][1] = pv.y;
+            qvv[j][0] = qv.x; qvv[j][1] = qv.y;
+            phv[j][0] = pv.x + f0 * dt / 2.0;
+            phv[j][1] = pv.y + f1 * dt / 2.0;
+            qnv[j][0] = qv.x + pv.x * dt + f0 * dt2 / 2.0;
+            qnv[j][1] = qv.y + pv.y * dt + f1 * dt2 / 2.0;
             // column sums over this warp's 8 rows: reduce-scatter, lane lr ends with the sum of v[lr]
-            const double r = rs8(v, lr);
-            const int qn = lr >> 1;              // 0: kinetic energy, 1..3: bath qn-1
-            if (qn <= nb) sm[P.off_curp + (((qn == 0) ? nb : qn - 1) * FW + w) * N + n + (lr & 1)] = r;
-            if (nb > 3) {
-                c3a = colsum8(c3a);
-                c3b = colsum8(c3b);
-                if (lr == 0) st2(&sm[P.off_curp + (3 * FW + w) * N + n], c3a, c3b);
+            rsum[j] = rs8(v, lr);
+            if (nb > 3) { c3a[j] = colsum8(c3a[j]); c3b[j] = colsum8(c3b[j]); }
+        }
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int n = 8 * j + 2 * lc;
+            if (live) {
+                st2(&sm[xpn + own + 8 * j], phv[j][0], phv[j][1]);
+                st2(&sm[xq + own + 8 * j], qnv[j][0], qnv[j][1]);
+                if (P.ps) st2(&P.ps[((size_t)tn_cur * nd + row) * ldb + col0 + n], pvv[j][0], pvv[j][1]);
+                if (P.qs) st2(&P.qs[((size_t)tn_cur * nd + row) * ldb + col0 + n], qvv[j][0], qvv[j][1]);
             }
+            const int qn = lr >> 1;              // 0: kinetic energy, 1..3: bath qn-1
+            if (qn <= nb) sm[P.off_curp + (((qn == 0) ? nb : qn - 1) * FW + w) * N + n + (lr & 1)] = rsum[j];
+            if (nb > 3 && lr == 0) st2(&sm[P.off_curp + (3 * FW + w) * N + n], c3a[j], c3b[j]);
         }
         // noise of the direct bath at time t+1 (used from round B on)
 #pragma unroll
@@ -456,6 +465,7 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
             else matvec1<NT>(aD, ks, sm + xq, LD, aDq, lr, lc);
             matvec1<NT>(aM, ks, sm + xpc, LD, hB, lr, lc);
             TICK(4)
+            double p1v[NT][2];
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 fpot[j][0] = -aDq[j][0];
@@ -470,10 +480,13 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                 }
                 fb[j][0] = f0;
                 fb[j][1] = f1;
-                if (live) {
-                    const double2 ph = ld2(&sm[xpc + own + 8 * j]);
-                    st2(&sm[xpn + own + 8 * j], ph.x + dt * (f0 - hB[j][0]) / 2.0, ph.y + dt * (f1 - hB[j][1]) / 2.0);
-                }
+                const double2 ph = ld2(&sm[xpc + own + 8 * j]);
+                p1v[j][0] = ph.x + dt * (f0 - hB[j][0]) / 2.0;
+                p1v[j][1] = ph.y + dt * (f1 - hB[j][1]) / 2.0;
+            }
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < NT; ++j) st2(&sm[xpn + own + 8 * j], p1v[j][0], p1v[j][1]);
             }
         }
         TICK(5)
@@ -493,6 +506,10 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                 const double2 ph = ld2(&sm[xpn + own + 8 * j]);
                 pn[j][0] = live ? ph.x + dt * (fb[j][0] - hC[j][0]) / 2.0 : 0.0;
                 pn[j][1] = live ? ph.y + dt * (fb[j][1] - hC[j][1]) / 2.0 : 0.0;
+                if (HASCON) {
+                    const double2 q0 = ld2(&sm[xq + own + 8 * j]);
+                    qn[j][0] = q0.x; qn[j][1] = q0.y;
+                }
             }
             if (HASCON) {
                 // md.ApplyConstraint (md.py:739-762) with one constraint vector: the dots c.p', c.q' are
@@ -501,7 +518,7 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                 const double dv = sm[P.off_conv + NDP + row];
                 const double av = HASQ ? sm[P.off_conv + 2 * NDP + row] : 0.0;
                 constexpr int NG = (4 * NT + 7) / 8;
-                double tot[NG];
+                double tot[NG], part[NG];
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     double v[8];
@@ -509,15 +526,13 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                     for (int i = 0; i < 8; ++i) {
                         const int vi = 8 * g + i, j = vi >> 2, kind = vi & 3;       // d0, d1, g0, g1 of n-tile j
                         double x = 0.0;
-                        if (j < NT) {
-                            if (kind < 2) x = pn[j][kind] * cv;
-                            else x = (kind == 2 ? sm[xq + own + 8 * j] : sm[xq + own + 8 * j + 1]) * cv;
-                        }
+                        if (j < NT) x = (kind < 2 ? pn[j < NT ? j : 0][kind] : qn[j < NT ? j : 0][kind - 2]) * cv;
                         v[i] = x;
                     }
-                    const double r = rs8(v, lr);
-                    sm[P.off_conp + ((8 * g + lr) * FW + w) * 4 + lc] = r;
+                    part[g] = rs8(v, lr);
                 }
+#pragma unroll
+                for (int g = 0; g < NG; ++g) sm[P.off_conp + ((8 * g + lr) * FW + w) * 4 + lc] = part[g];
                 TICK(7)
                 __syncthreads();                                                // ---- S4
                 TICK(3)
@@ -537,34 +552,40 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                         const int vi = 4 * j + kind;
                         d[kind] = __shfl_sync(0xffffffffu, tot[vi >> 3], ((vi & 7) << 2) | lc);
                     }
-                    const double2 q0 = ld2(&sm[xq + own + 8 * j]);
                     pn[j][0] -= d[0] * cv;
                     pn[j][1] -= d[1] * cv;
-                    qn[j][0] = q0.x - d[2] * cv;
-                    qn[j][1] = q0.y - d[3] * cv;
+                    qn[j][0] -= d[2] * cv;
+                    qn[j][1] -= d[3] * cv;
                     // md.sameq (md.py:724-736): max_i |q(t+1)_i - q'_i| = |dq| max_i |c_i|; when it reaches 1e-9
                     // the cached force is dropped: -D q(t+1) = -D q' + dq (D c) by linearity
                     if (!(fabs(d[2]) * P.cmax < 10e-10)) fpot[j][0] += d[2] * dv;
                     if (!(fabs(d[3]) * P.cmax < 10e-10)) fpot[j][1] += d[3] * dv;
                     if (HASQ) { uq[j][0] -= d[2] * av; uq[j][1] -= d[3] * av; }      // AqT q(t+1)
-                    if (live) st2(&sm[xq + own + 8 * j], qn[j][0], qn[j][1]);
                 }
             }
             if (live) {
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
-                    const int n = 8 * j + 2 * lc;
                     st2(&sm[xpn + own + 8 * j], pn[j][0], pn[j][1]);
-                    // p_c(t+1) enters the block history / the HBM ring
+                    if (HASCON) st2(&sm[xq + own + 8 * j], qn[j][0], qn[j][1]);
+                }
+                // p_c(t+1) enters the block history / the HBM ring
 #pragma unroll
-                    for (int b = 0; b < FB_MAX; ++b) {
-                        if (ip[b] < 0 || P.b[b].direct) continue;
-                        const FusedBath& B = P.b[b];
-                        if (!B.nonlocal) st2(&sm[B.off_hist + ip[b] * LD + n], pn[j][0], pn[j][1]);
-                        else if (s + 1 < P.nsteps) {
-                            st2(&sm[B.off_hist + ((s + 1) * B.ncp + ip[b]) * LD + n], pn[j][0], pn[j][1]);
-                            const int slot = (B.slot0 + s + 1) % B.R;
-                            st2(&B.ring[((size_t)slot * B.ncp + ip[b]) * ldb + col0 + n], pn[j][0], pn[j][1]);
+                for (int b = 0; b < FB_MAX; ++b) {
+                    if (ip[b] < 0 || P.b[b].direct) continue;
+                    const FusedBath& B = P.b[b];
+                    if (!B.nonlocal) {
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) st2(&sm[B.off_hist + ip[b] * LD + 8 * j + 2 * lc], pn[j][0], pn[j][1]);
+                    } else if (s + 1 < P.nsteps) {
+                        const int hb = B.off_hist + ((s + 1) * B.ncp + ip[b]) * LD + 2 * lc;
+                        int slot = B.slot0 + s + 1;
+                        if (slot >= B.R) slot -= B.R;
+                        double* rp = &B.ring[((size_t)slot * B.ncp + ip[b]) * ldb + col0 + 2 * lc];
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) {
+                            st2(&sm[hb + 8 * j], pn[j][0], pn[j][1]);
+                            st2(rp + 8 * j, pn[j][0], pn[j][1]);
                         }
                     }
                 }
