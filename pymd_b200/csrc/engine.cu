@@ -27,6 +27,8 @@ void pymd_set_error(const char* fmt, ...) {
 
 namespace pymd {
 
+int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st, long long wmax = -1,
+                const double* bias = nullptr);
 int fused_supported(const pymd_ctx* c);
 int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t stream);
 
@@ -266,6 +268,11 @@ int finalize(pymd_ctx* c) {
                 for (int e = 0; e < nc * nc; ++e)
                     kin[(size_t)(k - 1) * nc * nc + e] = c->dt * H.kernel[(size_t)k * nc * nc + e];
             if ((rc = upload(&H.d_kintra, kin))) return rc;
+            if (far_supported(H)) {
+                if ((rc = far_build(c, b))) return rc;
+            } else if (H.d_ghat) {
+                cudaFree(H.d_ghat); H.d_ghat = nullptr;
+            }
             ws_doubles += (size_t)2 * kBlockT * nc * ldb;
         }
         ws_doubles += (size_t)2 * H.ncp * ldb;
@@ -334,14 +341,20 @@ static int gemm_plain(pymd_ctx* c, const double* A, int lda, int M, int K, const
 }
 
 // out[s][i][n] = dt * sum_{lag>=0} K[s + koff + lag][i][:] . ring(newest - lag)[:][n],  s < T
-int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st) {
+// wmax >= 0 limits the product to the newest wmax ring rows (the older ones are covered by the far
+// field `bias`, far.cu: out = bias + product).
+int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st, long long wmax,
+                const double* bias) {
     BathHost& H = c->bath[b];
     const int R = H.R, ncp = H.ncp;
     long long W = H.ml - koff;                 // lags 0 .. ml-1-koff contribute
+    if (wmax >= 0 && W > wmax) W = wmax;
     if (W > H.hcount) W = H.hcount;
     if (W > R) W = R;
     if (W <= 0) {
-        PYMD_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)T * H.nc * c->ldb * sizeof(double), st));
+        const size_t bytes = (size_t)T * H.nc * c->ldb * sizeof(double);
+        if (bias) PYMD_CUDA_CHECK(cudaMemcpyAsync(out, bias, bytes, cudaMemcpyDeviceToDevice, st));
+        else PYMD_CUDA_CHECK(cudaMemsetAsync(out, 0, bytes, st));
         return PYMD_OK;
     }
     const int h = (int)((H.hcount - 1) % R);
@@ -360,7 +373,7 @@ int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t s
         g.seg_lo[0] = 0; g.seg_hi[0] = (h + 1) * ncp; g.seg_aoff[0] = base;
         g.seg_lo[1] = (lo + R) * ncp; g.seg_hi[1] = R * ncp; g.seg_aoff[1] = base - (long long)R * ncp;
     }
-    g.alpha = c->dt; g.accumulate = 0;
+    g.alpha = c->dt; g.accumulate = 0; g.bias_base = bias;
     c->launches++;
     prof_begin(c, 0, st);
     const int rc = launch_gemm(g, st);
@@ -473,7 +486,7 @@ int pymd_ctx_destroy(pymd_ctx* c) {
     if (!c) return PYMD_OK;
     for (auto& H : c->bath) {
         cudaFree(H.d_cids); cudaFree(H.d_inv); cudaFree(H.d_head); cudaFree(H.d_aq);
-        cudaFree(H.d_krev); cudaFree(H.d_kintra);
+        cudaFree(H.d_krev); cudaFree(H.d_kintra); cudaFree(H.d_ghat); cudaFree(H.d_far);
     }
     cudaFree(c->d_dyn); cudaFree(c->d_mp); cudaFree(c->d_con); cudaFree(c->d_aqT); cudaFree(c->d_con3); cudaFree(c->ws);
     delete c;
@@ -570,6 +583,7 @@ int pymd_reset_history(pymd_ctx* c, void* stream) {
         if (H.ml > 1 && c->sd.b[b].ring)
             PYMD_CUDA_CHECK(cudaMemsetAsync(c->sd.b[b].ring, 0, (size_t)H.R * H.ncp * c->ldb * sizeof(double), st));
         H.hcount = 0;
+        H.far_valid = false;
     }
     c->tail_valid = false;
     return PYMD_OK;
@@ -590,6 +604,7 @@ static int history_copy(pymd_ctx* c, int b, double* dense, int nrows, int to_rin
         PYMD_CUDA_CHECK(cudaMemsetAsync(c->sd.b[b].ring, 0, (size_t)H.R * H.ncp * c->ldb * sizeof(double),
                                         static_cast<cudaStream_t>(stream)));
         H.hcount = nrows;
+        H.far_valid = false;
         c->tail_valid = false;
     }
     history_copy_kernel<<<592, 256, 0, static_cast<cudaStream_t>(stream)>>>(

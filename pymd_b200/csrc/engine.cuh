@@ -9,6 +9,8 @@
 namespace pymd {
 
 constexpr int kBlockT = 16;   // time-block length of the fused path (ring sizing uses it too)
+constexpr int kFarS = 32;     // super-block length of the FFT far field (far.cu)
+constexpr int kFarMinMl = 24; // shorter memories stay on the direct block-Toeplitz product
 
 struct BathDev {
     int nc, ncp, ml, R;
@@ -48,6 +50,10 @@ struct BathHost {
     double* d_aq = nullptr;       // [ncp][lda]
     double* d_krev = nullptr;     // [nc][Lk]    reversed, padded kernel table (tail operand)
     double* d_kintra = nullptr;   // [kBlockT][nc][nc] dt*K[1..T] for the fused path
+    double* d_ghat = nullptr;     // far.cu: transformed kernel as DMMA A fragments
+    double* d_far = nullptr;      // far.cu: [kFarS][nc][ldb] far field of the current super-block
+    bool far_valid = false;
+    long long far_base = 0;       // hcount at the start of the super-block d_far belongs to
     long long Lk = 0;
     int padf = 0;
     int lda = 0;
@@ -80,6 +86,9 @@ struct pymd_ctx {
 };
 
 namespace pymd {
+bool far_supported(const BathHost& H);
+int far_build(pymd_ctx* c, int b);
+int far_launch(pymd_ctx* c, unsigned mask, cudaStream_t st);
 inline void prof_begin(pymd_ctx* c, int cls, cudaStream_t st) {
     if (!c->prof) return;
     pymd_ctx::ProfRec r;

@@ -28,7 +28,8 @@
 
 namespace pymd {
 
-int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st);
+int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st, long long wmax = -1,
+                const double* bias = nullptr);
 
 namespace {
 
@@ -793,13 +794,31 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
     cudaMemsetAsync(d_timing, 0, 8 * sizeof(long long), st);
     fp.timing = d_timing;
 #endif
+    const bool far_on = !(getenv("PYMD_FAR") && atoi(getenv("PYMD_FAR")) == 0);          // testing knob
     for (int done = 0; done < nsteps; done += FT) {
         const int ns = std::min(FT, nsteps - done);
+        // far field (far.cu): history older than the current super-block of kFarS steps, one FFT
+        // convolution per super-block; a new super-block starts whenever this block leaves the old one
+        unsigned need = 0;
+        for (int b = 0; b < c->nbath; ++b) {
+            BathHost& H = c->bath[b];
+            if (H.ml <= 1 || !H.d_ghat || !far_on) continue;
+            const long long r0 = H.hcount - H.far_base;
+            if (!H.far_valid || r0 < 0 || r0 + ns > kFarS) need |= 1u << b;
+        }
+        if (need && (rc = far_launch(c, need, st))) return rc;
         for (int b = 0; b < c->nbath; ++b) {
             BathHost& H = c->bath[b];
             if (H.ml > 1) {
                 // pre-block part: history older than this block, read once for ns steps
-                if ((rc = launch_tail(c, b, ns, 2, d.b[b].tail_next, st))) return rc;
+                if (H.d_ghat && far_on) {
+                    // ... of which only the rows since p(u0-1) are multiplied directly
+                    const long long r0 = H.hcount - H.far_base;
+                    rc = launch_tail(c, b, ns, 2, d.b[b].tail_next, st, r0 + 1, H.d_far + (size_t)r0 * H.nc * c->ldb);
+                } else {
+                    rc = launch_tail(c, b, ns, 2, d.b[b].tail_next, st);
+                }
+                if (rc) return rc;
                 fp.b[b].slot0 = (int)(H.hcount % H.R);
             }
         }

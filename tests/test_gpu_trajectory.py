@@ -314,3 +314,36 @@ def test_external_driver_is_refused(cuda):
 def test_smoke_case(cuda):
     import smoke_case
     assert smoke_case.run(verbose=False) < 1e-10
+
+
+@pytest.mark.parametrize("case,nmd", [("chain39", 512), ("aubz", 256)])
+def test_far_field_fft_against_direct_product_and_oracle(cuda, case, nmd, monkeypatch):
+    """The FFT far field (csrc/far.cu, super-blocks of 32 steps) against the direct block-Toeplitz
+    product (PYMD_FAR=0) over several full 97-entry windows, with ragged steps() calls so that
+    super-blocks start at arbitrary times; and against the oracle over the whole horizon."""
+    c = dict(T.CASES[case]); c["nmd"] = nmd
+    batch = 9
+    runs = {}
+    for far in ("1", "0"):
+        monkeypatch.setenv("PYMD_FAR", far)
+        m, j = T.device_md(c, batch, step_mode=2)
+        xi, r = T.draw(c, m, batch, seed=13)
+        m.initialise(r=r)
+        m.ResetHis()
+        for b, bath in enumerate(m.baths):
+            bath.gnoi(xi=xi[0][b])
+        m.ResetSavepq()
+        done = 0
+        for n in [3, 8, 29, 1, 64, 7, 100, 40]:
+            n = min(n, nmd - done)
+            if n:
+                m.steps(n)
+                done += n
+        m.steps(nmd - done)
+        runs[far] = (m, [np.array(b.cur) for b in m.baths], np.array(m.ps), np.array(m.qs))
+    (m1, cur1, ps1, qs1), (m0, cur0, ps0, qs0) = runs["1"], runs["0"]
+    assert T.relerr(ps1, ps0) < 1e-12 and T.relerr(qs1, qs0) < 1e-12
+    for a, b in zip(cur1, cur0):
+        assert np.abs(a - b).max() < 1e-11 * max(np.abs(b).max(), 1e-300)
+    om, recs = T.run_oracle(c, j, m1, xi, r, 4, nmd)
+    compare(m1, recs[0], 4, tol=3e-11)
