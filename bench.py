@@ -265,12 +265,12 @@ def run_ours(a):
     import ctypes
     _lib.call("pymd_profile_enable", m._ctx, 1)
     m.steps(PIECE)
-    ms4 = (ctypes.c_double * 4)()
-    cnt4 = (ctypes.c_longlong * 4)()
+    ms4 = (ctypes.c_double * 8)()
+    cnt4 = (ctypes.c_longlong * 8)()
     _lib.call("pymd_profile_read", m._ctx, ctypes.addressof(ms4), ctypes.addressof(cnt4))
     _lib.call("pymd_profile_enable", m._ctx, 0)
-    names = ["tail_gemm", "fused_step", "other_gemm", "stage_kernels"]
-    kern = {names[i]: dict(ms=ms4[i], launches=int(cnt4[i])) for i in range(4) if cnt4[i]}
+    names = ["tail_gemm", "fused_step", "other_gemm", "stage_kernels", "far_fft"]
+    kern = {names[i]: dict(ms=ms4[i], launches=int(cnt4[i])) for i in range(5) if cnt4[i]}
     fl = algorithmic_flops()
     tot_ms = sum(v["ms"] for v in kern.values())
     roof = None

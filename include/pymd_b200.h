@@ -94,11 +94,13 @@ int pymd_step(pymd_ctx* ctx, long long t0, int nsteps, int mode, void* stream);
 long long pymd_launch_count(const pymd_ctx* ctx);
 /* Per-kernel-class device timing with CUDA events on the launching stream (measurement aid for
  * bench.py's roofline; adds an event pair per launch while enabled).  Classes: 0 = memory-kernel
- * tail GEMM, 1 = fused step kernel, 2 = other tensor-core GEMMs, 3 = elementwise stage kernels.
- * pymd_profile_read synchronises, writes the accumulated milliseconds and launch counts of the 4
+ * tail GEMM, 1 = fused step kernel, 2 = other tensor-core GEMMs, 3 = elementwise stage kernels,
+ * 4 = FFT far field of the memory kernel, 5..7 unused.
+ * pymd_profile_read synchronises, writes the accumulated milliseconds and launch counts of the 8
  * classes and clears them. */
+#define PYMD_PROFILE_CLASSES 8
 int pymd_profile_enable(pymd_ctx* ctx, int on);
-int pymd_profile_read(pymd_ctx* ctx, double* ms4, long long* count4);
+int pymd_profile_read(pymd_ctx* ctx, double* ms8, long long* count8);
 
 /* ---- noise generation: noise.phnoise / noise.enoise (noise.py:38-88, 135-190) --------
  * factors: L[f] = U_f diag(sqrt(max(lambda_f,0))) for f = 0..nmd/2, dev [nf][nc][nc]

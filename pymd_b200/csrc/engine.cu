@@ -486,7 +486,7 @@ int pymd_ctx_destroy(pymd_ctx* c) {
     if (!c) return PYMD_OK;
     for (auto& H : c->bath) {
         cudaFree(H.d_cids); cudaFree(H.d_inv); cudaFree(H.d_head); cudaFree(H.d_aq);
-        cudaFree(H.d_krev); cudaFree(H.d_kintra); cudaFree(H.d_ghat); cudaFree(H.d_far);
+        cudaFree(H.d_krev); cudaFree(H.d_kintra); cudaFree(H.d_ghat); cudaFree(H.d_far); cudaFree(H.d_kmid);
     }
     cudaFree(c->d_dyn); cudaFree(c->d_mp); cudaFree(c->d_con); cudaFree(c->d_aqT); cudaFree(c->d_con3); cudaFree(c->ws);
     delete c;
@@ -647,10 +647,10 @@ int pymd_profile_enable(pymd_ctx* c, int on) {
 int pymd_profile_read(pymd_ctx* c, double* ms4, long long* count4) {
     PYMD_REQUIRE(c && ms4 && count4, "profile_read: null argument");
     PYMD_CUDA_CHECK(cudaDeviceSynchronize());
-    for (int i = 0; i < 4; ++i) { ms4[i] = 0.0; count4[i] = 0; }
+    for (int i = 0; i < PYMD_PROFILE_CLASSES; ++i) { ms4[i] = 0.0; count4[i] = 0; }
     for (auto& r : c->prof_recs) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && r.cls >= 0 && r.cls < 4) {
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && r.cls >= 0 && r.cls < PYMD_PROFILE_CLASSES) {
             ms4[r.cls] += ms;
             count4[r.cls]++;
         }

@@ -11,6 +11,7 @@ namespace pymd {
 constexpr int kBlockT = 16;   // time-block length of the fused path (ring sizing uses it too)
 constexpr int kFarS = 32;     // super-block length of the FFT far field (far.cu)
 constexpr int kFarMinMl = 24; // shorter memories stay on the direct block-Toeplitz product
+constexpr int kMidK = 8 + kFarS;  // memory-kernel taps k = 2 .. 2+kMidK-1 can meet rows of the current super-block
 
 struct BathDev {
     int nc, ncp, ml, R;
@@ -52,6 +53,7 @@ struct BathHost {
     double* d_kintra = nullptr;   // [kBlockT][nc][nc] dt*K[1..T] for the fused path
     double* d_ghat = nullptr;     // far.cu: transformed kernel as DMMA A fragments
     double* d_far = nullptr;      // far.cu: [kFarS][nc][ldb] far field of the current super-block
+    double* d_kmid = nullptr;     // [kMidK][ncp/8][ncp/4][32] A fragments of dt K[k], k = 2.. (fused mid field)
     bool far_valid = false;
     long long far_base = 0;       // hcount at the start of the super-block d_far belongs to
     long long Lk = 0;

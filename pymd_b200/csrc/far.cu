@@ -264,8 +264,9 @@ int init_twiddles() {
 }  // namespace
 
 bool far_supported(const BathHost& H) {
-    // the 97-entry window + 32 outputs fill the length-128 transform exactly; 8*ncp series per CTA
-    return H.ml >= kFarMinMl && H.ml <= 100 && H.ncp <= 24 && H.R >= H.ml - 2;
+    // the 97-entry window + 32 outputs fill the length-128 transform exactly; the in-kernel mid field
+    // of fused.cu holds one tap (ncp x ncp) as at most 2 x 4 register fragments
+    return H.ml >= kFarMinMl && H.ml <= 100 && H.ncp <= 16 && H.R >= H.ml - 2;
 }
 
 // Host side, once per bath: Ghat[f] = (1/128) sum_d dt K[d+99] exp(-2 pi i f d / 128), d = -96..31,
@@ -298,6 +299,19 @@ int far_build(pymd_ctx* c, int b) {
     if (H.d_ghat) cudaFree(H.d_ghat);
     PYMD_CUDA_CHECK(cudaMalloc(&H.d_ghat, frag.size() * sizeof(double)));
     PYMD_CUDA_CHECK(cudaMemcpy(H.d_ghat, frag.data(), frag.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // dt K[k], k = 2 .. 2+kMidK-1, in the same fragment order, for the rows of the current super-block
+    std::vector<double> km((size_t)kMidK * MT * KK * 32, 0.0);
+    for (int kidx = 0; kidx < kMidK; ++kidx) {
+        const int k = kidx + 2;
+        if (k > H.ml - 1) break;
+        for (int i = 0; i < nc; ++i)
+            for (int j = 0; j < nc; ++j)
+                km[(((size_t)kidx * MT + i / 8) * KK + j / 4) * 32 + (i % 8) * 4 + j % 4] =
+                    c->dt * H.kernel[((size_t)k * nc + i) * nc + j];
+    }
+    if (H.d_kmid) cudaFree(H.d_kmid);
+    PYMD_CUDA_CHECK(cudaMalloc(&H.d_kmid, km.size() * sizeof(double)));
+    PYMD_CUDA_CHECK(cudaMemcpy(H.d_kmid, km.data(), km.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (H.d_far) cudaFree(H.d_far);
     PYMD_CUDA_CHECK(cudaMalloc(&H.d_far, (size_t)kFarS * nc * c->ldb * sizeof(double)));
     H.far_valid = false;
@@ -312,7 +326,7 @@ int far_launch_t(pymd_ctx* c, const FarParams& P, int nb, cudaStream_t st) {
         PYMD_CUDA_CHECK(cudaFuncSetAttribute(far_kernel<NCP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    prof_begin(c, 0, st);
+    prof_begin(c, 4, st);
     far_kernel<NCP><<<dim3(c->ldb / NTRAJ, nb), FAR_THREADS, smem, st>>>(P);
     prof_end(c, st);
     c->launches++;
@@ -323,7 +337,7 @@ int far_launch_t(pymd_ctx* c, const FarParams& P, int nb, cudaStream_t st) {
 // Far fields of the super-block that starts now (ring state: hcount rows appended) for every bath
 // in `mask`; one launch per distinct padded bath size.
 int far_launch(pymd_ctx* c, unsigned mask, cudaStream_t st) {
-    for (int ncp : {8, 16, 24}) {
+    for (int ncp : {8, 16}) {
         FarParams P{};
         P.ldb = c->ldb;
         int nb = 0;
@@ -337,7 +351,7 @@ int far_launch(pymd_ctx* c, unsigned mask, cudaStream_t st) {
             H.far_valid = true;
         }
         if (!nb) continue;
-        int rc = ncp == 8 ? far_launch_t<8>(c, P, nb, st) : ncp == 16 ? far_launch_t<16>(c, P, nb, st) : far_launch_t<24>(c, P, nb, st);
+        int rc = ncp == 8 ? far_launch_t<8>(c, P, nb, st) : far_launch_t<16>(c, P, nb, st);
         if (rc) return rc;
     }
     return PYMD_OK;

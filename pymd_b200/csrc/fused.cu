@@ -53,10 +53,16 @@ struct FusedBath {
     const double* kin_g;      // [kBlockT][nc][nc]
     const int* cids_g;
     const int* inv_g;
+    // in-kernel mid field (mid == 1): A fragments of dt K[k], k = 2..2+kMidK-1, and the far field
+    const double* kmid;       // [kMidK][ncp/8][ncp/4][32]
+    const double* F;          // [kFarS][nc][ldb] rows of the current super-block
 };
 
 struct FusedParams {
     int nd, ks, ldb, ldn, nbath, nmd, ncon, nsteps, rem, aq, carry_valid;
+    int mid;                  // 1: several blocks per launch, pre-block tails computed in the kernel
+    int r0;                   // steps since the start of the super-block at launch
+    long long hc0;            // history rows appended before p(t0)
     long long t0;
     double dt;
     double *p, *q, *ps, *qs, *etot, *fpotn;
@@ -134,6 +140,119 @@ __device__ __forceinline__ void matvec2(const double (&a0)[MAXKS], const double 
     }
 }
 
+// Pre-block tail of one block of up to FT steps, computed in the kernel (mid mode):
+//   P[s] = F[r0b+s] + dt sum_{a=0}^{W-1} K[s+2+a] p_c(t0-1-a),   W = rows since p(u0-1) (far.cu covers the rest).
+// Warp w owns step s = w: A fragments (dt K[w+2+a], pre-swizzled on the host) come from L2 one ring
+// row ahead of their use, the history rows are staged from the HBM ring through the free head
+// buffer, 64/ncp rows at a time, with the next stage prefetched into registers while the current
+// one is multiplied.  MT x KQ = m8 x k4 fragments of one ncp x ncp tap.
+template <int NT, int MT, int KQ>
+__device__ __forceinline__ void mid_bath(const FusedParams& P, const FusedBath& B, double* stage, int nsblk, int g,
+                                         int col0) {
+    constexpr int N = 8 * NT, LD = N + 4, ncp = 8 * MT, nA = MT * KQ;
+    constexpr int spst = NDP / ncp;                     // ring rows per stage
+    constexpr int per_slot = ncp * (N / 2);             // double2 per ring-row tile
+    constexpr int NPF = (spst * per_slot + FW * 32 - 1) / (FW * 32);
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+    const size_t ldb = P.ldb;
+    const int r0b = P.r0 + g, slotb = (B.slot0 + g) % B.R;
+    long long Wl = r0b + 1;
+    if (Wl > P.hc0 + g) Wl = P.hc0 + g;
+    if (Wl > B.ml - 2) Wl = B.ml - 2;
+    const int W = (int)Wl;
+    const bool mine = w < nsblk;
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[mt][j][0] = acc[mt][j][1] = 0.0;
+    // this thread's share of a stage: element e = tid + i * 256 -> (ring row sl, bath row j, column pair c2)
+    double2 pf[NPF];
+    auto fetch = [&](int a0) {
+#pragma unroll
+        for (int i = 0; i < NPF; ++i) {
+            const int e = tid + i * FW * 32;
+            const int sl = e / per_slot, j = (e % per_slot) / (N / 2), c2 = e % (N / 2);
+            pf[i] = make_double2(0.0, 0.0);
+            if (e < spst * per_slot && a0 + sl < W) {
+                int slot = slotb - 1 - a0 - sl;
+                if (slot < 0) slot += B.R;
+                pf[i] = __ldcg(reinterpret_cast<const double2*>(&B.ring[((size_t)slot * ncp + j) * ldb + col0 + 2 * c2]));
+            }
+        }
+    };
+    const double* Anext = B.kmid + ((size_t)w * nA) * 32 + lane;
+    double ac[nA], an[nA];
+    if (W > 0) {
+        fetch(0);
+        if (mine) {
+#pragma unroll
+            for (int i = 0; i < nA; ++i) an[i] = __ldg(Anext + i * 32);
+            Anext += nA * 32;
+        }
+    }
+    for (int a0 = 0; a0 < W; a0 += spst) {
+        __syncthreads();                                // previous stage fully consumed
+#pragma unroll
+        for (int i = 0; i < NPF; ++i) {
+            const int e = tid + i * FW * 32;
+            const int sl = e / per_slot, j = (e % per_slot) / (N / 2), c2 = e % (N / 2);
+            if (e < spst * per_slot) *reinterpret_cast<double2*>(&stage[(sl * ncp + j) * LD + 2 * c2]) = pf[i];
+        }
+        __syncthreads();
+        if (a0 + spst < W) fetch(a0 + spst);
+        if (mine) {
+            const int na = min(spst, W - a0);
+            for (int sl = 0; sl < na; ++sl) {
+#pragma unroll
+                for (int i = 0; i < nA; ++i) ac[i] = an[i];
+                if (a0 + sl + 1 < W) {
+#pragma unroll
+                    for (int i = 0; i < nA; ++i) an[i] = __ldg(Anext + i * 32);
+                    Anext += nA * 32;
+                }
+                const double* H = stage + (sl * ncp + lc) * LD + lr;
+#pragma unroll
+                for (int kq = 0; kq < KQ; ++kq) {
+                    double bf[NT];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) bf[j] = H[(4 * kq) * LD + 8 * j];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) dmma884(acc[mt][j][0], acc[mt][j][1], ac[mt * KQ + kq], bf[j]);
+                }
+            }
+        }
+    }
+    if (mine) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int rr = mt * 8 + lr;
+            if (rr < B.nc) {
+                const double* Fr = B.F + ((size_t)(r0b + w) * B.nc + rr) * ldb + col0 + 2 * lc;
+                double* Pr = const_cast<double*>(B.P) + ((size_t)w * B.nc + rr) * ldb + col0 + 2 * lc;
+                double2 f[NT];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) f[j] = __ldcg(reinterpret_cast<const double2*>(Fr + 8 * j));
+#pragma unroll
+                for (int j = 0; j < NT; ++j) st2(Pr + 8 * j, f[j].x + acc[mt][j][0], f[j].y + acc[mt][j][1]);
+            }
+        }
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void mid_phase(const FusedParams& P, double* sm, int stage_off, int nsblk, int g, int col0) {
+    for (int b = 0; b < P.nbath; ++b) {
+        const FusedBath& B = P.b[b];
+        if (!B.nonlocal) continue;
+        if (B.ncp == 16) mid_bath<NT, 2, 4>(P, B, sm + stage_off, nsblk, g, col0);
+        else mid_bath<NT, 1, 2>(P, B, sm + stage_off, nsblk, g, col0);      // far_supported: ncp is 8 or 16
+    }
+    __syncthreads();                                    // P visible to every warp; staging buffer free again
+}
+
 template <int NT, bool HASQ, bool HASCON>
 __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) {
     constexpr int N = 8 * NT, LD = N + 4;
@@ -175,14 +294,6 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
     if (HASCON)
         for (int e = tid; e < 3 * P.ncon * nd; e += FW * 32) sm[P.off_conv + (e / nd) * NDP + e % nd] = P.con3[e];
 
-    double aD[MAXKS], aM[MAXKS], aQ[MAXKS];
-#pragma unroll
-    for (int k = 0; k < MAXKS; ++k) {
-        const bool ok = k < ks && live;
-        aD[k] = ok ? P.dyn[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
-        aM[k] = ok ? P.mp[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
-        aQ[k] = (HASQ && ok) ? P.aqT[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
-    }
     // per-thread bath membership of the owned row: index into the bath's dofs or -1; smem offset of
     // the row's noise-minus-tail entry (a zero row when the dof is not coupled to the bath)
     int ip[FB_MAX], nbo[FB_MAX], nbs[FB_MAX];      // nbs: double-buffer stride (0 for the zero row)
@@ -265,24 +376,9 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
     double fpot[NT][2], uq[NT][2];              // -D q and AqT q at the current q, own rows
     zero_acc<NT>(fpot);
     zero_acc<NT>(uq);
-    if (HASQ) matvec2<NT>(aD, aQ, ks, sm + xq, LD, fpot, uq, lr, lc);
-    else matvec1<NT>(aD, ks, sm + xq, LD, fpot, lr, lc);
-#pragma unroll
-    for (int j = 0; j < NT; ++j) { fpot[j][0] = -fpot[j][0]; fpot[j][1] = -fpot[j][1]; }
-    if (HASCON) {
-        // constrained runs carry md.potforce's cache (md.py:456-457) across launches
-        if (P.carry_valid && live) {
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                const int n = col0 + 8 * j + 2 * lc;
-                if (P.samef[n]) fpot[j][0] = P.fpotn[(size_t)row * ldb + n];
-                if (P.samef[n + 1]) fpot[j][1] = P.fpotn[(size_t)row * ldb + n + 1];
-            }
-        }
-    }
     int nbuf = 0;                               // NB buffer holding noise-minus-tail at time t
 #ifdef PYMD_FUSED_TIMING
-    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
 #define TICK(i) { const long long _n = clock64(); tacc[i] += _n - tlast; tlast = _n; }
 #else
@@ -291,7 +387,43 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
 
     // ------------------------------------------------------------------ time loop
     int tn = (int)(P.t0 % P.nmd);               // noise row of time t (noise is periodic in nmd, phbath.py:196)
-    for (int s = 0; s < P.nsteps; ++s) {
+    for (int g0 = 0; g0 < P.nsteps; g0 += FT) {
+    // ---- block of up to FT steps.  Pre-block tails first (mid mode), while the register file is
+    // still free of the operator fragments, which are (re)loaded for every block.
+    if (P.mid) {
+        TICK(9)
+        mid_phase<NT>(P, sm, xpn, min(FT, P.nsteps - g0), g0, col0);
+        TICK(8)
+    }
+    double aD[MAXKS], aM[MAXKS], aQ[MAXKS];
+#pragma unroll
+    for (int k = 0; k < MAXKS; ++k) {
+        const bool ok = k < ks && live;
+        aD[k] = ok ? P.dyn[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
+        aM[k] = ok ? P.mp[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
+        aQ[k] = (HASQ && ok) ? P.aqT[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
+    }
+    if (g0 == 0) {
+        // forces at the initial q
+        if (HASQ) matvec2<NT>(aD, aQ, ks, sm + xq, LD, fpot, uq, lr, lc);
+        else matvec1<NT>(aD, ks, sm + xq, LD, fpot, lr, lc);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) { fpot[j][0] = -fpot[j][0]; fpot[j][1] = -fpot[j][1]; }
+        if (HASCON) {
+            // constrained runs carry md.potforce's cache (md.py:456-457) across launches
+            if (P.carry_valid && live) {
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const int n = col0 + 8 * j + 2 * lc;
+                    if (P.samef[n]) fpot[j][0] = P.fpotn[(size_t)row * ldb + n];
+                    if (P.samef[n + 1]) fpot[j][1] = P.fpotn[(size_t)row * ldb + n + 1];
+                }
+            }
+        }
+    }
+    const int gend = min(P.nsteps, g0 + FT);
+    for (int g = g0; g < gend; ++g) {
+        const int s = g - g0;                   // step within the block
         const int tn_cur = tn;
         const int tn1 = tn + 1 == P.nmd ? 0 : tn + 1;
 
@@ -305,7 +437,8 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
         double phv[NT][2], qnv[NT][2], pvv[NT][2], qvv[NT][2], rsum[NT], c3a[NT], c3b[NT];
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
-            const double2 pv = ld2(&sm[xpc + own + 8 * j]);
+            // padding rows (row >= nd) of the head buffers may hold staged history rows (mid_phase)
+            const double2 pv = live ? ld2(&sm[xpc + own + 8 * j]) : make_double2(0.0, 0.0);
             const double2 qv = ld2(&sm[xq + own + 8 * j]);
             double f0 = fpot[j][0] + uq[j][0] - hA[j][0];
             double f1 = fpot[j][1] + uq[j][1] - hA[j][1];
@@ -398,7 +531,7 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                     for (int j = 0; j < NT; ++j) {
                         const double t0v = pt[j].x + acc[j][0], t1v = pt[j].y + acc[j][1];
                         st2(&sm[B.off_nb + ((nbuf ^ 1) * B.ncp + rr) * LD + 8 * j + 2 * lc], xi[j].x - t0v, xi[j].y - t1v);
-                        if (B.nonlocal && s == P.nsteps - 1)
+                        if (B.nonlocal && g == P.nsteps - 1)
                             st2(&B.tail_cur[(size_t)rr * ldb + col0 + 8 * j + 2 * lc], t0v, t1v);
                     }
                 }
@@ -578,10 +711,9 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                     if (!B.nonlocal) {
 #pragma unroll
                         for (int j = 0; j < NT; ++j) st2(&sm[B.off_hist + ip[b] * LD + 8 * j + 2 * lc], pn[j][0], pn[j][1]);
-                    } else if (s + 1 < P.nsteps) {
-                        const int hb = B.off_hist + ((s + 1) * B.ncp + ip[b]) * LD + 2 * lc;
-                        int slot = B.slot0 + s + 1;
-                        if (slot >= B.R) slot -= B.R;
+                    } else if (g + 1 < P.nsteps) {
+                        const int hb = B.off_hist + (((s + 1) & (FT - 1)) * B.ncp + ip[b]) * LD + 2 * lc;
+                        int slot = (B.slot0 + g + 1) % B.R;
                         double* rp = &B.ring[((size_t)slot * B.ncp + ip[b]) * ldb + col0 + 2 * lc];
 #pragma unroll
                         for (int j = 0; j < NT; ++j) {
@@ -598,11 +730,12 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
         { const int tmp = xpc; xpc = xpn; xpn = tmp; }      // xpc: p(t+1)
         tn = tn1;
     }
+    }
 
     // ------------------------------------------------------------------ epilogue
 #ifdef PYMD_FUSED_TIMING
     if (P.timing && lane == 0)
-        for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(&P.timing[i]), (unsigned long long)tacc[i]);
+        for (int i = 0; i < 10; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(&P.timing[i]), (unsigned long long)tacc[i]);
 #endif
     if (live) {
 #pragma unroll
@@ -790,36 +923,56 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
     const int grid = c->ldb / (8 * NT);
 #ifdef PYMD_FUSED_TIMING
     static long long* d_timing = nullptr;
-    if (!d_timing) { cudaMalloc(&d_timing, 8 * sizeof(long long)); }
-    cudaMemsetAsync(d_timing, 0, 8 * sizeof(long long), st);
+    if (!d_timing) { cudaMalloc(&d_timing, 10 * sizeof(long long)); }
+    cudaMemsetAsync(d_timing, 0, 10 * sizeof(long long), st);
     fp.timing = d_timing;
 #endif
     const bool far_on = !(getenv("PYMD_FAR") && atoi(getenv("PYMD_FAR")) == 0);          // testing knob
-    for (int done = 0; done < nsteps; done += FT) {
-        const int ns = std::min(FT, nsteps - done);
-        // far field (far.cu): history older than the current super-block of kFarS steps, one FFT
-        // convolution per super-block; a new super-block starts whenever this block leaves the old one
-        unsigned need = 0;
-        for (int b = 0; b < c->nbath; ++b) {
-            BathHost& H = c->bath[b];
-            if (H.ml <= 1 || !H.d_ghat || !far_on) continue;
-            const long long r0 = H.hcount - H.far_base;
-            if (!H.far_valid || r0 < 0 || r0 + ns > kFarS) need |= 1u << b;
-        }
-        if (need && (rc = far_launch(c, need, st))) return rc;
-        for (int b = 0; b < c->nbath; ++b) {
-            BathHost& H = c->bath[b];
-            if (H.ml > 1) {
-                // pre-block part: history older than this block, read once for ns steps
-                if (H.d_ghat && far_on) {
-                    // ... of which only the rows since p(u0-1) are multiplied directly
-                    const long long r0 = H.hcount - H.far_base;
-                    rc = launch_tail(c, b, ns, 2, d.b[b].tail_next, st, r0 + 1, H.d_far + (size_t)r0 * H.nc * c->ldb);
-                } else {
-                    rc = launch_tail(c, b, ns, 2, d.b[b].tail_next, st);
-                }
-                if (rc) return rc;
+    // mid mode: every non-local bath has an FFT far field (far.cu); one launch then advances up to the
+    // end of the current super-block of kFarS steps, computing the pre-block tails in the kernel
+    bool mid = far_on;
+    int nonlocal = 0;
+    for (int b = 0; b < c->nbath; ++b)
+        if (c->bath[b].ml > 1) { ++nonlocal; mid = mid && c->bath[b].d_ghat != nullptr; }
+    mid = mid && nonlocal > 0;
+    for (int done = 0; done < nsteps;) {
+        int ns = std::min(FT, nsteps - done);
+        if (mid) {
+            unsigned need = 0;
+            long long r0 = 0;
+            for (int b = 0; b < c->nbath; ++b) {
+                BathHost& H = c->bath[b];
+                if (H.ml <= 1) continue;
+                r0 = H.hcount - H.far_base;
+                if (!H.far_valid || r0 < 0 || r0 >= kFarS) need |= 1u << b;
+            }
+            if (need) {
+                // a new super-block starts here: far field of everything older than p(t-1)
+                for (int b = 0; b < c->nbath; ++b)
+                    if (c->bath[b].ml > 1) need |= 1u << b;
+                if ((rc = far_launch(c, need, st))) return rc;
+                r0 = 0;
+            }
+            ns = std::min(nsteps - done, kFarS - (int)r0);
+            fp.mid = 1;
+            fp.r0 = (int)r0;
+            for (int b = 0; b < c->nbath; ++b) {
+                BathHost& H = c->bath[b];
+                if (H.ml <= 1) continue;
+                fp.hc0 = H.hcount;
                 fp.b[b].slot0 = (int)(H.hcount % H.R);
+                fp.b[b].kmid = H.d_kmid;
+                fp.b[b].F = H.d_far;
+            }
+        } else {
+            fp.mid = 0;
+            for (int b = 0; b < c->nbath; ++b) {
+                BathHost& H = c->bath[b];
+                if (H.ml > 1) {
+                    // pre-block part: history older than this block, read once for ns steps
+                    if ((rc = launch_tail(c, b, ns, 2, d.b[b].tail_next, st))) return rc;
+                    fp.b[b].slot0 = (int)(H.hcount % H.R);
+                }
             }
         }
         fp.t0 = t0 + done;
@@ -838,16 +991,17 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
             if (c->bath[b].ml > 1) c->bath[b].hcount += ns;
         c->fpot_valid = true;
         c->fpotc_valid = false;
+        done += ns;
     }
 #ifdef PYMD_FUSED_TIMING
     {
-        long long h[8];
+        long long h[10];
         cudaMemcpy(h, fp.timing, sizeof(h), cudaMemcpyDeviceToHost);
         const double nw = (double)grid * FW * nsteps;
-        const char* nm[8] = {"A.matvec", "A.elementwise", "A.items", "barrier-wait", "B.matvec", "B.elementwise", "C.matvec", "C.elementwise"};
-        double tot = 0; for (int i = 0; i < 8; ++i) tot += h[i] / nw;
+        const char* nm[10] = {"A.matvec", "A.elementwise", "A.items", "barrier-wait", "B.matvec", "B.elementwise", "C.matvec", "C.elementwise", "mid", "pre-mid"};
+        double tot = 0; for (int i = 0; i < 10; ++i) tot += h[i] / nw;
         fprintf(stderr, "[fused timing] cycles per warp-step (NT=%d):", NT);
-        for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.0f", nm[i], h[i] / nw);
+        for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%.0f", nm[i], h[i] / nw);
         fprintf(stderr, " total=%.0f\n", tot);
     }
 #endif

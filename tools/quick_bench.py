@@ -28,6 +28,17 @@ torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); m.steps(a.steps); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
+import ctypes
+from pymd_b200 import _lib
+_lib.call("pymd_profile_enable", m._ctx, 1)
+m.steps(a.steps)
+ms8 = (ctypes.c_double * 8)(); c8 = (ctypes.c_longlong * 8)()
+_lib.call("pymd_profile_read", m._ctx, ctypes.addressof(ms8), ctypes.addressof(c8))
+_lib.call("pymd_profile_enable", m._ctx, 0)
+names = ["tail_gemm", "fused_step", "other_gemm", "stage", "far_fft"]
+prof = {names[i]: dict(us_per_mdstep=round(1e3 * ms8[i] / a.steps, 3), us_per_launch=round(1e3 * ms8[i] / c8[i], 2), n=int(c8[i]))
+        for i in range(5) if c8[i]}
+print(json.dumps(prof))
 print(json.dumps(dict(case=a.case, batch=a.batch, mode=a.mode, steps=a.steps, ms_per_mdstep=ms / a.steps,
                       traj_steps_per_s=a.batch * a.steps / ms * 1e3, setup_s=setup,
                       finite=bool(np.isfinite(m.p).all()))))
