@@ -318,6 +318,15 @@ def run_ours(a):
         for b in me.baths:
             b.spectral_factors()                       # host setup (eigh per frequency), as the reference does once
         h2d = sum(b.spectral_factors().L.nbytes for b in me.baths)
+        # untimed warm-up of the same call sequence (buffer allocation, first-launch set-up); the timed
+        # region below then re-uploads the factors, regenerates the noise and runs every md step
+        me.initialise()
+        me.ResetHis()
+        for b in me.baths:
+            b.gnoi()
+        me.ResetSavepq(True)
+        me.steps(PIECE)
+        me.GetPower()
         torch.cuda.synchronize()
         barrier()
         t0 = time.perf_counter()
@@ -326,6 +335,7 @@ def run_ours(a):
             me.traj0 = rank * B + sub * Be
             for b in me.baths:
                 b._traj0 = me.traj0
+                b.spectral_factors().drop_device_copy()    # this segment's inputs cross the bus again
             me.initialise()
             me.ResetHis()
             for b in me.baths:

@@ -107,11 +107,12 @@ int pymd_profile_read(pymd_ctx* ctx, double* ms8, long long* count8);
  * (real part; imaginary part NULL for phonon baths).  xi: standard normals dev
  * [nf][nc][ldb].  Computes X_f = L_f xi_f, the Hermitian mirror (noise.py:74-81), the
  * w->t transform myfft.iFourier1D (myfft.py:35-52: fft/(nmd*dt)) and keeps the real part.
- * out: dev [nmd][nc][ldb]; only the component rows i0 <= i < i1 are produced by one call, so the
- * FFT scratch (pymd_noise_work_bytes(nmd, i1-i0, ldb)) can be kept small for large ensembles. */
-size_t pymd_noise_work_bytes(int nmd, int nrows, int ldb);
+ * out: dev [nmd][nc][ldb]; one call produces all component rows of the trajectories n0 <= n < n1
+ * (multiples of 8), so that the FFT scratch (pymd_noise_work_bytes(nmd, nc, n1-n0)) stays small for
+ * large ensembles and every white-noise row is read exactly once. */
+size_t pymd_noise_work_bytes(int nmd, int nc, int ncols);
 int pymd_noise_generate(const double* lre_dev, const double* lim_dev, const double* xi_dev,
-                        int nmd, int nc, int ldb, int i0, int i1, double dt, double* out_dev,
+                        int nmd, int nc, int ldb, int n0, int n1, double dt, double* out_dev,
                         void* work_dev, void* stream);
 
 /* N.random.normal replacement (noise.py:282): counter-based Philox4x32-10 + Box-Muller.

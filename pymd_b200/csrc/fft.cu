@@ -1,4 +1,5 @@
 // See fft.cuh.  Replaces numpy.fft in myfft.Fourier1D / iFourier1D (reference myfft.py:15-52).
+#include <algorithm>
 #include <cmath>
 #include <map>
 #include <mutex>
@@ -61,8 +62,8 @@ __global__ void __launch_bounds__(128) fft_pass_kernel(const void* __restrict__ 
                                                        int n, int Ns, long long cols, int conj_in, int conj_out,
                                                        const double2* __restrict__ tw, int twN, int loadmode,
                                                        int storemode, long long src_ld, long long dst_ld,
-                                                       double scale) {
-    const int j = blockIdx.x;
+                                                       double scale, long long dst_cw, long long dst_cs) {
+    const int j = blockIdx.y;                   // blockIdx.x: column tile (neighbouring CTAs share DRAM pages)
     const int k = j % Ns;
     const int base = (j / Ns) * Ns * R + k;
     const int nr = n / R;
@@ -72,8 +73,8 @@ __global__ void __launch_bounds__(128) fft_pass_kernel(const void* __restrict__ 
 #pragma unroll
         for (int r = 1; r < R; ++r) w[r] = tw[(size_t)r * k * step];
     }
-    for (long long col = blockIdx.y * (long long)blockDim.x + threadIdx.x; col < cols;
-         col += (long long)gridDim.y * blockDim.x) {
+    for (long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x; col < cols;
+         col += (long long)gridDim.x * blockDim.x) {
         double2 v[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -99,8 +100,91 @@ __global__ void __launch_bounds__(128) fft_pass_kernel(const void* __restrict__ 
                 static_cast<double2*>(dst)[o * dst_ld + col] = out;
             } else {
                 double* dr = static_cast<double*>(dst);
-                dr[(2 * o) * dst_ld + col] = out.x;
-                dr[(2 * o + 1) * dst_ld + col] = out.y;
+                const long long dc = dst_cw ? (col / dst_cw) * dst_cs + col % dst_cw : col;
+                dr[(2 * o) * dst_ld + dc] = out.x;
+                dr[(2 * o + 1) * dst_ld + dc] = out.y;
+            }
+        }
+    }
+}
+
+// Fused radix R*R pass (R = 8: 64, R = 4: 16).  blockDim = (32 columns, R): thread (x, r1) first
+// transforms inputs r1 + R r2 (r2 < R), the R x R intermediate goes through shared memory with
+// the inner twiddles W_{R^2}^{r1 q2} applied, thread (x, q2) then transforms over r1 and stores
+// outputs R q1 + q2.  Same Stockham indexing as fft_pass_kernel with radix R^2.
+template <int R>
+__global__ void __launch_bounds__(32 * R, 512 / (32 * R)) fft_pass2_kernel(const void* __restrict__ src, void* __restrict__ dst,
+                                                           int n, int Ns, long long cols, int conj_in, int conj_out,
+                                                           const double2* __restrict__ tw, int twN, int loadmode,
+                                                           int storemode, long long src_ld, long long dst_ld,
+                                                           double scale, long long dst_cw, long long dst_cs) {
+    constexpr int RR = R * R;
+    __shared__ double2 ex[RR][32];
+    // blockIdx.x runs over column tiles so that the CTAs resident at the same time read neighbouring
+    // 512-byte pieces of the same rows (DRAM page locality); blockIdx.y is the butterfly index
+    const int j = blockIdx.y;
+    const int k = j % Ns;
+    const int base = (j / Ns) * Ns * RR + k;
+    const int nr = n / RR;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int step = twN / (Ns * RR);                 // outer twiddle W_{Ns RR}^{r k}
+    const int istep = twN / RR;                        // inner twiddle W_{RR}^{r1 q2}
+    const long long cstride = (long long)gridDim.x * 32;
+    // the loads of the next column tile are in flight while the current one is transformed
+    auto issue = [&](double2 (&d)[R], long long c0) {
+        const long long col = c0 + tx;
+#pragma unroll
+        for (int r2 = 0; r2 < R; ++r2) {
+            const long long idx = j + (long long)(ty + R * r2) * nr;
+            d[r2] = make_double2(0.0, 0.0);
+            if (col < cols) {
+                if (loadmode == LOAD_C) {
+                    d[r2] = __ldcs(static_cast<const double2*>(src) + idx * src_ld + col);
+                } else {
+                    const double* xr = static_cast<const double*>(src);
+                    d[r2] = make_double2(__ldcs(xr + (2 * idx) * src_ld + col), __ldcs(xr + (2 * idx + 1) * src_ld + col));
+                }
+            }
+        }
+    };
+    double2 v[R], nx[R];
+    long long c0 = (long long)blockIdx.x * 32;
+    issue(nx, c0);
+    for (; c0 < cols; c0 += cstride) {
+        const long long col = c0 + tx;
+        const bool ok = col < cols;
+#pragma unroll
+        for (int r2 = 0; r2 < R; ++r2) v[r2] = nx[r2];
+        if (c0 + cstride < cols) issue(nx, c0 + cstride);
+        // stage 1: r1 = ty, r2 = 0..R-1
+#pragma unroll
+        for (int r2 = 0; r2 < R; ++r2) {
+            const int r = ty + R * r2;
+            if (conj_in) v[r2].y = -v[r2].y;
+            if (Ns > 1 && r > 0) v[r2] = cmul(v[r2], tw[r * k * step]);
+        }
+        butterfly<R>(v);                                // v[q2] = sum_r2 ... exp(-2 pi i r2 q2 / R)
+        __syncthreads();                                // previous tile consumed
+#pragma unroll
+        for (int q2 = 0; q2 < R; ++q2) ex[ty * R + q2][tx] = (ty * q2) ? cmul(v[q2], tw[ty * q2 * istep]) : v[q2];
+        __syncthreads();
+        // stage 2: q2 = ty, over r1
+#pragma unroll
+        for (int r1 = 0; r1 < R; ++r1) v[r1] = ex[r1 * R + ty][tx];
+        butterfly<R>(v);                                // v[q1]: output R q1 + q2
+        if (ok) {
+            const long long dc = (storemode != STORE_C && dst_cw) ? (col / dst_cw) * dst_cs + col % dst_cw : col;
+#pragma unroll
+            for (int q1 = 0; q1 < R; ++q1) {
+                const long long o = base + (long long)(R * q1 + ty) * Ns;
+                const double2 out = make_double2(scale * v[q1].x, (conj_out ? -scale : scale) * v[q1].y);
+                if (storemode == STORE_C) {
+                    __stcs(static_cast<double2*>(dst) + o * dst_ld + col, out);
+                } else {
+                    double* dr = static_cast<double*>(dst);
+                    dr[(2 * o) * dst_ld + dc] = out.x;
+                    dr[(2 * o + 1) * dst_ld + dc] = out.y;
+                }
             }
         }
     }
@@ -141,7 +225,9 @@ int fft_columns(const void* src, void* dst, double2* bufA, double2* bufB, const 
     const double2* tw = twiddle_table(p.n);
     PYMD_REQUIRE(tw, "fft: twiddle table allocation failed");
     int radices[32], np = 0, rem = p.n;
-    while (rem >= 8) { radices[np++] = 8; rem /= 8; }
+    while (rem >= 64) { radices[np++] = 64; rem /= 64; }
+    if (rem == 32) { radices[np++] = 16; rem = 2; }
+    if (rem == 16) { radices[np++] = 16; rem = 1; }
     if (rem > 1) radices[np++] = rem;
     PYMD_REQUIRE(np == 1 || (bufA && (np == 2 || bufB)), "fft: work buffers required");
     int Ns = 1;
@@ -154,20 +240,33 @@ int fft_columns(const void* src, void* dst, double2* bufA, double2* bufB, const 
         const int lm = first ? p.load : LOAD_C, sm = last ? p.store : STORE_C;
         const long long sld = first ? p.src_ld : p.cols, dld = last ? p.dst_ld : p.cols;
         const double sc = last ? p.scale : 1.0;
-        long long yb = (p.cols + 127) / 128;
-        if (yb > 65535) yb = 65535;
-        dim3 grid(p.n / R, (unsigned)yb);
+        const long long cw = last ? p.dst_cw : 0, cs = last ? p.dst_cs : 0;
         // ifft(x) = conj(fft(conj(x))): conjugate on the first load and on the last store
         const int ci = (p.sign > 0 && first) ? 1 : 0, co = (p.sign > 0 && last) ? 1 : 0;
-        switch (R) {
-            case 8:
-                fft_pass_kernel<8><<<grid, 128, 0, stream>>>(cur, out, p.n, Ns, p.cols, ci, co, tw, p.n, lm, sm, sld, dld, sc);
-                break;
-            case 4:
-                fft_pass_kernel<4><<<grid, 128, 0, stream>>>(cur, out, p.n, Ns, p.cols, ci, co, tw, p.n, lm, sm, sld, dld, sc);
-                break;
-            default:
-                fft_pass_kernel<2><<<grid, 128, 0, stream>>>(cur, out, p.n, Ns, p.cols, ci, co, tw, p.n, lm, sm, sld, dld, sc);
+        if (R >= 16) {
+            long long xb = (p.cols + 31) / 32;
+            if (xb > 148) xb = 148;                     // half a wave of column tiles per butterfly index
+            PYMD_REQUIRE(p.n / R <= 65535, "fft: length %d too long for the fused pass", p.n);
+            dim3 grid((unsigned)xb, p.n / R);
+            if (R == 64)
+                fft_pass2_kernel<8><<<grid, dim3(32, 8), 0, stream>>>(cur, out, p.n, Ns, p.cols, ci, co, tw, p.n, lm, sm, sld, dld, sc, cw, cs);
+            else
+                fft_pass2_kernel<4><<<grid, dim3(32, 4), 0, stream>>>(cur, out, p.n, Ns, p.cols, ci, co, tw, p.n, lm, sm, sld, dld, sc, cw, cs);
+        } else {
+            long long xb = (p.cols + 127) / 128;
+            if (xb > 592) xb = 592;
+            PYMD_REQUIRE(p.n / R <= 65535, "fft: length %d too long for a radix-%d pass", p.n, R);
+            dim3 grid((unsigned)xb, p.n / R);
+            switch (R) {
+                case 8:
+                    fft_pass_kernel<8><<<grid, 128, 0, stream>>>(cur, out, p.n, Ns, p.cols, ci, co, tw, p.n, lm, sm, sld, dld, sc, cw, cs);
+                    break;
+                case 4:
+                    fft_pass_kernel<4><<<grid, 128, 0, stream>>>(cur, out, p.n, Ns, p.cols, ci, co, tw, p.n, lm, sm, sld, dld, sc, cw, cs);
+                    break;
+                default:
+                    fft_pass_kernel<2><<<grid, 128, 0, stream>>>(cur, out, p.n, Ns, p.cols, ci, co, tw, p.n, lm, sm, sld, dld, sc, cw, cs);
+            }
         }
         PYMD_CUDA_CHECK(cudaGetLastError());
         cur = out;

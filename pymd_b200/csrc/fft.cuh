@@ -1,5 +1,7 @@
 // Batched FFT along the SLOW axis of [n][cols] arrays (cols = dof x trajectory, contiguous),
-// Stockham autosort, radix-8/4/2 register passes, every access coalesced over columns.
+// Stockham autosort, every access coalesced over columns.  A pass is either a register radix-8/4/2
+// butterfly per thread or a fused radix-64/16 pass (two butterfly stages exchanged through shared
+// memory), so a length-2^14 transform reads and writes HBM three times instead of five.
 #pragma once
 #include "common.cuh"
 
@@ -19,6 +21,9 @@ struct FftPlan {
     FftStore store;       // STORE_REAL_ROWS: dst real [2n][dst_ld]: row 2m = scale*re, row 2m+1 = scale*im
     long long src_ld, dst_ld;
     double scale;
+    // STORE_REAL_ROWS only: column c of the transform lands at (c / dst_cw) * dst_cs + c % dst_cw of
+    // a destination row (a chunk of dst_cw trajectories of every component row); 0 = plain c.
+    long long dst_cw = 0, dst_cs = 0;
 };
 
 // Runs all passes.  `src` is read by the first pass only (never written unless it aliases a

@@ -59,9 +59,11 @@ constexpr int SX = 32, SY = 8, JC = 64;
 
 __global__ void __launch_bounds__(SX* SY) shape_kernel(const double* __restrict__ lre, const double* __restrict__ lim,
                                                        const double* __restrict__ xi, int N, int nc, int ldb,
-                                                       int i0, int i1, const double2* __restrict__ twN,
+                                                       int n0, int cw, const double2* __restrict__ twN,
                                                        double2* __restrict__ Z) {
+    // scalar fallback for nc > 64; all component rows, trajectories [n0, n0 + cw); Z is [N/2][nc][cw]
     __shared__ double x1[JC][SX], x2[JC][SX];
+    const int i0 = 0, i1 = nc;
     const int kp = blockIdx.x;              // pair (k1, k2) = (kp, N/2 - kp), kp in [0, N/4]
     const int half = N / 2;
     const int k1 = kp, k2 = half - kp;
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(SX* SY) shape_kernel(const double* __restrict_
             __syncthreads();
             for (int e = tid; e < jn * SX; e += SX * SY) {
                 const int jj = e / SX, xx = e % SX;
-                const size_t col = (size_t)blockIdx.y * SX + xx;
+                const size_t col = (size_t)n0 + (size_t)blockIdx.y * SX + xx;
                 x1[jj][xx] = xi[((size_t)k1 * nc + j0 + jj) * ldb + col];
                 x2[jj][xx] = xi[((size_t)k2 * nc + j0 + jj) * ldb + col];
             }
@@ -123,22 +125,132 @@ __global__ void __launch_bounds__(SX* SY) shape_kernel(const double* __restrict_
                 const double dr = y1r - y2r, di = y1i + y2i;               // Y1 - conj(Y2)
                 const double2 w = twN[k1];
                 const double orr = dr * w.x - di * w.y, oi = dr * w.y + di * w.x;
-                Z[((size_t)k1 * rows + (i - i0)) * ldb + n] = make_double2(er - oi, ei + orr);
+                Z[((size_t)k1 * rows + (i - i0)) * cw + n] = make_double2(er - oi, ei + orr);
             }
             if (kp != 0 && k2 != k1) {
                 const double er = y2r + y1r, ei = y2i - y1i;               // Y2 + conj(Y1)
                 const double dr = y2r - y1r, di = y2i + y1i;               // Y2 - conj(Y1)
                 const double2 w = twN[k2];
                 const double orr = dr * w.x - di * w.y, oi = dr * w.y + di * w.x;
-                Z[((size_t)k2 * rows + (i - i0)) * ldb + n] = make_double2(er - oi, ei + orr);
+                Z[((size_t)k2 * rows + (i - i0)) * cw + n] = make_double2(er - oi, ei + orr);
             }
         }
     }
 }
 
-int fft_num_passes(int n) {
+
+// ------------------------------------------------------------------ shaping on the FP64 tensor pipe
+// One CTA per frequency pair (k1, k2 = N/2 - k1): the four nc x nc operand planes Re/Im L_{k1},
+// Re/Im L_{k2} are staged in shared memory once (row pitch = 4 mod 16 doubles: conflict-free A
+// fragments) and applied to the white noise of every trajectory of the column chunk: warp w
+// takes n8 tiles w, w+8, ...; the B fragments (xi rows of the two frequencies) come straight from
+// global memory into registers, Y = L xi is 4 DMMA chains per m8 tile (Re/Im of the two
+// frequencies), and the Hermitian pre-processing of the half-length real transform is the epilogue.
+template <int KKMAX, bool CPLX>
+__global__ void __launch_bounds__(256, 1) shape_dmma_kernel(const double* __restrict__ lre, const double* __restrict__ lim,
+                                                            const double* __restrict__ xi, int N, int nc, int ldb,
+                                                            int n0, int cw, const double2* __restrict__ twN,
+                                                            double2* __restrict__ Z) {
+    extern __shared__ __align__(16) double sh[];
+    const int half = N / 2, kp = blockIdx.x, k1 = kp, k2 = half - kp;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+    const int MT = (nc + 7) / 8, KK = (nc + 3) / 4;
+    const int LP = 4 * KK + 4 + ((4 * KK) % 16 == 0 ? 0 : 16 - (4 * KK) % 16);   // = 4 mod 16
+    const int plane = 8 * MT * LP;
+    double* A1r = sh;
+    double* A1i = sh + plane;
+    double* A2r = sh + 2 * plane;
+    double* A2i = sh + 3 * plane;
+    for (int e = tid; e < 8 * MT * 4 * KK; e += 256) {
+        const int i = e / (4 * KK), j = e % (4 * KK);
+        const bool in = i < nc && j < nc;
+        const size_t o1 = ((size_t)k1 * nc + i) * nc + j, o2 = ((size_t)k2 * nc + i) * nc + j;
+        A1r[i * LP + j] = in ? lre[o1] : 0.0;
+        A2r[i * LP + j] = in ? lre[o2] : 0.0;
+        if (CPLX) {
+            A1i[i * LP + j] = in ? lim[o1] : 0.0;
+            A2i[i * LP + j] = in ? lim[o2] : 0.0;
+        }
+    }
+    __syncthreads();
+    const double2 w1 = twN[k1], w2 = twN[k2];
+    for (int nt = warp; nt < cw / 8; nt += 8) {
+        const int col = n0 + nt * 8;
+        double b1[KKMAX], b2[KKMAX];
+#pragma unroll
+        for (int kk = 0; kk < KKMAX; ++kk) {
+            const int j = 4 * kk + lc;
+            const bool in = kk < KK && j < nc;
+            b1[kk] = in ? xi[((size_t)k1 * nc + j) * ldb + col + lr] : 0.0;
+            b2[kk] = in ? xi[((size_t)k2 * nc + j) * ldb + col + lr] : 0.0;
+        }
+        for (int mt = 0; mt < MT; ++mt) {
+            double y1r[2] = {0.0, 0.0}, y1i[2] = {0.0, 0.0}, y2r[2] = {0.0, 0.0}, y2i[2] = {0.0, 0.0};
+            const int ao = (8 * mt + lr) * LP + lc;
+#pragma unroll
+            for (int kk = 0; kk < KKMAX; ++kk) {
+                if (kk < KK) {
+                    dmma884(y1r[0], y1r[1], A1r[ao + 4 * kk], b1[kk]);
+                    dmma884(y2r[0], y2r[1], A2r[ao + 4 * kk], b2[kk]);
+                    if (CPLX) {
+                        dmma884(y1i[0], y1i[1], A1i[ao + 4 * kk], b1[kk]);
+                        dmma884(y2i[0], y2i[1], A2i[ao + 4 * kk], b2[kk]);
+                    }
+                }
+            }
+            const int i = 8 * mt + lr;
+            if (i < nc) {
+                double2 z1[2], z2[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    double a1r = y1r[c], a1i = y1i[c], a2r = y2r[c], a2i = y2i[c];
+                    if (kp == 0) { a1i = 0.0; a2i = 0.0; }          // DC and Nyquist rows: real part only
+                    {
+                        const double er = a1r + a2r, ei = a1i - a2i;               // Y1 + conj(Y2)
+                        const double dr = a1r - a2r, di = a1i + a2i;               // Y1 - conj(Y2)
+                        const double orr = dr * w1.x - di * w1.y, oi = dr * w1.y + di * w1.x;
+                        z1[c] = make_double2(er - oi, ei + orr);
+                    }
+                    {
+                        const double er = a2r + a1r, ei = a2i - a1i;               // Y2 + conj(Y1)
+                        const double dr = a2r - a1r, di = a2i + a1i;               // Y2 - conj(Y1)
+                        const double orr = dr * w2.x - di * w2.y, oi = dr * w2.y + di * w2.x;
+                        z2[c] = make_double2(er - oi, ei + orr);
+                    }
+                }
+                // Z is [N/2][nc][cw] for this chunk of trajectories
+                double2* d1 = Z + ((size_t)k1 * nc + i) * cw + nt * 8 + 2 * lc;
+                d1[0] = z1[0]; d1[1] = z1[1];
+                if (kp != 0 && k2 != k1) {
+                    double2* d2 = Z + ((size_t)k2 * nc + i) * cw + nt * 8 + 2 * lc;
+                    d2[0] = z2[0]; d2[1] = z2[1];
+                }
+            }
+        }
+    }
+}
+
+template <int KKMAX, bool CPLX>
+int launch_shape(const double* lre, const double* lim, const double* xi, int nmd, int nc, int ldb, int n0, int cw,
+                 const double2* twN, double2* Z, cudaStream_t st) {
+    const int MT = (nc + 7) / 8, KK = (nc + 3) / 4;
+    const int LP = 4 * KK + 4 + ((4 * KK) % 16 == 0 ? 0 : 16 - (4 * KK) % 16);
+    const size_t smem = (size_t)4 * 8 * MT * LP * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+        PYMD_CUDA_CHECK(cudaFuncSetAttribute(shape_dmma_kernel<KKMAX, CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    shape_dmma_kernel<KKMAX, CPLX><<<nmd / 4 + 1, 256, smem, st>>>(lre, lim, xi, nmd, nc, ldb, n0, cw, twN, Z);
+    PYMD_CUDA_CHECK(cudaGetLastError());
+    return PYMD_OK;
+}
+
+int fft_num_passes(int n) {                 // must mirror the plan of fft_columns (fft.cu)
     int np = 0;
-    while (n >= 8) { ++np; n /= 8; }
+    while (n >= 64) { ++np; n /= 64; }
+    if (n == 32) { ++np; n = 2; }
+    if (n == 16) { ++np; n = 1; }
     if (n > 1) ++np;
     return np;
 }
@@ -149,32 +261,45 @@ using namespace pymd;
 
 extern "C" {
 
-size_t pymd_noise_work_bytes(int nmd, int nrows, int ldb) {
-    return 2 * (size_t)(nmd / 2) * nrows * ldb * sizeof(double2);
+size_t pymd_noise_work_bytes(int nmd, int nc, int ncols) {
+    return 2 * (size_t)(nmd / 2) * nc * ncols * sizeof(double2);
 }
 
 int pymd_noise_generate(const double* lre, const double* lim, const double* xi, int nmd, int nc, int ldb,
-                        int i0, int i1, double dt, double* out, void* work, void* stream) {
+                        int n0, int n1, double dt, double* out, void* work, void* stream) {
     PYMD_REQUIRE(lre && xi && out && work, "noise_generate: null argument");
     PYMD_REQUIRE(nmd >= 4 && (nmd & (nmd - 1)) == 0, "noise_generate: nmd=%d must be a power of two >= 4", nmd);
     PYMD_REQUIRE(nc > 0 && ldb > 0 && ldb % 32 == 0, "noise_generate: nc=%d ldb=%d", nc, ldb);
-    PYMD_REQUIRE(0 <= i0 && i0 < i1 && i1 <= nc, "noise_generate: row range [%d, %d) of %d", i0, i1, nc);
+    PYMD_REQUIRE(0 <= n0 && n0 < n1 && n1 <= ldb && n0 % 8 == 0 && (n1 - n0) % 8 == 0,
+                 "noise_generate: trajectory range [%d, %d) of %d (multiples of 8)", n0, n1, ldb);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int half = nmd / 2, rows = i1 - i0;
+    const int half = nmd / 2, cw = n1 - n0;
     const double2* twN = twiddle_table(nmd);
     PYMD_REQUIRE(twN, "noise_generate: twiddle table allocation failed");
     // Z goes to W0; the passes ping-pong W1, W0, W1, ...; the last one writes the real rows of `out`
     double2* W0 = static_cast<double2*>(work);
-    double2* W1 = W0 + (size_t)half * rows * ldb;
-    dim3 grid(half / 2 + 1, ldb / SX), blk(SX, SY);
-    shape_kernel<<<grid, blk, 0, st>>>(lre, lim, xi, nmd, nc, ldb, i0, i1, twN, W0);
-    PYMD_CUDA_CHECK(cudaGetLastError());
+    double2* W1 = W0 + (size_t)half * nc * cw;
+    int rc;
+    if (nc <= 64) {
+        // tensor-pipe shaping: all operand planes of a frequency pair fit in shared memory
+        if (nc <= 16) rc = lim ? launch_shape<4, true>(lre, lim, xi, nmd, nc, ldb, n0, cw, twN, W0, st)
+                               : launch_shape<4, false>(lre, lim, xi, nmd, nc, ldb, n0, cw, twN, W0, st);
+        else rc = lim ? launch_shape<16, true>(lre, lim, xi, nmd, nc, ldb, n0, cw, twN, W0, st)
+                      : launch_shape<16, false>(lre, lim, xi, nmd, nc, ldb, n0, cw, twN, W0, st);
+        if (rc) return rc;
+    } else {
+        PYMD_REQUIRE(cw % SX == 0, "noise_generate: trajectory chunks must be multiples of %d for nc > 64", SX);
+        dim3 grid(half / 2 + 1, cw / SX), blk(SX, SY);
+        shape_kernel<<<grid, blk, 0, st>>>(lre, lim, xi, nmd, nc, ldb, n0, cw, twN, W0);
+        PYMD_CUDA_CHECK(cudaGetLastError());
+    }
     FftPlan p{};
-    p.n = half; p.cols = (long long)rows * ldb; p.sign = -1;
+    p.n = half; p.cols = (long long)nc * cw; p.sign = -1;
     p.load = LOAD_C; p.store = STORE_REAL_ROWS;
     p.src_ld = p.cols; p.dst_ld = (long long)nc * ldb;
+    p.dst_cw = cw; p.dst_cs = ldb;
     p.scale = 1.0 / ((double)nmd * dt);
-    return fft_columns(W0, out + (size_t)i0 * ldb, W1, W0, p, st, nullptr);
+    return fft_columns(W0, out + n0, W1, W0, p, st, nullptr);
 }
 
 int pymd_philox_normal(double* out, long long rows, int ldb, uint64_t seed, uint32_t stream_id,

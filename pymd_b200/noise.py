@@ -63,17 +63,36 @@ class SpectralFactors:
         self.L = vec * N.sqrt(N.maximum(lam, 0.0))[:, None, :]
         self.complex = N.iscomplexobj(vec)
         self._dev = {}                      # device -> (lre, lim): uploaded once, reused by every gnoi()
+        self._host = None
+
+    def _pinned(self):
+        """L as page-locked host tensors (real, imaginary), made once: uploads then run at PCIe/NVLink-C2C
+        speed and can be asynchronous."""
+        import torch
+        if self._host is None:
+            re = torch.as_tensor(N.ascontiguousarray(self.L.real), dtype=torch.float64)
+            im = torch.as_tensor(N.ascontiguousarray(self.L.imag), dtype=torch.float64) if self.complex else None
+            try:
+                re = re.pin_memory()
+                im = im.pin_memory() if im is not None else None
+            except RuntimeError:
+                pass
+            self._host = (re, im)
+        return self._host
 
     def device_factors(self, dev):
         """L on the device (real and imaginary parts as separate [nf][nc][nc] arrays)."""
-        import torch
         key = str(dev)
         if key not in self._dev:
-            lre = torch.as_tensor(N.ascontiguousarray(self.L.real), dtype=torch.float64).to(dev)
-            lim = torch.as_tensor(N.ascontiguousarray(self.L.imag), dtype=torch.float64).to(dev) \
-                if self.complex else None
+            re, im = self._pinned()
+            lre = re.to(dev, non_blocking=True)
+            lim = im.to(dev, non_blocking=True) if im is not None else None
             self._dev[key] = (lre, lim)
         return self._dev[key]
+
+    def drop_device_copy(self):
+        """Forget the device copies: the next gnoi() uploads the factors again."""
+        self._dev = {}
 
     def as_oracle(self):
         return self.lam, self.U
@@ -104,6 +123,22 @@ def electron_factors(efric, exim, exip, bias, T, ecut, dt, nmd, classical=False,
 # ------------------------------------------------------------------ device pipeline
 MAX_WORK_BYTES = 12 << 30    # FFT scratch bound for noise generation
 
+_SCRATCH = {}
+
+
+def _scratch(nbytes, device):
+    """Grow-only FFT scratch per device, shared by all baths (the generate calls are stream-ordered)."""
+    import torch
+    key = str(device)
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _SCRATCH[key] = None
+        buf = None
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _SCRATCH[key] = buf
+    return buf
+
+
 def white_noise(nf, nc, ldb, seed, stream_id, traj0=0, device=None):
     """Standard normals [nf][nc][ldb] from the library's Philox generator (replaces the
     sequential N.random.normal draws of noise.vargau, noise.py:282)."""
@@ -124,13 +159,13 @@ def generate(factors, xi, dt, nmd, out=None):
     lre, lim = factors.device_factors(dev)
     if out is None:
         out = torch.empty((nmd, nc, ldb), dtype=torch.float64, device=dev)
-    # component rows are transformed in chunks so that the FFT scratch stays below MAX_WORK_BYTES
-    per_row = _lib.load().pymd_noise_work_bytes(nmd, 1, ldb)
-    rows = max(1, min(nc, MAX_WORK_BYTES // per_row))
-    work = torch.empty(per_row * rows, dtype=torch.uint8, device=dev)
-    for i0 in range(0, nc, rows):
-        i1 = min(nc, i0 + rows)
-        _lib.call("pymd_noise_generate", lre.data_ptr(), _lib.ptr(lim), xi.data_ptr(), nmd, nc, ldb, i0, i1,
+    # trajectories are transformed in chunks so that the FFT scratch stays below MAX_WORK_BYTES
+    per_col = _lib.load().pymd_noise_work_bytes(nmd, nc, 1)
+    cw = max(32, min(ldb, (MAX_WORK_BYTES // per_col) // 32 * 32))
+    work = _scratch(per_col * cw, dev)
+    for n0 in range(0, ldb, cw):
+        n1 = min(ldb, n0 + cw)
+        _lib.call("pymd_noise_generate", lre.data_ptr(), _lib.ptr(lim), xi.data_ptr(), nmd, nc, ldb, n0, n1,
                   float(dt), out.data_ptr(), work.data_ptr(), _lib.stream_ptr())
     return out
 
