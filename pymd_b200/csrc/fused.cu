@@ -109,12 +109,15 @@ __device__ __forceinline__ void zero_acc(double (&a)[NT][2]) {
 }
 
 // acc[j] += A(rows of this warp) . X[:, 8j..8j+7]   (A fragments in registers, X in smem)
-template <int NT>
+// FULLK: all MAXKS k-steps without the per-step branch (operator columns >= nd are zero, the padding
+// rows of X finite), so that the compiler can overlap the B loads of one k-step with the DMMAs of
+// the previous one.
+template <int NT, bool FULLK>
 __device__ __forceinline__ void matvec1(const double (&a)[MAXKS], int ks, const double* X, int LD,
                                         double (&acc)[NT][2], int lr, int lc) {
 #pragma unroll
     for (int k = 0; k < MAXKS; ++k) {
-        if (k < ks) {
+        if (FULLK || k < ks) {
             const double* xr = X + (4 * k + lc) * LD + lr;
 #pragma unroll
             for (int j = 0; j < NT; ++j) dmma884(acc[j][0], acc[j][1], a[k], xr[8 * j]);
@@ -122,13 +125,13 @@ __device__ __forceinline__ void matvec1(const double (&a)[MAXKS], int ks, const 
     }
 }
 // two operators sharing one B operand
-template <int NT>
+template <int NT, bool FULLK>
 __device__ __forceinline__ void matvec2(const double (&a0)[MAXKS], const double (&a1)[MAXKS], int ks,
                                         const double* X, int LD, double (&acc0)[NT][2],
                                         double (&acc1)[NT][2], int lr, int lc) {
 #pragma unroll
     for (int k = 0; k < MAXKS; ++k) {
-        if (k < ks) {
+        if (FULLK || k < ks) {
             const double* xr = X + (4 * k + lc) * LD + lr;
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
@@ -253,7 +256,7 @@ __device__ __forceinline__ void mid_phase(const FusedParams& P, double* sm, int 
     __syncthreads();                                    // P visible to every warp; staging buffer free again
 }
 
-template <int NT, bool HASQ, bool HASCON>
+template <int NT, bool HASQ, bool HASCON, bool FULLK>
 __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) {
     constexpr int N = 8 * NT, LD = N + 4;
     extern __shared__ __align__(16) double sm[];
@@ -405,8 +408,8 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
     }
     if (g0 == 0) {
         // forces at the initial q
-        if (HASQ) matvec2<NT>(aD, aQ, ks, sm + xq, LD, fpot, uq, lr, lc);
-        else matvec1<NT>(aD, ks, sm + xq, LD, fpot, lr, lc);
+        if (HASQ) matvec2<NT, FULLK>(aD, aQ, ks, sm + xq, LD, fpot, uq, lr, lc);
+        else matvec1<NT, FULLK>(aD, ks, sm + xq, LD, fpot, lr, lc);
 #pragma unroll
         for (int j = 0; j < NT; ++j) { fpot[j][0] = -fpot[j][0]; fpot[j][1] = -fpot[j][1]; }
         if (HASCON) {
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
         // ============ round A: first force evaluation at time t, head p(t) ============
         double hA[NT][2];
         zero_acc<NT>(hA);
-        matvec1<NT>(aM, ks, sm + xpc, LD, hA, lr, lc);
+        matvec1<NT, FULLK>(aM, ks, sm + xpc, LD, hA, lr, lc);
         TICK(0)
         // stage 1: every shared-memory load and all arithmetic for all n-tiles (no stores in between, so
         // the loads of different n-tiles overlap); stage 2: the stores
@@ -595,9 +598,9 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
             zero_acc<NT>(aDq);
             zero_acc<NT>(hB);
             zero_acc<NT>(uq);
-            if (HASQ) matvec2<NT>(aD, aQ, ks, sm + xq, LD, aDq, uq, lr, lc);
-            else matvec1<NT>(aD, ks, sm + xq, LD, aDq, lr, lc);
-            matvec1<NT>(aM, ks, sm + xpc, LD, hB, lr, lc);
+            if (HASQ) matvec2<NT, FULLK>(aD, aQ, ks, sm + xq, LD, aDq, uq, lr, lc);
+            else matvec1<NT, FULLK>(aD, ks, sm + xq, LD, aDq, lr, lc);
+            matvec1<NT, FULLK>(aM, ks, sm + xpc, LD, hB, lr, lc);
             TICK(4)
             double p1v[NT][2];
 #pragma unroll
@@ -632,7 +635,7 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
         {
             double hC[NT][2];
             zero_acc<NT>(hC);
-            matvec1<NT>(aM, ks, sm + xpc, LD, hC, lr, lc);
+            matvec1<NT, FULLK>(aM, ks, sm + xpc, LD, hC, lr, lc);
             TICK(6)
             double pn[NT][2], qn[NT][2];
 #pragma unroll
@@ -823,20 +826,29 @@ void choose_roles(const pymd_ctx* c, FusedParams& fp) {
 
 template <int NT>
 int launch_nt(const FusedParams& fp, size_t smem, int grid, bool hasq, bool hascon, cudaStream_t st) {
-#define PYMD_FUSED_CASE(Q, C)                                                                              \
+#define PYMD_FUSED_CASE(Q, C, F)                                                                             \
     {                                                                                                      \
         static bool cfg = false;                                                                           \
         if (!cfg) {                                                                                        \
-            PYMD_CUDA_CHECK(cudaFuncSetAttribute(fused_kernel<NT, Q, C>,                                   \
+            PYMD_CUDA_CHECK(cudaFuncSetAttribute(fused_kernel<NT, Q, C, F>,                                \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
             cfg = true;                                                                                    \
         }                                                                                                  \
-        fused_kernel<NT, Q, C><<<grid, FW * 32, smem, st>>>(fp);                                           \
+        fused_kernel<NT, Q, C, F><<<grid, FW * 32, smem, st>>>(fp);                                        \
     }
-    if (hasq && hascon) PYMD_FUSED_CASE(true, true)
-    else if (hasq) PYMD_FUSED_CASE(true, false)
-    else if (hascon) PYMD_FUSED_CASE(false, true)
-    else PYMD_FUSED_CASE(false, false)
+    // operators with more than 12 of the 16 k-steps run all 16 branch-free
+    const bool fullk = fp.ks > 12;
+    if (fullk) {
+        if (hasq && hascon) PYMD_FUSED_CASE(true, true, true)
+        else if (hasq) PYMD_FUSED_CASE(true, false, true)
+        else if (hascon) PYMD_FUSED_CASE(false, true, true)
+        else PYMD_FUSED_CASE(false, false, true)
+    } else {
+        if (hasq && hascon) PYMD_FUSED_CASE(true, true, false)
+        else if (hasq) PYMD_FUSED_CASE(true, false, false)
+        else if (hascon) PYMD_FUSED_CASE(false, true, false)
+        else PYMD_FUSED_CASE(false, false, false)
+    }
 #undef PYMD_FUSED_CASE
     PYMD_CUDA_CHECK(cudaGetLastError());
     return PYMD_OK;

@@ -36,7 +36,7 @@ def test_dmma_gemm_matches_numpy(cuda, M, K, ldb):
     assert np.abs(y.cpu().numpy() - (Y0 + 2.0 * (A[:, :K] @ X))).max() <= 1e-13 * 4 * scale
 
 
-@pytest.mark.parametrize("n", [2, 4, 8, 16, 64, 512, 4096, 16384])
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 65536])
 @pytest.mark.parametrize("sign", [-1, 1])
 def test_column_fft_matches_numpy(cuda, n, sign):
     import torch
