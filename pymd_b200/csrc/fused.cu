@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "engine.cuh"
@@ -60,6 +61,7 @@ struct FusedBath {
 
 struct FusedParams {
     int nd, ks, ldb, ldn, nbath, nmd, ncon, nsteps, rem, aq, carry_valid;
+    int nosplit;              // testing knob (PYMD_FUSED_SPLIT=0): never split work items into n-tile halves
     int mid;                  // 1: several blocks per launch, pre-block tails computed in the kernel
     int r0;                   // steps since the start of the super-block at launch
     long long hc0;            // history rows appended before p(t0)
@@ -314,17 +316,27 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
     // one bath for ALL n-tiles (A fragment loaded once per k-step, NT independent DMMA chains).  The
     // heavier tap items (kind 1) are dealt first, then the heads of the small baths (kind 0).
     int items[MAXIT], nit = 0;
+    bool split_items = false;
     {
+        int total = 0;
+        for (int b = 0; b < nb; ++b) {
+            if (!P.b[b].direct) total += P.b[b].ncp / 8;
+            if (b != P.rem) total += P.b[b].ncp / 8;
+        }
+        split_items = NT >= 2 && !P.nosplit && 2 * total <= FW * MAXIT;
+        const int nh = split_items ? 2 : 1;
         int item = 0;
         for (int b = 0; b < nb; ++b) {
             if (P.b[b].direct) continue;
-            for (int mt = 0; mt < P.b[b].ncp / 8; ++mt, ++item)
-                if (item % FW == w && nit < MAXIT) items[nit++] = b | (mt << 4) | (1 << 8);
+            for (int mt = 0; mt < P.b[b].ncp / 8; ++mt)
+                for (int h = 0; h < nh; ++h, ++item)
+                    if (item % FW == w && nit < MAXIT) items[nit++] = b | (mt << 4) | (1 << 8) | ((h * (NT / 2)) << 12);
         }
         for (int b = 0; b < nb; ++b) {
             if (b == P.rem) continue;
-            for (int mt = 0; mt < P.b[b].ncp / 8; ++mt, ++item)
-                if (item % FW == w && nit < MAXIT) items[nit++] = b | (mt << 4);
+            for (int mt = 0; mt < P.b[b].ncp / 8; ++mt)
+                for (int h = 0; h < nh; ++h, ++item)
+                    if (item % FW == w && nit < MAXIT) items[nit++] = b | (mt << 4) | ((h * (NT / 2)) << 12);
         }
     }
 
@@ -498,83 +510,136 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
         __syncwarp();
         TICK(1)
         // ---- work items ----
-        for (int q = 0; q < nit; ++q) {
-            const int b = items[q] & 15, mt = (items[q] >> 4) & 15;
+        // An item is one m8 tile of one bath for NJ n-tiles starting at j0: all NT tiles, or half of
+        // them when the item list is short enough to be split (every warp then gets a tap half and a
+        // head half instead of four warps a whole tap item and four a whole head item).
+        auto run_item = [&](auto njc, const int code) {
+            constexpr int NJ = decltype(njc)::value;
+            const int b = code & 15, mt = (code >> 4) & 15, j0 = (code >> 12) & 15;
             const FusedBath& B = P.b[b];
             const int rr = mt * 8 + lr;
             const bool valid = rr < B.nc;
-            if (items[q] >> 8) {
+            const int cb = 8 * j0;                       // first column of the item
+            if ((code >> 8) & 1) {
                 // noise minus memory-kernel tail at time t+1: xi(t+1) - P[s] - sum_{k=1}^{s+1} dt K[k] p_c(t+1-k)
-                double2 xi[NT], pt[NT];
+                double2 xi[NJ], pt[NJ];
 #pragma unroll
-                for (int j = 0; j < NT; ++j) {
+                for (int j = 0; j < NJ; ++j) {
                     xi[j] = make_double2(0.0, 0.0);
                     pt[j] = make_double2(0.0, 0.0);
                     if (valid) {
-                        xi[j] = ld2(&B.noise[((size_t)tn1 * B.nc + rr) * ldb + col0 + 8 * j + 2 * lc]);
-                        if (B.nonlocal) pt[j] = ld2(&B.P[((size_t)s * B.nc + rr) * ldb + col0 + 8 * j + 2 * lc]);
+                        xi[j] = ld2(&B.noise[((size_t)tn1 * B.nc + rr) * ldb + col0 + cb + 8 * j + 2 * lc]);
+                        if (B.nonlocal) pt[j] = ld2(&B.P[((size_t)s * B.nc + rr) * ldb + col0 + cb + 8 * j + 2 * lc]);
                     }
                 }
-                double acc[NT][2];
-                zero_acc<NT>(acc);
+                double acc[NJ][2];
+                zero_acc<NJ>(acc);
                 if (B.nonlocal) {
                     const int ntap = min(s + 1, B.ntap);
-                    for (int k = 1; k <= ntap; ++k) {
-                        const double* A = sm + B.off_kin + ((k - 1) * B.ncp + rr) * B.ldk + lc;
-                        const double* H = sm + B.off_hist + ((s + 1 - k) * B.ncp + lc) * LD + lr;
-                        for (int kk = 0; kk < B.ncp; kk += 4) {
-                            const double a = A[kk];
+                    if (B.ncp == 16) {
+                        // the usual lead size (nc <= 16): four k-steps per tap, unrolled, and two
+                        // accumulator sets (odd / even taps) to halve the dependent DMMA chains
+                        double acc2[NJ][2];
+                        zero_acc<NJ>(acc2);
+                        const double* A0 = sm + B.off_kin + rr * B.ldk + lc;
+                        const double* H0 = sm + B.off_hist + lc * LD + lr + cb;
+                        int k = 1;
+                        for (; k + 1 <= ntap; k += 2) {
+                            const double* A = A0 + (k - 1) * 16 * B.ldk;         // taps k and k + 1
+                            const double* H = H0 + (s + 1 - k) * 16 * LD;        // p_c(t+1-k); one slot below: p_c(t-k)
 #pragma unroll
-                            for (int j = 0; j < NT; ++j) dmma884(acc[j][0], acc[j][1], a, H[kk * LD + 8 * j]);
+                            for (int kk = 0; kk < 16; kk += 4) {
+                                const double a0 = A[kk], a1 = A[16 * B.ldk + kk];
+#pragma unroll
+                                for (int j = 0; j < NJ; ++j) {
+                                    dmma884(acc[j][0], acc[j][1], a0, H[kk * LD + 8 * j]);
+                                    dmma884(acc2[j][0], acc2[j][1], a1, H[(kk - 16) * LD + 8 * j]);
+                                }
+                            }
+                        }
+                        if (k <= ntap) {
+                            const double* A = A0 + (k - 1) * 16 * B.ldk;
+                            const double* H = H0 + (s + 1 - k) * 16 * LD;
+#pragma unroll
+                            for (int kk = 0; kk < 16; kk += 4) {
+                                const double a0 = A[kk];
+#pragma unroll
+                                for (int j = 0; j < NJ; ++j) dmma884(acc[j][0], acc[j][1], a0, H[kk * LD + 8 * j]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) { acc[j][0] += acc2[j][0]; acc[j][1] += acc2[j][1]; }
+                    } else {
+                        for (int k = 1; k <= ntap; ++k) {
+                            const double* A = sm + B.off_kin + ((k - 1) * B.ncp + rr) * B.ldk + lc;
+                            const double* H = sm + B.off_hist + ((s + 1 - k) * B.ncp + lc) * LD + lr + cb;
+                            for (int kk = 0; kk < B.ncp; kk += 4) {
+                                const double a = A[kk];
+#pragma unroll
+                                for (int j = 0; j < NJ; ++j) dmma884(acc[j][0], acc[j][1], a, H[kk * LD + 8 * j]);
+                            }
                         }
                     }
                 }
                 if (valid) {
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) {
+                    for (int j = 0; j < NJ; ++j) {
                         const double t0v = pt[j].x + acc[j][0], t1v = pt[j].y + acc[j][1];
-                        st2(&sm[B.off_nb + ((nbuf ^ 1) * B.ncp + rr) * LD + 8 * j + 2 * lc], xi[j].x - t0v, xi[j].y - t1v);
+                        st2(&sm[B.off_nb + ((nbuf ^ 1) * B.ncp + rr) * LD + cb + 8 * j + 2 * lc], xi[j].x - t0v, xi[j].y - t1v);
                         if (B.nonlocal && g == P.nsteps - 1)
-                            st2(&B.tail_cur[(size_t)rr * ldb + col0 + 8 * j + 2 * lc], t0v, t1v);
+                            st2(&B.tail_cur[(size_t)rr * ldb + col0 + cb + 8 * j + 2 * lc], t0v, t1v);
                     }
                 }
             } else {
                 // head of a small bath: only the scalars p_c.g_b (currents) are needed
                 const int hs = B.nonlocal ? s : 0;
                 const int inrem = valid ? reinterpret_cast<const int*>(sm + B.off_inrem)[rr] : 0;
-                double g[NT][2];
-                zero_acc<NT>(g);
+                double gh[NJ][2];
+                zero_acc<NJ>(gh);
                 const double* A = sm + B.off_hd + rr * B.ldk + lc;
-                const double* H = sm + B.off_hist + (hs * B.ncp + lc) * LD + lr;
-                for (int kk = 0; kk < B.ncp; kk += 4) {
-                    const double a = A[kk];
+                const double* H = sm + B.off_hist + (hs * B.ncp + lc) * LD + lr + cb;
+                if (B.ncp == 16) {
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) dmma884(g[j][0], g[j][1], a, H[kk * LD + 8 * j]);
+                    for (int kk = 0; kk < 16; kk += 4) {
+                        const double a = A[kk];
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) dmma884(gh[j][0], gh[j][1], a, H[kk * LD + 8 * j]);
+                    }
+                } else {
+                    for (int kk = 0; kk < B.ncp; kk += 4) {
+                        const double a = A[kk];
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) dmma884(gh[j][0], gh[j][1], a, H[kk * LD + 8 * j]);
+                    }
                 }
 #pragma unroll
-                for (int j2 = 0; j2 < NT; j2 += 2) {
+                for (int j2 = 0; j2 < NJ; j2 += 2) {
                     double v[8];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int j = j2 + h;
                         double s0 = 0.0, s1 = 0.0;
-                        if (j < NT && valid) {
-                            const double2 pv = ld2(&sm[B.off_hist + (hs * B.ncp + rr) * LD + 8 * j + 2 * lc]);
-                            s0 = pv.x * g[j < NT ? j : 0][0];
-                            s1 = pv.y * g[j < NT ? j : 0][1];
+                        if (j < NJ && valid) {
+                            const double2 pv = ld2(&sm[B.off_hist + (hs * B.ncp + rr) * LD + cb + 8 * j + 2 * lc]);
+                            s0 = pv.x * gh[j < NJ ? j : 0][0];
+                            s1 = pv.y * gh[j < NJ ? j : 0][1];
                         }
                         v[4 * h + 0] = s0; v[4 * h + 1] = s1;
                         v[4 * h + 2] = inrem ? s0 : 0.0; v[4 * h + 3] = inrem ? s1 : 0.0;
                     }
                     const double r = rs8(v, lr);     // lane lr: n-tile j2 + (lr>>2), kind lr&3 (s0, s1, r0, r1)
                     const int j = j2 + (lr >> 2), kind = lr & 3;
-                    if (j < NT) {
-                        if (kind < 2) sm[P.off_curp + (b * FW + w) * N + 8 * j + 2 * lc + kind] -= r;
-                        else if (P.rem >= 0) sm[P.off_curp + (P.rem * FW + w) * N + 8 * j + 2 * lc + kind - 2] += r;
+                    if (j < NJ) {
+                        if (kind < 2) sm[P.off_curp + (b * FW + w) * N + cb + 8 * j + 2 * lc + kind] -= r;
+                        else if (P.rem >= 0) sm[P.off_curp + (P.rem * FW + w) * N + cb + 8 * j + 2 * lc + kind - 2] += r;
                     }
                     __syncwarp();
                 }
             }
+        };
+        for (int q = 0; q < nit; ++q) {
+            if (NT >= 2 && split_items) run_item(std::integral_constant<int, (NT >= 2 ? NT / 2 : 1)>{}, items[q]);
+            else run_item(std::integral_constant<int, NT>{}, items[q]);
         }
         TICK(2)
         __syncthreads();                                                        // ---- S2
@@ -939,6 +1004,7 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
     cudaMemsetAsync(d_timing, 0, 10 * sizeof(long long), st);
     fp.timing = d_timing;
 #endif
+    fp.nosplit = (getenv("PYMD_FUSED_SPLIT") && atoi(getenv("PYMD_FUSED_SPLIT")) == 0) ? 1 : 0;
     const bool far_on = !(getenv("PYMD_FAR") && atoi(getenv("PYMD_FAR")) == 0);          // testing knob
     // mid mode: every non-local bath has an FFT far field (far.cu); one launch then advances up to the
     // end of the current super-block of kFarS steps, computing the pre-block tails in the kernel
