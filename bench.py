@@ -34,6 +34,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_emit = print
 CFG = dict(nd=60, ncl=15, ncr=15, seed=4, dt=1.0, T=300.0, dT=10.0, ml=100, nw=200, hwcut=0.03, bias=0.5)
 PIECE = 256
 
@@ -115,7 +116,7 @@ def run_reference(a):
                cpu_baseline=dict(value=r["value"], unit="trajectory-steps/s", cores=r["cores"], kind=r["kind"],
                                  sample=sample, per_core=r["per_core"]),
                e2e=dict(value=r["value"], unit="trajectory-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(out), flush=True)
+    _emit(json.dumps(out))
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -375,7 +376,7 @@ def run_ours(a):
                    vs_baseline=None, dtype="f64", data="synthetic", config=workload_config(a), clocks=clocks,
                    gpu_launches=int(launches), e2e=e2e, roofline=roof, cpu_baseline=cpu,
                    setup_s=t_setup, finite=finite, step_mode=a.mode)
-        print(json.dumps(out), flush=True)
+        _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -397,6 +398,15 @@ def main():
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
+    # stdout carries exactly ONE JSON line: everything else that libraries print there (e.g. the NCCL
+    # version banner) is sent to stderr by pointing fd 1 at fd 2 until the result is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    def _emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (line + "\n").encode())
     if a.impl == "reference":
         run_reference(a)
     else:
