@@ -315,7 +315,10 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
     // static work-item list of this warp: code = b | mt << 4 | kind << 8.  An item covers one m8 tile of
     // one bath for ALL n-tiles (A fragment loaded once per k-step, NT independent DMMA chains).  The
     // heavier tap items (kind 1) are dealt first, then the heads of the small baths (kind 0).
-    int items[MAXIT], nit = 0;
+    // up to MAXIT items of 16 bits each in one register (a local array indexed by the loop counter would
+    // live in local memory and cost a long-scoreboard stall per item)
+    unsigned long long items = 0;
+    int nit = 0;
     bool split_items = false;
     {
         int total = 0;
@@ -330,13 +333,32 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
             if (P.b[b].direct) continue;
             for (int mt = 0; mt < P.b[b].ncp / 8; ++mt)
                 for (int h = 0; h < nh; ++h, ++item)
-                    if (item % FW == w && nit < MAXIT) items[nit++] = b | (mt << 4) | (1 << 8) | ((h * (NT / 2)) << 12);
+                    if (item % FW == w && nit < MAXIT)
+                        items |= (unsigned long long)(b | (mt << 4) | (1 << 8) | ((h * (NT / 2)) << 12)) << (16 * nit++);
         }
         for (int b = 0; b < nb; ++b) {
             if (b == P.rem) continue;
             for (int mt = 0; mt < P.b[b].ncp / 8; ++mt)
                 for (int h = 0; h < nh; ++h, ++item)
-                    if (item % FW == w && nit < MAXIT) items[nit++] = b | (mt << 4) | ((h * (NT / 2)) << 12);
+                    if (item % FW == w && nit < MAXIT)
+                        items |= (unsigned long long)(b | (mt << 4) | ((h * (NT / 2)) << 12)) << (16 * nit++);
+        }
+    }
+
+    // L2 prefetch of the noise rows two steps ahead (they stream from HBM, 8 nc_b N bytes per bath and
+    // step): thread tid owns one 128-byte line of one (bath, row), or nothing
+    const double* pf_base = nullptr;
+    size_t pf_stride = 0;
+    {
+        constexpr int LPR = (N * 8 + 127) / 128;           // lines per row tile
+        int e = tid;
+        for (int b = 0; b < nb; ++b) {
+            const int cnt = P.b[b].nc * LPR;
+            if (e >= 0 && e < cnt) {
+                pf_base = P.b[b].noise + (size_t)(e / LPR) * ldb + col0 + (e % LPR) * 16;
+                pf_stride = (size_t)P.b[b].nc * ldb;
+            }
+            e -= cnt;
         }
     }
 
@@ -441,6 +463,10 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
         const int s = g - g0;                   // step within the block
         const int tn_cur = tn;
         const int tn1 = tn + 1 == P.nmd ? 0 : tn + 1;
+        if (pf_base) {
+            const int tn2 = tn1 + 1 == P.nmd ? 0 : tn1 + 1;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_base + (size_t)tn2 * pf_stride));
+        }
 
         // ============ round A: first force evaluation at time t, head p(t) ============
         double hA[NT][2];
@@ -638,8 +664,9 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
             }
         };
         for (int q = 0; q < nit; ++q) {
-            if (NT >= 2 && split_items) run_item(std::integral_constant<int, (NT >= 2 ? NT / 2 : 1)>{}, items[q]);
-            else run_item(std::integral_constant<int, NT>{}, items[q]);
+            const int code = (int)((items >> (16 * q)) & 0xffffu);
+            if (NT >= 2 && split_items) run_item(std::integral_constant<int, (NT >= 2 ? NT / 2 : 1)>{}, code);
+            else run_item(std::integral_constant<int, NT>{}, code);
         }
         TICK(2)
         __syncthreads();                                                        // ---- S2
