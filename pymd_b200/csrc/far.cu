@@ -39,18 +39,20 @@ constexpr int FAR_THREADS = 256;
 __constant__ double2 c_w64[64];   // exp(-2 pi i k / 64)
 __constant__ double2 c_w128[65];  // exp(-2 pi i k / 128)
 
-__host__ __device__ constexpr int rev4(int k) { return ((k & 3) << 4) | (k & 12) | (k >> 4); }
+// Position of bin f after the 32-point transform below (mixed radix 4, 4, 2, decimation in
+// frequency: every stage scatters its outputs by residue).
+__host__ __device__ constexpr int pos32(int f) { return (f & 3) * 8 + ((f >> 2) & 3) * 2 + (f >> 4); }
 
-// 64-point complex FFT, radix-4 decimation in frequency, all indices compile-time: the arrays live
-// in registers.  Input in natural order, output bin k at position rev4(k).  SIGN = -1 forward,
-// +1 inverse (unnormalised).
+// 32-point complex FFT, radix 4 x 4 x 2 decimation in frequency, all indices compile-time: the
+// arrays live in registers.  Input in natural order, output bin k at position pos32(k).
+// SIGN = -1 forward, +1 inverse (unnormalised).
 template <int SIGN>
-__device__ __forceinline__ void fft64(double (&re)[64], double (&im)[64]) {
+__device__ __forceinline__ void fft32(double (&re)[32], double (&im)[32]) {
 #pragma unroll
-    for (int stage = 0; stage < 3; ++stage) {
-        const int s = 64 >> (2 * stage), q = s >> 2, tw = 64 / s;
+    for (int stage = 0; stage < 2; ++stage) {
+        const int s = stage == 0 ? 32 : 8, q = s >> 2, tw = 64 / s;
 #pragma unroll
-        for (int b = 0; b < 64; b += s) {
+        for (int b = 0; b < 32; b += s) {
 #pragma unroll
             for (int j = 0; j < q; ++j) {
                 const int i0 = b + j, i1 = i0 + q, i2 = i1 + q, i3 = i2 + q;
@@ -64,7 +66,7 @@ __device__ __forceinline__ void fft64(double (&re)[64], double (&im)[64]) {
                 double y1r = t1r + t3r, y1i = t1i + t3i;
                 double y2r = t0r - t2r, y2i = t0i - t2i;
                 double y3r = t1r - t3r, y3i = t1i - t3i;
-                const int e1 = j * tw, e2 = 2 * j * tw, e3 = 3 * j * tw;     // < 64 for every stage
+                const int e1 = j * tw, e2 = 2 * j * tw, e3 = 3 * j * tw;     // < 64 for both stages
                 if (e1 != 0) {
                     const double c1 = c_w64[e1].x, s1 = SIGN < 0 ? c_w64[e1].y : -c_w64[e1].y;
                     const double c2 = c_w64[e2].x, s2 = SIGN < 0 ? c_w64[e2].y : -c_w64[e2].y;
@@ -80,6 +82,29 @@ __device__ __forceinline__ void fft64(double (&re)[64], double (&im)[64]) {
             }
         }
     }
+#pragma unroll
+    for (int b = 0; b < 32; b += 2) {
+        const double ar = re[b], ai = im[b], br = re[b + 1], bi = im[b + 1];
+        re[b] = ar + br; im[b] = ai + bi;
+        re[b + 1] = ar - br; im[b + 1] = ai - bi;
+    }
+}
+
+// untangle one conjugate pair of the packed real transform: X[f] from Z[f] = (zr, zi), Z[64-f] = (cr, ci)
+__device__ __forceinline__ void untangle(double zr, double zi, double cr, double ci, int f, double* out, int plane) {
+    const double ar = 0.5 * (zr + cr), ai = 0.5 * (zi - ci);
+    const double br = 0.5 * (zr - cr), bi = 0.5 * (zi + ci);
+    const double wr = c_w128[f].x, wi = c_w128[f].y;
+    // X[f] = a - i w b = a + (wi br + wr bi) + i (wi bi - wr br)
+    out[(2 * f) * plane] = ar + (wi * br + wr * bi);
+    out[(2 * f + 1) * plane] = ai + (wi * bi - wr * br);
+}
+// the inverse step: Z'[f] = (Y[f] + conj Y[64-f]) + i conj(w128^f) (Y[f] - conj Y[64-f])
+__device__ __forceinline__ void retangle(double yr, double yi, double cr, double ci, int f, double& zr, double& zi) {
+    const double ar = yr + cr, ai = yi - ci, br = yr - cr, bi = yi + ci;
+    const double wr = c_w128[f].x, wi = -c_w128[f].y;
+    zr = ar - (wr * bi + wi * br);
+    zi = ai + (wr * br - wi * bi);
 }
 
 struct FarBath {
@@ -104,58 +129,79 @@ __global__ void __launch_bounds__(FAR_THREADS, 1) far_kernel(const FarParams P) 
     const size_t ldb = P.ldb;
     const int col0 = blockIdx.x * NTRAJ;
     const int plane = ncp * NTRAJ;                          // doubles per (f, part)
-    const int j = tid / NTRAJ, n = tid % NTRAJ;             // series of this thread
+    // a series (dof j, trajectory n) is shared by two threads: half h = 0 takes the even bins, h = 1
+    // the odd bins of its 64-point complex transform (one radix-2 step, then a 32-point FFT each)
+    const int e = tid & 127, h = tid >> 7;
+    const int j = e / NTRAJ, n = e % NTRAJ;
     const bool series = j < nc;
 
     // padding rows (j >= nc) are B operands of phase 2 against zero A columns: keep them finite
-    for (int e = tid; e < NF * 2 * (ncp - nc) * NTRAJ; e += FAR_THREADS) {
-        const int fp = e / ((ncp - nc) * NTRAJ), r = e % ((ncp - nc) * NTRAJ);
+    for (int i = tid; i < NF * 2 * (ncp - nc) * NTRAJ; i += FAR_THREADS) {
+        const int fp = i / ((ncp - nc) * NTRAJ), r = i % ((ncp - nc) * NTRAJ);
         spec[fp * plane + nc * NTRAJ + r] = 0.0;
     }
 
     // ------------------------------------------------------------------ phase 1: forward
     if (series) {
-        double re[64], im[64];
+        double re[32], im[32];
         // x[m] = p_c(u0-98+m) lives in ring slot (hc0-98+m) mod R; entries older than the memory
-        // (age a = 97-m > ml-3) or older than the run (slot index < 0) are zero
+        // (age a = 97-m > ml-3) or older than the run (slot index < 0) are zero.  z[m] = x[2m] + i x[2m+1];
+        // a[m] = (z[m] +- z[m+32]) w64^(h m) feeds the even (h = 0) / odd (h = 1) bins.
         const long long first = B.hc0 - 98;
         int mlo = 100 - B.ml;
         if (first + mlo < 0) mlo = (int)(-first);
         int slot = (int)(((first % B.R) + B.R) % B.R);
-        const double* src = B.ring + (size_t)j * ldb + col0 + n;
         const size_t rowpitch = (size_t)ncp * ldb;
+        const double* base = B.ring + (size_t)j * ldb + col0 + n;
+        const double* src = base + (size_t)slot * rowpitch;
+        const double sgn = h ? -1.0 : 1.0;
 #pragma unroll
-        for (int m = 0; m < 128; ++m) {
+        for (int m = 0; m < 64; ++m) {                      // x[m]: first half of z
             double v = 0.0;
-            if (m < 97) {
-                if (m >= mlo) v = src[(size_t)slot * rowpitch];
-                if (++slot == B.R) slot = 0;
-            }
+            if (m >= mlo) v = *src;
+            src += rowpitch;
+            if (++slot == B.R) { slot = 0; src = base; }
             if (m & 1) im[m >> 1] = v; else re[m >> 1] = v;
         }
-        fft64<-1>(re, im);
-        // untangle: X[f] = (Z[f] + conj Z[64-f])/2 - (i/2) w128^f (Z[f] - conj Z[64-f])
-        double* out = spec + j * NTRAJ + n;
 #pragma unroll
-        for (int f = 0; f <= 32; ++f) {
-            const int g = 64 - f;
-            const double zr = re[rev4(f)], zi = im[rev4(f)];
-            const double cr = re[rev4(g & 63)], ci = im[rev4(g & 63)];
-            // f and its partner 64-f
-            {
-                const double ar = 0.5 * (zr + cr), ai = 0.5 * (zi - ci);
-                const double br = 0.5 * (zr - cr), bi = 0.5 * (zi + ci);
-                const double wr = c_w128[f].x, wi = c_w128[f].y;
-                // -i w (br + i bi) = (wi br + wr bi) + i (wi bi - wr br)
-                out[(2 * f) * plane] = ar + (wi * br + wr * bi);
-                out[(2 * f + 1) * plane] = ai + (wi * bi - wr * br);
+        for (int m = 64; m < 97; ++m) {                     // x[m]: z[32..48], folded in with the sign
+            double v = 0.0;
+            if (m >= mlo) v = *src;
+            src += rowpitch;
+            if (++slot == B.R) { slot = 0; src = base; }
+            if (m & 1) im[(m >> 1) - 32] += sgn * v; else re[(m >> 1) - 32] += sgn * v;
+        }
+        // (entries 17..31 have no partner: z[m+32] = 0 there.)  The odd half carries the twiddle w64^m.
+        if (h) {
+#pragma unroll
+            for (int m = 1; m < 32; ++m) {
+                const double c = c_w64[m].x, sn = c_w64[m].y;
+                const double t = re[m] * c - im[m] * sn;
+                im[m] = re[m] * sn + im[m] * c;
+                re[m] = t;
             }
-            if (g != f) {
-                const double ar = 0.5 * (cr + zr), ai = 0.5 * (ci - zi);
-                const double br = 0.5 * (cr - zr), bi = 0.5 * (ci + zi);
-                const double wr = c_w128[g].x, wi = c_w128[g].y;
-                out[(2 * g) * plane] = ar + (wi * br + wr * bi);
-                out[(2 * g + 1) * plane] = ai + (wi * bi - wr * br);
+        }
+        fft32<-1>(re, im);
+        // untangle: X[f] = (Z[f] + conj Z[64-f])/2 - (i/2) w128^f (Z[f] - conj Z[64-f]); Z[f] of this
+        // thread's parity sits at pos32((f - h) / 2)
+        double* out = spec + j * NTRAJ + n;
+        if (h == 0) {
+#pragma unroll
+            for (int f = 0; f <= 32; f += 2) {
+                const int g = 64 - f;
+                const double zr = re[pos32(f / 2)], zi = im[pos32(f / 2)];
+                const double cr = re[pos32((g & 63) / 2)], ci = im[pos32((g & 63) / 2)];
+                untangle(zr, zi, cr, ci, f, out, plane);
+                if (g != f) untangle(cr, ci, zr, zi, g, out, plane);
+            }
+        } else {
+#pragma unroll
+            for (int f = 1; f < 32; f += 2) {
+                const int g = 64 - f;
+                const double zr = re[pos32((f - 1) / 2)], zi = im[pos32((f - 1) / 2)];
+                const double cr = re[pos32((g - 1) / 2)], ci = im[pos32((g - 1) / 2)];
+                untangle(zr, zi, cr, ci, f, out, plane);
+                untangle(cr, ci, zr, zi, g, out, plane);
             }
         }
     }
@@ -207,36 +253,53 @@ __global__ void __launch_bounds__(FAR_THREADS, 1) far_kernel(const FarParams P) 
     __syncthreads();
 
     // ------------------------------------------------------------------ phase 3: inverse
-    if (series) {
-        double re[64], im[64];
+    {
+        double re[32], im[32];
         const double* in = spec + j * NTRAJ + n;
-        // re-tangle: Z'[f] = (Y[f] + conj Y[64-f]) + i conj(w128^f) (Y[f] - conj Y[64-f]),  f = 0..63
+        if (series) {
+            // re-tangle this thread's parity: Z'[k] <- bins f = 2k + h and 64 - f
+            if (h == 0) {
 #pragma unroll
-        for (int f = 0; f <= 32; ++f) {
-            const int g = 64 - f;
-            const double yr = in[(2 * f) * plane], yi = in[(2 * f + 1) * plane];
-            const double cr = in[(2 * g) * plane], ci = in[(2 * g + 1) * plane];
-            {
-                const double ar = yr + cr, ai = yi - ci, br = yr - cr, bi = yi + ci;
-                const double wr = c_w128[f].x, wi = -c_w128[f].y;
-                // i w (br + i bi) = -(wr bi + wi br) + i (wr br - wi bi)
-                re[f] = ar - (wr * bi + wi * br);
-                im[f] = ai + (wr * br - wi * bi);
+                for (int k = 0; k <= 16; ++k) {
+                    const int f = 2 * k, g = 64 - f;
+                    const double yr = in[(2 * f) * plane], yi = in[(2 * f + 1) * plane];
+                    const double cr = in[(2 * g) * plane], ci = in[(2 * g + 1) * plane];
+                    retangle(yr, yi, cr, ci, f, re[k], im[k]);
+                    if (k != 0 && k != 16) retangle(cr, ci, yr, yi, g, re[32 - k], im[32 - k]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int f = 2 * k + 1, g = 64 - f;
+                    const double yr = in[(2 * f) * plane], yi = in[(2 * f + 1) * plane];
+                    const double cr = in[(2 * g) * plane], ci = in[(2 * g + 1) * plane];
+                    retangle(yr, yi, cr, ci, f, re[k], im[k]);
+                    retangle(cr, ci, yr, yi, g, re[31 - k], im[31 - k]);
+                }
             }
-            if (g != f && g < 64) {
-                const double ar = cr + yr, ai = ci - yi, br = cr - yr, bi = ci + yi;
-                const double wr = c_w128[g].x, wi = -c_w128[g].y;
-                re[g] = ar - (wr * bi + wi * br);
-                im[g] = ai + (wr * br - wi * bi);
+            fft32<+1>(re, im);          // E[m] = sum_k Z'[2k+h] w32^(-k m) at pos32(m)
+        }
+        __syncthreads();                // every thread has read its bins: the spectra can be overwritten
+        // z'[m] = E_0[m] + conj(w64^m) E_1[m], m < 16: the odd half hands its term over through shared memory
+        double2* xch = reinterpret_cast<double2*>(spec);     // [16][128]
+        if (series && h) {
+#pragma unroll
+            for (int m = 0; m < kFarS / 2; ++m) {
+                const double c = c_w64[m].x, sn = -c_w64[m].y;
+                const double er = re[pos32(m)], ei = im[pos32(m)];
+                xch[m * 128 + e] = make_double2(er * c - ei * sn, er * sn + ei * c);
             }
         }
-        fft64<+1>(re, im);
-        double* dst = B.F + (size_t)j * ldb + col0 + n;
-        const size_t rowpitch = (size_t)nc * ldb;
+        __syncthreads();
+        if (series && !h) {
+            double* dst = B.F + (size_t)j * ldb + col0 + n;
+            const size_t rowpitch = (size_t)nc * ldb;
 #pragma unroll
-        for (int m = 0; m < kFarS / 2; ++m) {
-            dst[(size_t)(2 * m) * rowpitch] = re[rev4(m)];
-            dst[(size_t)(2 * m + 1) * rowpitch] = im[rev4(m)];
+            for (int m = 0; m < kFarS / 2; ++m) {
+                const double2 o = xch[m * 128 + e];
+                dst[(size_t)(2 * m) * rowpitch] = re[pos32(m)] + o.x;
+                dst[(size_t)(2 * m + 1) * rowpitch] = im[pos32(m)] + o.y;
+            }
         }
     }
 }
