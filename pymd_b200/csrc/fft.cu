@@ -111,38 +111,44 @@ __global__ void __launch_bounds__(128) fft_pass_kernel(const void* __restrict__ 
 // Fused radix R*R pass (R = 8: 64, R = 4: 16).  blockDim = (32 columns, R): thread (x, r1) first
 // transforms inputs r1 + R r2 (r2 < R), the R x R intermediate goes through shared memory with
 // the inner twiddles W_{R^2}^{r1 q2} applied, thread (x, q2) then transforms over r1 and stores
-// outputs R q1 + q2.  Same Stockham indexing as fft_pass_kernel with radix R^2.
-template <int R>
+// outputs R q1 + q2.  Same Stockham indexing as fft_pass_kernel with radix R^2.  The loads of the
+// next column tile are in flight while the current one is transformed; per-thread base pointers
+// keep the address arithmetic (and with it the register count: two CTAs per SM) small.
+template <int R, int LM, int SM>
 __global__ void __launch_bounds__(32 * R, 512 / (32 * R)) fft_pass2_kernel(const void* __restrict__ src, void* __restrict__ dst,
-                                                           int n, int Ns, long long cols, int conj_in, int conj_out,
-                                                           const double2* __restrict__ tw, int twN, int loadmode,
-                                                           int storemode, long long src_ld, long long dst_ld,
-                                                           double scale, long long dst_cw, long long dst_cs) {
+                                                                          int n, int Ns, long long cols, int conj_in, int conj_out,
+                                                                          const double2* __restrict__ tw, int twN,
+                                                                          long long src_ld, long long dst_ld,
+                                                                          double scale, long long dst_cw, long long dst_cs) {
     constexpr int RR = R * R;
     __shared__ double2 ex[RR][32];
     // blockIdx.x runs over column tiles so that the CTAs resident at the same time read neighbouring
     // 512-byte pieces of the same rows (DRAM page locality); blockIdx.y is the butterfly index
     const int j = blockIdx.y;
     const int k = j % Ns;
-    const int base = (j / Ns) * Ns * RR + k;
     const int nr = n / RR;
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int step = twN / (Ns * RR);                 // outer twiddle W_{Ns RR}^{r k}
-    const int istep = twN / RR;                        // inner twiddle W_{RR}^{r1 q2}
+    const int tw0 = ty * k * (twN / (Ns * RR)), twd = R * k * (twN / (Ns * RR));   // outer twiddle index: tw0 + r2 twd
+    const int twi = ty * (twN / RR);                                                // inner twiddle index: q2 twi
     const long long cstride = (long long)gridDim.x * 32;
-    // the loads of the next column tile are in flight while the current one is transformed
+    // element (row r = ty + R r2 of this butterfly, column c): sbase + r2 * sstep + c
+    const long long srow = LM == LOAD_C ? 1 : 2;            // real-pair sources hold two rows per complex row
+    const long long sbase = (long long)(j + (long long)ty * nr) * srow * src_ld + tx;
+    const long long sstep = (long long)R * nr * srow * src_ld;
+    const long long drow = SM == STORE_C ? 1 : 2;
+    const long long dbase = ((long long)(j / Ns) * Ns * RR + k + (long long)ty * Ns) * drow * dst_ld;
+    const long long dstep = (long long)R * Ns * drow * dst_ld;
     auto issue = [&](double2 (&d)[R], long long c0) {
-        const long long col = c0 + tx;
+        const bool ok = c0 + tx < cols;
 #pragma unroll
         for (int r2 = 0; r2 < R; ++r2) {
-            const long long idx = j + (long long)(ty + R * r2) * nr;
             d[r2] = make_double2(0.0, 0.0);
-            if (col < cols) {
-                if (loadmode == LOAD_C) {
-                    d[r2] = __ldcs(static_cast<const double2*>(src) + idx * src_ld + col);
+            if (ok) {
+                if (LM == LOAD_C) {
+                    d[r2] = __ldcs(static_cast<const double2*>(src) + sbase + r2 * sstep + c0);
                 } else {
-                    const double* xr = static_cast<const double*>(src);
-                    d[r2] = make_double2(__ldcs(xr + (2 * idx) * src_ld + col), __ldcs(xr + (2 * idx + 1) * src_ld + col));
+                    const double* xr = static_cast<const double*>(src) + sbase + r2 * sstep + c0;
+                    d[r2] = make_double2(__ldcs(xr), __ldcs(xr + src_ld));
                 }
             }
         }
@@ -159,31 +165,31 @@ __global__ void __launch_bounds__(32 * R, 512 / (32 * R)) fft_pass2_kernel(const
         // stage 1: r1 = ty, r2 = 0..R-1
 #pragma unroll
         for (int r2 = 0; r2 < R; ++r2) {
-            const int r = ty + R * r2;
             if (conj_in) v[r2].y = -v[r2].y;
-            if (Ns > 1 && r > 0) v[r2] = cmul(v[r2], tw[r * k * step]);
+            if (Ns > 1 && (r2 > 0 || ty > 0)) v[r2] = cmul(v[r2], tw[tw0 + r2 * twd]);
         }
         butterfly<R>(v);                                // v[q2] = sum_r2 ... exp(-2 pi i r2 q2 / R)
         __syncthreads();                                // previous tile consumed
 #pragma unroll
-        for (int q2 = 0; q2 < R; ++q2) ex[ty * R + q2][tx] = (ty * q2) ? cmul(v[q2], tw[ty * q2 * istep]) : v[q2];
+        for (int q2 = 0; q2 < R; ++q2) ex[ty * R + q2][tx] = (q2 > 0 && ty > 0) ? cmul(v[q2], tw[q2 * twi]) : v[q2];
         __syncthreads();
         // stage 2: q2 = ty, over r1
 #pragma unroll
         for (int r1 = 0; r1 < R; ++r1) v[r1] = ex[r1 * R + ty][tx];
         butterfly<R>(v);                                // v[q1]: output R q1 + q2
         if (ok) {
-            const long long dc = (storemode != STORE_C && dst_cw) ? (col / dst_cw) * dst_cs + col % dst_cw : col;
+            const double si = conj_out ? -scale : scale;
+            if (SM == STORE_C) {
+                double2* dp = static_cast<double2*>(dst) + dbase + col;
 #pragma unroll
-            for (int q1 = 0; q1 < R; ++q1) {
-                const long long o = base + (long long)(R * q1 + ty) * Ns;
-                const double2 out = make_double2(scale * v[q1].x, (conj_out ? -scale : scale) * v[q1].y);
-                if (storemode == STORE_C) {
-                    __stcs(static_cast<double2*>(dst) + o * dst_ld + col, out);
-                } else {
-                    double* dr = static_cast<double*>(dst);
-                    dr[(2 * o) * dst_ld + dc] = out.x;
-                    dr[(2 * o + 1) * dst_ld + dc] = out.y;
+                for (int q1 = 0; q1 < R; ++q1) __stcs(dp + q1 * dstep, make_double2(scale * v[q1].x, si * v[q1].y));
+            } else {
+                const long long dc = dst_cw ? (col / dst_cw) * dst_cs + col % dst_cw : col;
+                double* dp = static_cast<double*>(dst) + dbase + dc;
+#pragma unroll
+                for (int q1 = 0; q1 < R; ++q1) {
+                    dp[q1 * dstep] = scale * v[q1].x;
+                    dp[q1 * dstep + dst_ld] = si * v[q1].y;
                 }
             }
         }
@@ -248,10 +254,21 @@ int fft_columns(const void* src, void* dst, double2* bufA, double2* bufB, const 
             if (xb > 148) xb = 148;                     // half a wave of column tiles per butterfly index
             PYMD_REQUIRE(p.n / R <= 65535, "fft: length %d too long for the fused pass", p.n);
             dim3 grid((unsigned)xb, p.n / R);
-            if (R == 64)
-                fft_pass2_kernel<8><<<grid, dim3(32, 8), 0, stream>>>(cur, out, p.n, Ns, p.cols, ci, co, tw, p.n, lm, sm, sld, dld, sc, cw, cs);
-            else
-                fft_pass2_kernel<4><<<grid, dim3(32, 4), 0, stream>>>(cur, out, p.n, Ns, p.cols, ci, co, tw, p.n, lm, sm, sld, dld, sc, cw, cs);
+#define PYMD_FFT2(RAD, LMODE, SMODE)                                                                       \
+    fft_pass2_kernel<RAD, LMODE, SMODE><<<grid, dim3(32, RAD), 0, stream>>>(cur, out, p.n, Ns, p.cols, ci, co, tw, \
+                                                                            p.n, sld, dld, sc, cw, cs)
+            if (R == 64) {
+                if (lm == LOAD_C && sm == STORE_C) PYMD_FFT2(8, LOAD_C, STORE_C);
+                else if (lm == LOAD_C) PYMD_FFT2(8, LOAD_C, STORE_REAL_ROWS);
+                else if (sm == STORE_C) PYMD_FFT2(8, LOAD_REAL_PAIRS, STORE_C);
+                else PYMD_FFT2(8, LOAD_REAL_PAIRS, STORE_REAL_ROWS);
+            } else {
+                if (lm == LOAD_C && sm == STORE_C) PYMD_FFT2(4, LOAD_C, STORE_C);
+                else if (lm == LOAD_C) PYMD_FFT2(4, LOAD_C, STORE_REAL_ROWS);
+                else if (sm == STORE_C) PYMD_FFT2(4, LOAD_REAL_PAIRS, STORE_C);
+                else PYMD_FFT2(4, LOAD_REAL_PAIRS, STORE_REAL_ROWS);
+            }
+#undef PYMD_FFT2
         } else {
             long long xb = (p.cols + 127) / 128;
             if (xb > 592) xb = 592;
