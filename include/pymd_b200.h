@@ -115,9 +115,10 @@ int pymd_noise_generate(const double* lre_dev, const double* lim_dev, const doub
                         int nmd, int nc, int ldb, int n0, int n1, double dt, double* out_dev,
                         void* work_dev, void* stream);
 
-/* N.random.normal replacement (noise.py:282): counter-based Philox4x32-10 + Box-Muller.
- * Element (row r, trajectory n) depends only on (seed, stream_id, r, traj0+n): results do
- * not depend on how the ensemble is sharded over GPUs.  out: dev [rows][ldb]. */
+/* N.random.normal replacement (noise.py:282): counter-based Philox4x32-10 + Box-Muller using both
+ * outputs (rows 2r and 2r+1 share the counter r).  Element (row r, trajectory n) depends only on
+ * (seed, stream_id, r, traj0+n): results do not depend on how the ensemble is sharded over GPUs.
+ * out: dev [rows][ldb]. */
 int pymd_philox_normal(double* out_dev, long long rows, int ldb, uint64_t seed, uint32_t stream_id,
                        long long traj0, void* stream);
 /* N.random.rand replacement (md.py:280). */

@@ -33,21 +33,30 @@ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
     return ((double)(v >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
+// NORMAL = 0: one uniform per (row, trajectory), counter (row, trajectory).
+// NORMAL = 1: Box-Muller with BOTH outputs: the counter (row pair r/2, trajectory) yields the normals of
+// rows 2(r/2) (cosine branch) and 2(r/2)+1 (sine branch), halving the Philox / log / sqrt work per number.
 template <int NORMAL>
 __global__ void philox_kernel(double* out, long long rows, int ldb, uint32_t k0, uint32_t k1,
                               uint32_t stream_id, long long traj0) {
-    const size_t total = (size_t)rows * ldb;
+    const long long prow = NORMAL ? (rows + 1) / 2 : rows;
+    const size_t total = (size_t)prow * ldb;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
         const unsigned long long r = idx / ldb;
-        const unsigned long long tr = (unsigned long long)(traj0 + (long long)(idx % ldb));
+        const int n = (int)(idx % ldb);
+        const unsigned long long tr = (unsigned long long)(traj0 + n);
         uint32_t x[4];
         philox4x32_10((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)tr, stream_id ^ (uint32_t)(tr >> 32) * 0x85EBCA6Bu,
                       k0, k1, x);
         const double u1 = u53(x[0], x[1]);
         if (NORMAL) {
             const double u2 = u53(x[2], x[3]);
-            out[idx] = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+            const double rad = sqrt(-2.0 * log(u1));
+            double sn, cs;
+            sincospi(2.0 * u2, &sn, &cs);
+            out[(size_t)(2 * r) * ldb + n] = rad * cs;
+            if ((long long)(2 * r + 1) < rows) out[(size_t)(2 * r + 1) * ldb + n] = rad * sn;
         } else {
             out[idx] = u1;
         }

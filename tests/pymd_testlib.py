@@ -120,5 +120,11 @@ def philox_uniforms(rows, ldb, seed, stream_id, traj0=0):
 
 
 def philox_normals(rows, ldb, seed, stream_id, traj0=0):
-    u1, u2 = philox_uniforms(rows, ldb, seed, stream_id, traj0)
-    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+    """Box-Muller with both outputs: counter row r' feeds rows 2r' (cos) and 2r'+1 (sin)."""
+    pr = (rows + 1) // 2
+    u1, u2 = philox_uniforms(pr, ldb, seed, stream_id, traj0)
+    rad = np.sqrt(-2.0 * np.log(u1))
+    z = np.empty((2 * pr, ldb))
+    z[0::2] = rad * np.cos(2.0 * np.pi * u2)
+    z[1::2] = rad * np.sin(2.0 * np.pi * u2)
+    return z[:rows]
