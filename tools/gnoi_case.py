@@ -16,12 +16,12 @@ lre = T(lambda: torch.as_tensor(np.ascontiguousarray(fac.L.real)).cuda(), "H2D L
 lim = T(lambda: torch.as_tensor(np.ascontiguousarray(fac.L.imag)).cuda(), "H2D L.imag")
 xi = T(lambda: PN.white_noise(nf, nc, ldb, 1, 1), "philox normals")
 out = torch.empty((nmd, nc, ldb), dtype=torch.float64, device="cuda")
-per_row = _lib.load().pymd_noise_work_bytes(nmd, 1, ldb)
-rows = max(1, min(nc, PN.MAX_WORK_BYTES // per_row))
-work = torch.empty(per_row * rows, dtype=torch.uint8, device="cuda")
+per_col = _lib.load().pymd_noise_work_bytes(nmd, nc, 1)
+cw = max(32, min(ldb, (PN.MAX_WORK_BYTES // per_col) // 32 * 32))
+work = torch.empty(per_col * cw, dtype=torch.uint8, device="cuda")
 def gen():
-    for i0 in range(0, nc, rows):
-        _lib.call("pymd_noise_generate", lre.data_ptr(), lim.data_ptr(), xi.data_ptr(), nmd, nc, ldb, i0, min(nc, i0 + rows),
+    for n0 in range(0, ldb, cw):
+        _lib.call("pymd_noise_generate", lre.data_ptr(), lim.data_ptr(), xi.data_ptr(), nmd, nc, ldb, n0, min(ldb, n0 + cw),
                   1.0, out.data_ptr(), work.data_ptr(), _lib.stream_ptr())
-T(gen, "shape+fft (%d row chunks)" % ((nc + rows - 1) // rows))
+T(gen, "shape+fft (%d trajectory chunks)" % ((ldb + cw - 1) // cw))
 T(lambda: b.gnoi(), "bath.gnoi() total")
