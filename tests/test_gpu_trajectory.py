@@ -347,3 +347,49 @@ def test_far_field_fft_against_direct_product_and_oracle(cuda, case, nmd, monkey
         assert np.abs(a - b).max() < 1e-11 * max(np.abs(b).max(), 1e-300)
     om, recs = T.run_oracle(c, j, m1, xi, r, 4, nmd)
     compare(m1, recs[0], 4, tol=3e-11)
+
+
+def test_long_run_statistics_against_the_oracle_ensemble(cuda):
+    """North star: long-run kinetic energy and heat currents must agree with the reference path
+    within statistical error.  A two-lead junction with a 40 K bias (ph2 shape, quantum baths) is run
+    for 1024 steps: 4096 trajectories on the device (Philox noise, random phases) against 48
+    independent trajectories of the CPU oracle (numpy RNG).  After a burn-in the time-averaged kinetic
+    energy and lead currents of the two ensembles must agree within 4 combined standard errors, and
+    the device ensemble must carry a resolved, directed current that roughly balances (the slowest
+    modes are still relaxing at this horizon: <J_L> + <J_R> is 1e-7 of 2.4e-5 only after 2048 steps)."""
+    c = dict(T.CASES["ph2"]); c.update(nmd=1024, dT=40.0)
+    burn = 512
+    B = 4096
+    m, j = T.device_md(c, B, savepq=False, seed=77)
+    m.initialise(); m.ResetHis()
+    for b in m.baths:
+        b.gnoi()
+    m.steps(c["nmd"])
+    ek = m._etot[burn:, :B].mean(0).cpu().numpy()                       # per trajectory time averages
+    cur = [b._cur_dev[burn:, :B].mean(0).cpu().numpy() for b in m.baths]
+    dev = [(x.mean(), x.std(ddof=1) / np.sqrt(B)) for x in [ek] + cur]
+
+    rng = np.random.default_rng(5)
+    no = 48
+    ora = [[] for _ in range(1 + len(m.baths))]
+    nf = c["nmd"] // 2 + 1
+    for n in range(no):
+        om = T.oracle_md(c, j)
+        om.initialise(r=rng.uniform(0, 1, c["nd"]))
+        om.ResetHis()
+        for b, ob in enumerate(om.baths):
+            ob.gnoi(xi=rng.standard_normal((nf, ob.nc)), factors=m.baths[b].spectral_factors().as_oracle())
+        om.ResetSavepq()
+        for _ in range(c["nmd"]):
+            om.vv()
+        ora[0].append(om.etot[burn:].mean())
+        for b, ob in enumerate(om.baths):
+            ora[1 + b].append(ob.cur[burn:].mean())
+    for (dm, ds), o in zip(dev, ora):
+        o = np.asarray(o)
+        om_, os_ = o.mean(), o.std(ddof=1) / np.sqrt(no)
+        assert abs(dm - om_) < 4.0 * np.hypot(ds, os_), (dm, ds, om_, os_)
+    # what enters from the hot lead leaves into the cold one
+    tot = cur[0] + cur[1]
+    assert abs(tot.mean()) < 0.35 * abs(cur[0].mean())
+    assert cur[0].mean() > 0 > cur[1].mean() and abs(cur[0].mean()) > 5.0 * dev[1][1]
