@@ -22,6 +22,7 @@
 //            back in place;
 //   phase 3  thread (dof i, trajectory n): re-tangles, inverse 64-point FFT in registers, stores
 //            the 32 wanted outputs to F[r][i][n].
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <vector>
@@ -112,6 +113,8 @@ struct FarBath {
     const double* ghat;     // [NF][2][ncp/8][ncp/4][32] A fragments of Re/Im Ghat (1/128 folded in)
     double* F;              // [kFarS][nc][ldb]
     int R, nc, ncp, ml;
+    int seg;                // window segment m: ages 1 + 97 m .. 97 (m + 1) before p(u0-1)
+    int accumulate;         // add to F (segments m > 0)
     long long hc0;          // rows appended to the ring before p(u0)
 };
 struct FarParams {
@@ -147,9 +150,9 @@ __global__ void __launch_bounds__(FAR_THREADS, 1) far_kernel(const FarParams P) 
         // x[m] = p_c(u0-98+m) lives in ring slot (hc0-98+m) mod R; entries older than the memory
         // (age a = 97-m > ml-3) or older than the run (slot index < 0) are zero.  z[m] = x[2m] + i x[2m+1];
         // a[m] = (z[m] +- z[m+32]) w64^(h m) feeds the even (h = 0) / odd (h = 1) bins.
-        const long long first = B.hc0 - 98;
-        int mlo = 100 - B.ml;
-        if (first + mlo < 0) mlo = (int)(-first);
+        const long long first = B.hc0 - 98 - 97LL * B.seg;
+        int mlo = 100 + 97 * B.seg - B.ml;
+        if (first + mlo < 0) mlo = first + 97 < 0 ? 97 : (int)(-first);
         int slot = (int)(((first % B.R) + B.R) % B.R);
         const size_t rowpitch = (size_t)ncp * ldb;
         const double* base = B.ring + (size_t)j * ldb + col0 + n;
@@ -297,8 +300,13 @@ __global__ void __launch_bounds__(FAR_THREADS, 1) far_kernel(const FarParams P) 
 #pragma unroll
             for (int m = 0; m < kFarS / 2; ++m) {
                 const double2 o = xch[m * 128 + e];
-                dst[(size_t)(2 * m) * rowpitch] = re[pos32(m)] + o.x;
-                dst[(size_t)(2 * m + 1) * rowpitch] = im[pos32(m)] + o.y;
+                double y0 = re[pos32(m)] + o.x, y1 = im[pos32(m)] + o.y;
+                if (B.accumulate) {
+                    y0 += dst[(size_t)(2 * m) * rowpitch];
+                    y1 += dst[(size_t)(2 * m + 1) * rowpitch];
+                }
+                dst[(size_t)(2 * m) * rowpitch] = y0;
+                dst[(size_t)(2 * m + 1) * rowpitch] = y1;
             }
         }
     }
@@ -326,10 +334,14 @@ int init_twiddles() {
 
 }  // namespace
 
+// windows of 97 ring rows needed to cover the taps k = 3 .. ml-1
+static int far_segments(int ml) { return std::max(1, (ml - 3 + 96) / 97); }
+
 bool far_supported(const BathHost& H) {
-    // the 97-entry window + 32 outputs fill the length-128 transform exactly; the in-kernel mid field
-    // of fused.cu holds one tap (ncp x ncp) as at most 2 x 4 register fragments
-    return H.ml >= kFarMinMl && H.ml <= 100 && H.ncp <= 16 && H.R >= H.ml - 2;
+    // a 97-entry window + 32 outputs fill the length-128 transform exactly: memories longer than 100
+    // steps take one window (one launch) per 97 further taps; the in-kernel mid field of fused.cu holds
+    // one tap (ncp x ncp) as at most 2 x 4 register fragments
+    return H.ml >= kFarMinMl && H.ncp <= 16 && H.R >= H.ml - 2;
 }
 
 // Host side, once per bath: Ghat[f] = (1/128) sum_d dt K[d+99] exp(-2 pi i f d / 128), d = -96..31,
@@ -342,23 +354,26 @@ int far_build(pymd_ctx* c, int b) {
     const long double pi = 3.14159265358979323846264338327950288L;
     std::vector<std::complex<double>> w(128);
     for (int k = 0; k < 128; ++k) w[k] = std::complex<double>((double)cosl(2.0L * pi * k / 128.0L), (double)-sinl(2.0L * pi * k / 128.0L));
-    std::vector<double> frag((size_t)NF * 2 * MT * KK * 32, 0.0);
+    const int nseg = far_segments(H.ml);
+    const size_t segsize = (size_t)NF * 2 * MT * KK * 32;
+    std::vector<double> frag(segsize * nseg, 0.0);
     std::vector<std::complex<double>> gh(NF);
-    for (int i = 0; i < nc; ++i)
-        for (int j = 0; j < nc; ++j) {
-            for (int f = 0; f < NF; ++f) gh[f] = 0.0;
-            for (int d = -96; d <= 31; ++d) {
-                const int k = d + 99;
-                if (k < 3 || k > H.ml - 1) continue;
-                const double g = c->dt * H.kernel[((size_t)k * nc + i) * nc + j] / 128.0;
-                for (int f = 0; f < NF; ++f) gh[f] += g * w[(((long long)f * d) % 128 + 128) % 128];
+    for (int sg = 0; sg < nseg; ++sg)
+        for (int i = 0; i < nc; ++i)
+            for (int j = 0; j < nc; ++j) {
+                for (int f = 0; f < NF; ++f) gh[f] = 0.0;
+                for (int d = -96; d <= 31; ++d) {
+                    const int k = d + 99 + 97 * sg;
+                    if (k < 3 || k > H.ml - 1) continue;
+                    const double g = c->dt * H.kernel[((size_t)k * nc + i) * nc + j] / 128.0;
+                    for (int f = 0; f < NF; ++f) gh[f] += g * w[(((long long)f * d) % 128 + 128) % 128];
+                }
+                const int mt = i / 8, lr = i % 8, kk = j / 4, lc = j % 4, lane = lr * 4 + lc;
+                for (int f = 0; f < NF; ++f) {
+                    frag[sg * segsize + (((size_t)(2 * f) * MT + mt) * KK + kk) * 32 + lane] = gh[f].real();
+                    frag[sg * segsize + (((size_t)(2 * f + 1) * MT + mt) * KK + kk) * 32 + lane] = gh[f].imag();
+                }
             }
-            const int mt = i / 8, lr = i % 8, kk = j / 4, lc = j % 4, lane = lr * 4 + lc;
-            for (int f = 0; f < NF; ++f) {
-                frag[(((size_t)(2 * f) * MT + mt) * KK + kk) * 32 + lane] = gh[f].real();
-                frag[(((size_t)(2 * f + 1) * MT + mt) * KK + kk) * 32 + lane] = gh[f].imag();
-            }
-        }
     if (H.d_ghat) cudaFree(H.d_ghat);
     PYMD_CUDA_CHECK(cudaMalloc(&H.d_ghat, frag.size() * sizeof(double)));
     PYMD_CUDA_CHECK(cudaMemcpy(H.d_ghat, frag.data(), frag.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -400,22 +415,30 @@ int far_launch_t(pymd_ctx* c, const FarParams& P, int nb, cudaStream_t st) {
 // Far fields of the super-block that starts now (ring state: hcount rows appended) for every bath
 // in `mask`; one launch per distinct padded bath size.
 int far_launch(pymd_ctx* c, unsigned mask, cudaStream_t st) {
-    for (int ncp : {8, 16}) {
-        FarParams P{};
-        P.ldb = c->ldb;
-        int nb = 0;
-        for (int b = 0; b < c->nbath; ++b) {
-            BathHost& H = c->bath[b];
-            if (!(mask & (1u << b)) || H.ncp != ncp) continue;
-            FarBath& B = P.b[nb++];
-            B.ring = c->sd.b[b].ring; B.ghat = H.d_ghat; B.F = H.d_far;
-            B.R = H.R; B.nc = H.nc; B.ncp = H.ncp; B.ml = H.ml; B.hc0 = H.hcount;
-            H.far_base = H.hcount;
-            H.far_valid = true;
+    int maxseg = 1;
+    for (int b = 0; b < c->nbath; ++b)
+        if ((mask & (1u << b)) && c->bath[b].ml > 1) maxseg = std::max(maxseg, far_segments(c->bath[b].ml));
+    for (int sg = 0; sg < maxseg; ++sg) {
+        for (int ncp : {8, 16}) {
+            FarParams P{};
+            P.ldb = c->ldb;
+            int nb = 0;
+            for (int b = 0; b < c->nbath; ++b) {
+                BathHost& H = c->bath[b];
+                if (!(mask & (1u << b)) || H.ncp != ncp || sg >= far_segments(H.ml)) continue;
+                if (sg > 0 && H.hcount < 2 + 97LL * sg) continue;       // window entirely before the run began
+                FarBath& B = P.b[nb++];
+                const size_t segsize = (size_t)NF * 2 * (ncp / 8) * (ncp / 4) * 32;
+                B.ring = c->sd.b[b].ring; B.ghat = H.d_ghat + sg * segsize; B.F = H.d_far;
+                B.R = H.R; B.nc = H.nc; B.ncp = H.ncp; B.ml = H.ml; B.hc0 = H.hcount;
+                B.seg = sg; B.accumulate = sg > 0;
+                H.far_base = H.hcount;
+                H.far_valid = true;
+            }
+            if (!nb) continue;
+            int rc = ncp == 8 ? far_launch_t<8>(c, P, nb, st) : far_launch_t<16>(c, P, nb, st);
+            if (rc) return rc;
         }
-        if (!nb) continue;
-        int rc = ncp == 8 ? far_launch_t<8>(c, P, nb, st) : far_launch_t<16>(c, P, nb, st);
-        if (rc) return rc;
     }
     return PYMD_OK;
 }

@@ -316,12 +316,15 @@ def test_smoke_case(cuda):
     assert smoke_case.run(verbose=False) < 1e-10
 
 
-@pytest.mark.parametrize("case,nmd", [("chain39", 512), ("aubz", 256)])
-def test_far_field_fft_against_direct_product_and_oracle(cuda, case, nmd, monkeypatch):
+@pytest.mark.parametrize("case,nmd,ml", [("chain39", 512, None), ("aubz", 256, None), ("chain39", 512, 250), ("ragged", 256, 120)])
+def test_far_field_fft_against_direct_product_and_oracle(cuda, case, nmd, ml, monkeypatch):
     """The FFT far field (csrc/far.cu, super-blocks of 32 steps) against the direct block-Toeplitz
     product (PYMD_FAR=0) over several full 97-entry windows, with ragged steps() calls so that
-    super-blocks start at arbitrary times; and against the oracle over the whole horizon."""
+    super-blocks start at arbitrary times; and against the oracle over the whole horizon.  Memories
+    longer than 100 steps (ml = 250, 120) take several 97-row windows per super-block."""
     c = dict(T.CASES[case]); c["nmd"] = nmd
+    if ml:
+        c["ml"] = ml
     batch = 9
     runs = {}
     for far in ("1", "0"):
