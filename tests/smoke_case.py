@@ -1,6 +1,7 @@
 """__graft_entry__.smoke(): one small ensemble run of the hot path on cuda:0 -- noise
-generation, 32 velocity-Verlet steps with an electron bath, two non-local phonon baths and
-a constraint, power spectra -- checked against the oracle (test infrastructure)."""
+generation (tensor-pipe shaping + FFT), 64 velocity-Verlet steps with an electron bath, two
+non-local phonon baths with a 40-step memory (fused step kernel with in-kernel mid field + FFT far
+field) and a constraint, power spectra -- checked against the oracle (test infrastructure)."""
 import os
 import sys
 
@@ -15,7 +16,7 @@ def run(verbose=True):
     import torch
     assert torch.cuda.is_available(), "smoke() needs a CUDA device"
     import pymd_testlib as T
-    c = T.CASES["eph"]
+    c = dict(T.CASES["eph"], ml=40, nmd=64)
     B = 5
     m, j = T.device_md(c, B)
     xi, r = T.draw(c, m, B, seed=123)
