@@ -312,10 +312,12 @@ __global__ void __launch_bounds__(FAR_THREADS, 1) far_kernel(const FarParams P) 
     }
 }
 
-bool g_tw_ready = false;
+unsigned long long g_tw_ready = 0;      // bit d: constant tables uploaded to device d
 
 int init_twiddles() {
-    if (g_tw_ready) return PYMD_OK;
+    int dev = 0;
+    PYMD_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 64 && (g_tw_ready >> dev) & 1ull) return PYMD_OK;
     double2 w64[64], w128[65];
     const long double pi = 3.14159265358979323846264338327950288L;
     for (int k = 0; k < 64; ++k) {
@@ -328,7 +330,7 @@ int init_twiddles() {
     }
     PYMD_CUDA_CHECK(cudaMemcpyToSymbol(c_w64, w64, sizeof(w64)));
     PYMD_CUDA_CHECK(cudaMemcpyToSymbol(c_w128, w128, sizeof(w128)));
-    g_tw_ready = true;
+    if (dev < 64) g_tw_ready |= 1ull << dev;
     return PYMD_OK;
 }
 
