@@ -27,8 +27,7 @@ void pymd_set_error(const char* fmt, ...) {
 
 namespace pymd {
 
-int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st, long long wmax = -1,
-                const double* bias = nullptr);
+int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st);
 int fused_supported(const pymd_ctx* c);
 int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t stream);
 
@@ -341,20 +340,14 @@ static int gemm_plain(pymd_ctx* c, const double* A, int lda, int M, int K, const
 }
 
 // out[s][i][n] = dt * sum_{lag>=0} K[s + koff + lag][i][:] . ring(newest - lag)[:][n],  s < T
-// wmax >= 0 limits the product to the newest wmax ring rows (the older ones are covered by the far
-// field `bias`, far.cu: out = bias + product).
-int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st, long long wmax,
-                const double* bias) {
+int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st) {
     BathHost& H = c->bath[b];
     const int R = H.R, ncp = H.ncp;
     long long W = H.ml - koff;                 // lags 0 .. ml-1-koff contribute
-    if (wmax >= 0 && W > wmax) W = wmax;
     if (W > H.hcount) W = H.hcount;
     if (W > R) W = R;
     if (W <= 0) {
-        const size_t bytes = (size_t)T * H.nc * c->ldb * sizeof(double);
-        if (bias) PYMD_CUDA_CHECK(cudaMemcpyAsync(out, bias, bytes, cudaMemcpyDeviceToDevice, st));
-        else PYMD_CUDA_CHECK(cudaMemsetAsync(out, 0, bytes, st));
+        PYMD_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)T * H.nc * c->ldb * sizeof(double), st));
         return PYMD_OK;
     }
     const int h = (int)((H.hcount - 1) % R);
@@ -373,7 +366,7 @@ int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t s
         g.seg_lo[0] = 0; g.seg_hi[0] = (h + 1) * ncp; g.seg_aoff[0] = base;
         g.seg_lo[1] = (lo + R) * ncp; g.seg_hi[1] = R * ncp; g.seg_aoff[1] = base - (long long)R * ncp;
     }
-    g.alpha = c->dt; g.accumulate = 0; g.bias_base = bias;
+    g.alpha = c->dt; g.accumulate = 0;
     c->launches++;
     prof_begin(c, 0, st);
     const int rc = launch_gemm(g, st);

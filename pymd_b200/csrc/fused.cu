@@ -1,17 +1,22 @@
-// Fused on-chip step kernel (mode 2): up to FT consecutive md.vv steps (reference md.py:315-358)
-// for a tile of 8*NT trajectories per CTA, without leaving the SM.
+// Fused on-chip step kernel (mode 2): up to 32 consecutive md.vv steps (reference md.py:315-358)
+// per launch, in blocks of FT = 8, for a tile of 8*NT trajectories per CTA, without leaving the SM.
 //
 //   * The three nd x nd operators -- dyn (md.py:484), the summed k=0 bath heads
 //     Mp = sum_b scatter(alpha_b K_b[0]) (phbath.py:197-201 / ebath.py:191,194) and the q-coupled
 //     electron operator AqT (ebath.py:192-193) -- are held in REGISTERS as DMMA A-fragments: warp w
-//     owns rows 8w..8w+7, so one mat-vec round is ks DMMA.8x8x4 per 8 trajectories per warp.
+//     owns rows 8w..8w+7, so one mat-vec round is ks DMMA.8x8x4 per 8 trajectories per warp (all 16
+//     k-steps, branch-free, when nd > 48: FULLK).
 //   * State vectors (head velocity, q', half-kick, base force) live in shared memory, [64][N+4]
 //     doubles; the B-fragment read (ld % 16 == 4) and the C-fragment write are conflict free.
-//   * Memory-kernel friction: the block-Toeplitz GEMM (launch_tail, koff = 2) has already
-//     produced P[s] = dt sum_{k>=s+2} K[k] p(t0+1+s-k), the part that only needs history older
-//     than this block; the causal in-block part sum_{k=1}^{s+1} dt K[k] p(t0+1+s-k) is contracted
-//     here from an in-smem block history.  So the velocity history is read from HBM once per FT
-//     steps instead of once per step.
+//   * Memory-kernel friction on three time scales:
+//       - taps that meet the history of the current block: contracted here from an in-smem block
+//         history by the "tap" work items;
+//       - taps that meet earlier blocks of the current super-block of 32 steps: mid_phase() at
+//         every block start (mid mode), ring rows staged from HBM, taps prefetched from L2;
+//       - everything older: the far field F of far.cu (FFT convolution, one launch per super-block),
+//         added in mid_phase().
+//     Without a far field (short memories, nc > 16, PYMD_FAR=0) one launch covers one block and the
+//     block-Toeplitz GEMM (launch_tail, koff = 2) has produced the pre-block part P[s] beforehand.
 //   * The three force evaluations of a step are sequential (each head depends on the previous
 //     result): three rounds A/B/C separated by one __syncthreads each; the head buffer is
 //     double buffered so no extra barrier protects it.
@@ -29,8 +34,7 @@
 
 namespace pymd {
 
-int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st, long long wmax = -1,
-                const double* bias = nullptr);
+int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st);
 
 namespace {
 

@@ -136,11 +136,7 @@ __global__ void __launch_bounds__((WM * WN + NPROD) * 32) gemm_kernel(const Gemm
                 v.x += o.x;
                 v.y += o.y;
             }
-            if (g.bias_base) {
-                const double2 o = *reinterpret_cast<const double2*>(g.bias_base + (long long)m * g.y_ld + n);
-                v.x += o.x;
-                v.y += o.y;
-            }
+
             *dst = v;
         }
     }

@@ -31,8 +31,6 @@ struct GemmArgs {
     long long seg_aoff[2];
     double alpha;
     int accumulate;
-    // optional: Y row m = bias row m (at bias_base + m * y_ld) + alpha * A X
-    const double* bias_base;
 };
 
 // Launch on `stream`; returns a PYMD_* status.
