@@ -154,10 +154,12 @@ __device__ __forceinline__ void matvec2(const double (&a0)[MAXKS], const double 
 // Warp w owns step s = w: A fragments (dt K[w+2+a], pre-swizzled on the host) come from L2 one ring
 // row ahead of their use, the history rows are staged from the HBM ring through the free head
 // buffer, 64/ncp rows at a time, with the next stage prefetched into registers while the current
-// one is multiplied.  MT x KQ = m8 x k4 fragments of one ncp x ncp tap.
+// one is multiplied.  From the second block of a launch on, the seven newest rows p_c(t0-1 .. t0-7)
+// are still in the shared-memory block history (slots 7 .. 1) and are multiplied in place, without
+// staging or barriers.  MT x KQ = m8 x k4 fragments of one ncp x ncp tap.
 template <int NT, int MT, int KQ>
-__device__ __forceinline__ void mid_bath(const FusedParams& P, const FusedBath& B, double* stage, int nsblk, int g,
-                                         int col0) {
+__device__ __forceinline__ void mid_bath(const FusedParams& P, const FusedBath& B, double* stage, const double* hist,
+                                         int nsblk, int g, int col0) {
     constexpr int N = 8 * NT, LD = N + 4, ncp = 8 * MT, nA = MT * KQ;
     constexpr int spst = NDP / ncp;                     // ring rows per stage
     constexpr int per_slot = ncp * (N / 2);             // double2 per ring-row tile
@@ -192,15 +194,36 @@ __device__ __forceinline__ void mid_bath(const FusedParams& P, const FusedBath& 
     };
     const double* Anext = B.kmid + ((size_t)w * nA) * 32 + lane;
     double ac[nA], an[nA];
-    if (W > 0) {
-        fetch(0);
-        if (mine) {
+    const int nh = g > 0 ? min(W, FT - 1) : 0;          // rows taken from the block history
+    if (W > nh) fetch(nh);
+    if (W > 0 && mine) {
+#pragma unroll
+        for (int i = 0; i < nA; ++i) an[i] = __ldg(Anext + i * 32);
+        Anext += nA * 32;
+    }
+    // products of one ring row whose B fragments start at H
+    auto row_products = [&](const double* H, bool more) {
+#pragma unroll
+        for (int i = 0; i < nA; ++i) ac[i] = an[i];
+        if (more) {
 #pragma unroll
             for (int i = 0; i < nA; ++i) an[i] = __ldg(Anext + i * 32);
             Anext += nA * 32;
         }
-    }
-    for (int a0 = 0; a0 < W; a0 += spst) {
+#pragma unroll
+        for (int kq = 0; kq < KQ; ++kq) {
+            double bf[NT];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) bf[j] = H[(4 * kq) * LD + 8 * j];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) dmma884(acc[mt][j][0], acc[mt][j][1], ac[mt * KQ + kq], bf[j]);
+        }
+    };
+    if (mine)
+        for (int a = 0; a < nh; ++a) row_products(hist + ((FT - 1 - a) * ncp + lc) * LD + lr, a + 1 < W);
+    for (int a0 = nh; a0 < W; a0 += spst) {
         __syncthreads();                                // previous stage fully consumed
 #pragma unroll
         for (int i = 0; i < NPF; ++i) {
@@ -212,26 +235,7 @@ __device__ __forceinline__ void mid_bath(const FusedParams& P, const FusedBath& 
         if (a0 + spst < W) fetch(a0 + spst);
         if (mine) {
             const int na = min(spst, W - a0);
-            for (int sl = 0; sl < na; ++sl) {
-#pragma unroll
-                for (int i = 0; i < nA; ++i) ac[i] = an[i];
-                if (a0 + sl + 1 < W) {
-#pragma unroll
-                    for (int i = 0; i < nA; ++i) an[i] = __ldg(Anext + i * 32);
-                    Anext += nA * 32;
-                }
-                const double* H = stage + (sl * ncp + lc) * LD + lr;
-#pragma unroll
-                for (int kq = 0; kq < KQ; ++kq) {
-                    double bf[NT];
-#pragma unroll
-                    for (int j = 0; j < NT; ++j) bf[j] = H[(4 * kq) * LD + 8 * j];
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                        for (int j = 0; j < NT; ++j) dmma884(acc[mt][j][0], acc[mt][j][1], ac[mt * KQ + kq], bf[j]);
-                }
-            }
+            for (int sl = 0; sl < na; ++sl) row_products(stage + (sl * ncp + lc) * LD + lr, a0 + sl + 1 < W);
         }
     }
     if (mine) {
@@ -256,8 +260,8 @@ __device__ __forceinline__ void mid_phase(const FusedParams& P, double* sm, int 
     for (int b = 0; b < P.nbath; ++b) {
         const FusedBath& B = P.b[b];
         if (!B.nonlocal) continue;
-        if (B.ncp == 16) mid_bath<NT, 2, 4>(P, B, sm + stage_off, nsblk, g, col0);
-        else mid_bath<NT, 1, 2>(P, B, sm + stage_off, nsblk, g, col0);      // far_supported: ncp is 8 or 16
+        if (B.ncp == 16) mid_bath<NT, 2, 4>(P, B, sm + stage_off, sm + B.off_hist, nsblk, g, col0);
+        else mid_bath<NT, 1, 2>(P, B, sm + stage_off, sm + B.off_hist, nsblk, g, col0);      // far_supported: ncp is 8 or 16
     }
     __syncthreads();                                    // P visible to every warp; staging buffer free again
 }
