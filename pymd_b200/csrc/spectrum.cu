@@ -13,33 +13,48 @@ int fft_num_passes(int n);
 
 constexpr int PB = 256;
 
+// One thread per (frequency pair k / n-k, column): Z_k and Z_{n-k} are read once and give both
+// |X_k|^2 and |X_{n-k}|^2 (X_{n-k} uses the same two values with the roles exchanged).
 __global__ void __launch_bounds__(PB) power_partial_kernel(const double2* __restrict__ Z, int n, long long cols,
                                                            int ldb, int nvalid, long long c0,
                                                            const double2* __restrict__ twN,
                                                            double* __restrict__ partial, int ncb_total, int cb0) {
-    __shared__ double red[PB / 32];
-    const int k = blockIdx.x;                       // 0 .. n
+    __shared__ double red[2][PB / 32];
+    const int k = blockIdx.x;                       // 0 .. n/2; partner m = n - k
+    const int m = n - k;
     const long long col = blockIdx.y * (long long)PB + threadIdx.x;
-    double v = 0.0;
+    double vk = 0.0, vm = 0.0;
     if (col < cols && ((c0 + col) % ldb) < nvalid) {
         const double2 zk = Z[(size_t)(k % n) * cols + col];
-        const double2 zm = Z[(size_t)((n - k) % n) * cols + col];
-        const double ar = zk.x + zm.x, ai = zk.y - zm.y;      // Zk + conj(Zm)
-        const double br = zk.x - zm.x, bi = zk.y + zm.y;      // Zk - conj(Zm)
-        const double2 w = twN[k];
-        const double wr = br * w.x - bi * w.y, wi = br * w.y + bi * w.x;   // W^k (Zk - conj Zm)
-        // X = (A - i*Wb)/2 ;  -i*(wr + i wi) = wi - i wr
-        const double xr = 0.5 * (ar + wi), xi = 0.5 * (ai - wr);
-        v = xr * xr + xi * xi;
+        const double2 zm = Z[(size_t)(m % n) * cols + col];
+        {
+            const double ar = zk.x + zm.x, ai = zk.y - zm.y;      // Zk + conj(Zm)
+            const double br = zk.x - zm.x, bi = zk.y + zm.y;      // Zk - conj(Zm)
+            const double2 w = twN[k];
+            const double wr = br * w.x - bi * w.y, wi = br * w.y + bi * w.x;   // W^k (Zk - conj Zm)
+            // X = (A - i*Wb)/2 ;  -i*(wr + i wi) = wi - i wr
+            const double xr = 0.5 * (ar + wi), xi = 0.5 * (ai - wr);
+            vk = xr * xr + xi * xi;
+        }
+        {
+            const double ar = zm.x + zk.x, ai = zm.y - zk.y;      // Zm + conj(Zk)
+            const double br = zm.x - zk.x, bi = zm.y + zk.y;      // Zm - conj(Zk)
+            const double2 w = twN[m];
+            const double wr = br * w.x - bi * w.y, wi = br * w.y + bi * w.x;
+            const double xr = 0.5 * (ar + wi), xi = 0.5 * (ai - wr);
+            vm = xr * xr + xi * xi;
+        }
     }
-    v = warp_sum(v);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    vk = warp_sum(vk);
+    vm = warp_sum(vm);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = vk; red[1][threadIdx.x >> 5] = vm; }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 2) {
         double s = 0.0;
 #pragma unroll
-        for (int i = 0; i < PB / 32; ++i) s += red[i];
-        partial[(size_t)k * ncb_total + cb0 + blockIdx.y] = s;
+        for (int i = 0; i < PB / 32; ++i) s += red[threadIdx.x][i];
+        const int row = threadIdx.x == 0 ? k : m;
+        if (threadIdx.x == 0 || m != k) partial[(size_t)row * ncb_total + cb0 + blockIdx.y] = s;
     }
 }
 
@@ -105,7 +120,7 @@ int pymd_powerspec(const double* traj, int nmd, int nd, int ldb, int nvalid, dou
         double2* b = bufB;
         int rc = fft_columns(traj + c0, dst, a, b, p, st, nullptr);
         if (rc) return rc;
-        dim3 grid(half + 1, (unsigned)((cols + PB - 1) / PB));
+        dim3 grid(half / 2 + 1, (unsigned)((cols + PB - 1) / PB));
         power_partial_kernel<<<grid, PB, 0, st>>>(dst, half, cols, ldb, nvalid, c0, twN, partial, ncb_total, ch * cb_per);
         PYMD_CUDA_CHECK(cudaGetLastError());
     }
