@@ -520,31 +520,95 @@ class md(object):
                     f.write("%f     %f \n" % (arr[i, 0], arr[i, 1]))
 
     def _ckpt_name(self, j):
-        return os.path.join(self.outdir, "MD%d.npz" % j)
+        """Single trajectories checkpoint into the reference's own container, ``MD<j>.nc`` (NetCDF-3 with the
+        variables and dimensions of md.py:654-705, written with scipy); ensembles add a trailing axis that the
+        reference's schema has no dimension for and go to ``MD<j>.npz``."""
+        return os.path.join(self.outdir, ("MD%d.nc" if self.batch == 1 else "MD%d.npz") % j)
 
     def dump(self, ipie, id):
-        """Checkpoint with the reference's variable names (md.py:654-705); NetCDF is not
-        available in this image, so the container is a numpy .npz."""
+        """Checkpoint with the reference's variable names (md.py:654-705)."""
         if not self.write_files:
             return
         d = dict(power=self.power, power2=self.power2, energy=self.etot, p=self.p, q=self.q,
-                 t=N.array([self.t]), ipie=N.array([ipie]), phis=self._history(),
-                 created=N.array([time.time()]))
+                 t=N.array([self.t]), ipie=N.array([ipie]), phis=self._history())
         if self._savepq:
             d["ps"], d["qs"] = self.ps, self.qs
         for i, b in enumerate(self.baths):
             d["noise%d" % i] = b.noise
             d["cur%d" % i] = b.cur
-        tmp = self._ckpt_name(id) + ".tmp.npz"
-        N.savez(tmp, **d)
-        os.replace(tmp, self._ckpt_name(id))
+        name = self._ckpt_name(id)
+        tmp = name + ".tmp" + os.path.splitext(name)[1]
+        if self.batch == 1:
+            self._write_nc(tmp, d)
+        else:
+            d["created"] = N.array([time.time()])
+            N.savez(tmp, **d)
+        os.replace(tmp, name)
+
+    def _write_nc(self, path, d):
+        """The reference's MD<j>.nc layout: dimensions nph, one, two, mem, nmd, nnmd, n<i>; variables
+        noise<i> (nnmd, n<i>), [fhis<i> (nnmd, nph) when recorded], ps, qs, power, power2, energy, p, q, t,
+        ipie, phis, qhis (only row 0 of qhis is ever read, md.py:380), plus cur<i> (nnmd) for the restart."""
+        from scipy.io import netcdf_file
+        f = netcdf_file(path, "w")
+        try:
+            f.title = "Output from md.py"
+            f.history = "Created " + time.ctime(time.time())
+            for name, n in (("nph", self.nph), ("one", 1), ("two", 2), ("mem", max(self.ml, 1)), ("nmd", self.nmd),
+                            ("nnmd", self.nmd)):
+                f.createDimension(name, n)
+            for i, b in enumerate(self.baths):
+                f.createDimension("n%d" % i, b.nc)
+
+            def put(label, a, dims):
+                v = f.createVariable(label, "d", dims)
+                v[:] = N.asarray(a, dtype=float).reshape([f.dimensions[k] for k in dims])
+                v.units = ""
+            for i, b in enumerate(self.baths):
+                put("noise%d" % i, d["noise%d" % i], ("nnmd", "n%d" % i))
+                put("cur%d" % i, d["cur%d" % i], ("nnmd",))
+                if self.record_fhis and i in self._fhis:
+                    full = N.zeros((self.nmd, self.nph))
+                    full[:, N.asarray(b.cids)] = N.asarray(self.fhis[i]).reshape(self.nmd, -1)
+                    put("fhis%d" % i, full, ("nnmd", "nph"))
+            if "ps" in d:
+                put("ps", d["ps"], ("nnmd", "nph"))
+                put("qs", d["qs"], ("nnmd", "nph"))
+            put("power", d["power"], ("nnmd", "two"))
+            put("power2", d["power2"], ("nnmd", "two"))
+            put("energy", d["energy"], ("nnmd",))
+            put("p", d["p"], ("nph",))
+            put("q", d["q"], ("nph",))
+            put("t", [float(self.t)], ("one",))
+            put("ipie", d["ipie"], ("one",))
+            phis = N.asarray(d["phis"], dtype=float).reshape(-1, self.nph)
+            mem = N.zeros((max(self.ml, 1), self.nph))
+            mem[:min(len(phis), len(mem))] = phis[:len(mem)]
+            put("phis", mem, ("mem", "nph"))
+            qh = N.zeros_like(mem)
+            qh[0] = N.asarray(d["q"], dtype=float).ravel()
+            put("qhis", qh, ("mem", "nph"))
+        finally:
+            f.close()
+
+    @staticmethod
+    def _read_ckpt(path):
+        """npz or NetCDF-3 checkpoint -> dict of arrays (ipie and t as 1-element arrays)."""
+        if path.endswith(".npz"):
+            return N.load(path)
+        from scipy.io import netcdf_file
+        f = netcdf_file(path, "r", mmap=False)
+        try:
+            return {k: N.array(v[...], dtype=float) for k, v in f.variables.items()}
+        finally:
+            f.close()
 
     def _resume(self, j):
         """md.py:541-582: resume an unfinished segment, skip a finished one, or chain the
         state from the previous segment's checkpoint."""
         fn, fnm = self._ckpt_name(j), self._ckpt_name(j - 1)
         if self.write_files and os.path.isfile(fn):
-            d = N.load(fn)
+            d = self._read_ckpt(fn)
             ipie = int(d["ipie"][0])
             if ipie + 1 < self.npie:
                 self.p, self.q = d["p"], d["q"]
@@ -565,7 +629,7 @@ class md(object):
                 return "finished"
             raise ValueError("ipie error")
         if self.write_files and os.path.isfile(fnm):
-            d = N.load(fnm)
+            d = self._read_ckpt(fnm)
             self.p, self.q = d["p"], d["q"]
             self.t = int(d["t"][0])
             if d["phis"].shape[:2] == (self.ml, self.nph):

@@ -396,3 +396,50 @@ def test_long_run_statistics_against_the_oracle_ensemble(cuda):
     tot = cur[0] + cur[1]
     assert abs(tot.mean()) < 0.35 * abs(cur[0].mean())
     assert cur[0].mean() > 0 > cur[1].mean() and abs(cur[0].mean()) > 5.0 * dev[1][1]
+
+
+def test_single_trajectory_checkpoint_is_the_reference_netcdf_schema(cuda, tmp_path):
+    """batch = 1: md.dump writes MD<j>.nc with the reference's dimensions and variables (md.py:654-705,
+    NetCDF-3), and md.Run resumes from it."""
+    import os
+    from scipy.io import netcdf_file
+    c = dict(T.CASES["ph2"])
+
+    def fresh():
+        m, j = T.device_md(c, 1, seed=8)
+        m.write_files = True
+        m.outdir = str(tmp_path)
+        m.npie = 4
+        return m
+
+    a = fresh()
+    a.Run()
+    ref_p, ref_pow = a.p, a.power2.copy()
+    f = netcdf_file(os.path.join(tmp_path, "MD0.nc"), "r", mmap=False)
+    dims = dict(f.dimensions)
+    assert dims["nph"] == c["nd"] and dims["two"] == 2 and dims["mem"] == c["ml"] and dims["nmd"] == c["nmd"]
+    assert dims["n0"] == 3 and dims["n1"] == 3
+    want = {"noise0": ("nnmd", "n0"), "noise1": ("nnmd", "n1"), "ps": ("nnmd", "nph"), "qs": ("nnmd", "nph"),
+            "power": ("nnmd", "two"), "power2": ("nnmd", "two"), "energy": ("nnmd",), "p": ("nph",), "q": ("nph",),
+            "t": ("one",), "ipie": ("one",), "phis": ("mem", "nph"), "qhis": ("mem", "nph")}
+    for k, d in want.items():
+        assert f.variables[k].dimensions == d, k
+    assert int(f.variables["ipie"][0]) == 3 and int(f.variables["t"][0]) == c["nmd"]
+    assert np.array_equal(np.array(f.variables["p"][:]), a.p) and np.array_equal(np.array(f.variables["ps"][:]), a.ps)
+    cols = np.concatenate([np.asarray(b.cids) for b in a.baths])
+    assert np.abs(np.array(f.variables["phis"][:])[:, cols]).max() > 0    # history of the bath dofs
+    f.close()
+    for fn in os.listdir(tmp_path):
+        os.remove(os.path.join(tmp_path, fn))
+    b = fresh()
+    b.initialise(); b.ResetHis()
+    for bath in b.baths:
+        bath.gnoi()
+    b.ResetSavepq()
+    for i in range(2):
+        b.steps(b.nmd // b.npie)
+        b.dump(i, 0)
+    del b
+    r = fresh()
+    r.Run()
+    assert T.relerr(r.p, ref_p) < 1e-12 and T.relerr(r.power2, ref_pow) < 1e-12
