@@ -443,3 +443,23 @@ def test_single_trajectory_checkpoint_is_the_reference_netcdf_schema(cuda, tmp_p
     r = fresh()
     r.Run()
     assert T.relerr(r.p, ref_p) < 1e-12 and T.relerr(r.power2, ref_pow) < 1e-12
+
+
+def test_example_driver_script(cuda, tmp_path, monkeypatch):
+    """examples/synthetic_junction.py: the reference's script flow (read NetCDF inputs, build EPH.nc, three
+    baths, mdrun.Run()) end to end on the device."""
+    import importlib.util
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("synthetic_junction", os.path.join(root, "examples", "synthetic_junction.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = str(tmp_path / "run")
+    monkeypatch.setattr(sys, "argv", ["synthetic_junction.py", "--batch", "40", "--nmd", "128", "--outdir", out])
+    m = mod.main()
+    assert m.t == 128 and np.isfinite(m.p).all() and np.isfinite(m.power2).all()
+    files = set(os.listdir(out))
+    assert {"EPH.nc", "Dev.nc", "MD0.npz", "power2.300.0.run0.dat", "kappa.300.0.bath0.run0.dat"} <= files
+    e = mod.ReadNewEPHNCFile(os.path.join(out, "EPH.nc"))
+    assert e.DynMat.shape == (48, 48) and np.allclose(e.DynMat, e.DynMat.T)
