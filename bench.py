@@ -123,7 +123,7 @@ def run_reference(a):
 def workload_config(a):
     return dict(workload="cfg2 AuBZ-like junction: nd=60, electron bath nc=60 at bias 0.5 eV (5 matrices), "
                          "2 phonon baths nc=15 ml=100, 1 constraint, dt=1, nmd=%d" % a.nmd,
-                batch_per_gpu=a.batch, md_steps_per_step=PIECE, nmd=a.nmd,
+                batch_per_gpu=a.batch, md_steps_per_step=PIECE, nmd=a.nmd, savepq=False,
                 l2="inputs exceed L2: each step streams %d MB of noise rows (%.0f GB resident), 126 MB L2"
                    % (PIECE * 90 * a.batch * 8 // 2 ** 20, a.nmd * 90 * a.batch * 8 / 2 ** 30))
 
@@ -315,6 +315,35 @@ def run_ours(a):
     del m
     torch.cuda.empty_cache()
 
+    # `value` runs with trajectory saving off: ps/qs for 4096 trajectories x 2^15 steps (128 GB) do not fit
+    # beside the 90 GB of noise.  The same loop WITH the ps/qs stores of md.vv (md.py:330-333), on a shorter
+    # noise period so that the buffers fit, shows what saving costs; e2e below always saves.
+    value_savepq = None
+    if not a.no_e2e:
+        nmd_s = min(nmd, 4096)
+        ms_ = build(B, nmd_s, rank * B, True, a.seed, a.mode)
+        ms_.initialise()
+        ms_.ResetHis()
+        for b in ms_.baths:
+            b.gnoi()
+        ms_.ResetSavepq(True)
+        for _ in range(a.warmup):
+            ms_.steps(PIECE)
+        torch.cuda.synchronize()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(min(a.steps, 16)):
+            ms_.steps(PIECE)
+        s1.record()
+        torch.cuda.synchronize()
+        barrier()
+        t_s = max_over_ranks(s0.elapsed_time(s1))
+        value_savepq = dict(value=B * world * PIECE * min(a.steps, 16) / (t_s * 1e-3), nmd=nmd_s,
+                            note="same loop with savepq=True (960 B stored per trajectory-step)")
+        del ms_
+        torch.cuda.empty_cache()
+
     # ------------------------------------------------------------ end to end through the class API
     e2e = None
     if not a.no_e2e:
@@ -379,7 +408,7 @@ def run_ours(a):
         out = dict(metric="trajectory_steps_per_s", value=value, unit="trajectory-steps/s", n_gpus=world,
                    steps=a.steps, warmup=a.warmup, ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak",
                    vs_baseline=None, dtype="f64", data="synthetic", config=workload_config(a), clocks=clocks,
-                   gpu_launches=int(launches), e2e=e2e, roofline=roof, cpu_baseline=cpu,
+                   gpu_launches=int(launches), e2e=e2e, roofline=roof, cpu_baseline=cpu, value_with_savepq=value_savepq,
                    setup_s=t_setup, finite=finite, step_mode=a.mode)
         _emit(json.dumps(out))
     if world > 1:
