@@ -463,3 +463,36 @@ def test_example_driver_script(cuda, tmp_path, monkeypatch):
     assert {"EPH.nc", "Dev.nc", "MD0.npz", "power2.300.0.run0.dat", "kappa.300.0.bath0.run0.dat"} <= files
     e = mod.ReadNewEPHNCFile(os.path.join(out, "EPH.nc"))
     assert e.DynMat.shape == (48, 48) and np.allclose(e.DynMat, e.DynMat.T)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_randomized_configurations(cuda, seed):
+    """Random junction shapes around the path-selection boundaries (nd up to 63, leads of 3..18 dofs so
+    that padded sizes 8/16/24 and the nc <= 16 far-field limit are crossed, memories from below the
+    far-field minimum to several 97-row windows, with and without electron bath / constraint, odd ensemble
+    sizes, ragged steps() calls) against the oracle on two trajectories."""
+    rng = np.random.default_rng(1000 + seed)
+    nd = 3 * int(rng.integers(5, 22))
+    ncl = 3 * int(rng.integers(1, min(7, nd // 6 + 1)))
+    ncr = 3 * int(rng.integers(1, min(7, nd // 6 + 1)))
+    ml = int(rng.choice([2, 9, 23, 24, 40, 100, 101, 150, 230]))
+    eb = bool(rng.integers(0, 2))
+    c = dict(nd=nd, ncl=ncl, ncr=ncr, seed=50 + seed, dt=float(rng.choice([1.0, 4.0, 8.0])), nmd=256,
+             T=float(rng.choice([10.0, 77.0, 300.0])), dT=float(rng.choice([0.0, 20.0])), ml=ml, nw=60, hwcut=0.03,
+             ebath=eb, bias=0.3, constraint=bool(rng.integers(0, 2)), nce=(3 * int(rng.integers(1, nd // 3 + 1)) if eb else None))
+    batch = int(rng.choice([1, 2, 7, 33, 70]))
+    m, j = T.device_md(c, batch)
+    xi, r = T.draw(c, m, batch, seed=seed)
+    m.initialise(r=r)
+    m.ResetHis()
+    for b, bath in enumerate(m.baths):
+        bath.gnoi(xi=xi[0][b])
+    m.ResetSavepq()
+    left = c["nmd"]
+    while left:
+        n = min(left, int(rng.integers(1, 90)))
+        m.steps(n)
+        left -= n
+    for n in sorted({0, batch - 1}):
+        om, recs = T.run_oracle(c, j, m, xi, r, n, c["nmd"])
+        compare(m, recs[0], n, tol=3e-11)
