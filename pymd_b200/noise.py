@@ -55,6 +55,22 @@ def enoisew(wl, efric, exim, exip, bias, T, ecut, classical=False, zpmotion=True
     return _electron_cov(wl, efric, exim, exip, bias, T, ecut, classical, zpmotion)
 
 
+def _batched_eigh(amat):
+    """numpy.linalg.eigh of a stack of Hermitian matrices, the stack split over host threads (LAPACK
+    releases the GIL; every matrix is decomposed by the same routine as in one big call, so the
+    result is bit-identical to N.linalg.eigh(amat), noise.py:69,172)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    nf = amat.shape[0]
+    nt = min(os.cpu_count() or 1, 16, max(1, nf // 256))
+    if nt <= 1:
+        return N.linalg.eigh(amat)
+    bounds = N.linspace(0, nf, nt + 1).astype(int)
+    with ThreadPoolExecutor(nt) as ex:
+        parts = list(ex.map(lambda i: N.linalg.eigh(amat[bounds[i]:bounds[i + 1]]), range(nt)))
+    return N.concatenate([p[0] for p in parts]), N.concatenate([p[1] for p in parts])
+
+
 class SpectralFactors:
     """lam[f, i], U[f, :, i] (as numpy.linalg.eigh returns them) and L = U sqrt(max(lam,0))."""
 
@@ -106,7 +122,7 @@ def phonon_factors(gamma, wl, T, phcut, dt, nmd, classical=False, zpmotion=True)
     w = dw * N.arange(nf)
     amat = (delta * equ(w, phcut, T, classical, zpmotion))[:, None, None] * flinterp(w, wl, N.asarray(gamma))
     amat = 0.5 * (amat + N.conj(N.transpose(amat, (0, 2, 1))))
-    lam, vec = N.linalg.eigh(amat)
+    lam, vec = _batched_eigh(amat)
     return SpectralFactors(lam, vec)
 
 
@@ -116,7 +132,7 @@ def electron_factors(efric, exim, exip, bias, T, ecut, dt, nmd, classical=False,
     dw = 2.0 * N.pi / dt / nmd
     w = dw * N.arange(nf)
     amat = _electron_cov(w, efric, exim, exip, bias, T, ecut, classical, zpmotion, delta=dt * nmd)
-    lam, vec = N.linalg.eigh(amat)
+    lam, vec = _batched_eigh(amat)
     return SpectralFactors(lam, vec)
 
 
