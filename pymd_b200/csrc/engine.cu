@@ -8,6 +8,7 @@
 //   stage_c : third force evaluation -> p(t+1), constraints          (md.py:349-358)
 // using the identity of SURVEY.md section 8a: the three evaluations share one tail and
 // differ only in the k=0 "head"; heads of all baths are summed into one nd x nd operand.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -27,7 +28,8 @@ void pymd_set_error(const char* fmt, ...) {
 
 namespace pymd {
 
-int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st);
+int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st, long long wmax = -1,
+                int accumulate = 0);
 int fused_supported(const pymd_ctx* c);
 int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t stream);
 
@@ -306,6 +308,8 @@ int finalize(pymd_ctx* c) {
         if (H.ml > 1) {
             B.tail_cur = w; w += (size_t)kBlockT * H.nc * ldb;
             B.tail_next = w; w += (size_t)kBlockT * H.nc * ldb;
+            H.d_tailA = B.tail_cur;
+            H.d_tailB = B.tail_next;
         } else {
             B.tail_cur = B.tail_next = nullptr;
         }
@@ -340,14 +344,17 @@ static int gemm_plain(pymd_ctx* c, const double* A, int lda, int M, int K, const
 }
 
 // out[s][i][n] = dt * sum_{lag>=0} K[s + koff + lag][i][:] . ring(newest - lag)[:][n],  s < T
-int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st) {
+// wmax >= 0: only the newest wmax ring rows; accumulate: out += product.
+int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st, long long wmax, int accumulate) {
     BathHost& H = c->bath[b];
     const int R = H.R, ncp = H.ncp;
     long long W = H.ml - koff;                 // lags 0 .. ml-1-koff contribute
+    if (wmax >= 0 && W > wmax) W = wmax;
     if (W > H.hcount) W = H.hcount;
     if (W > R) W = R;
     if (W <= 0) {
-        PYMD_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)T * H.nc * c->ldb * sizeof(double), st));
+        if (!accumulate)
+            PYMD_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)T * H.nc * c->ldb * sizeof(double), st));
         return PYMD_OK;
     }
     const int h = (int)((H.hcount - 1) % R);
@@ -366,7 +373,7 @@ int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t s
         g.seg_lo[0] = 0; g.seg_hi[0] = (h + 1) * ncp; g.seg_aoff[0] = base;
         g.seg_lo[1] = (lo + R) * ncp; g.seg_hi[1] = R * ncp; g.seg_aoff[1] = base - (long long)R * ncp;
     }
-    g.alpha = c->dt; g.accumulate = 0;
+    g.alpha = c->dt; g.accumulate = accumulate;
     c->launches++;
     prof_begin(c, 0, st);
     const int rc = launch_gemm(g, st);
@@ -398,47 +405,80 @@ static int generic_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) 
             if (c->bath[b].ml > 1 && (rc = launch_tail(c, b, 1, 1, d.b[b].tail_cur, st))) return rc;
         c->tail_valid = true;
     }
-    for (int s = 0; s < nsteps; ++s) {
-        const long long t = t0 + s;
-        const int tn = (int)(t % c->nmd), tn1 = (int)((t + 1) % c->nmd);
-        Slots slots{};
-        // heads of the first force evaluation: g_b = alpha K_b[0] p_c - Aq q_c
+    // Memory-kernel tails in blocks of GT steps: the part of tail(t0+s+1) that only needs history older
+    // than the block, P[s] = dt sum_{k>=s+2} K[k] p_c(t0+s+1-k), is ONE block-Toeplitz GEMM with GT*nc
+    // rows per bath (the velocity history is read once per GT steps instead of every step); the rows that
+    // enter during the block are added per step by a small product over the s+1 newest ring rows.
+    constexpr int GT = 8;
+    for (int s0 = 0; s0 < nsteps; s0 += GT) {
+        const int T = std::min(GT, nsteps - s0);
+        double* Pblk[PYMD_MAX_BATHS] = {};
         for (int b = 0; b < c->nbath; ++b) {
             BathHost& H = c->bath[b];
-            if ((rc = gemm_plain(c, H.d_head, H.lda, H.nc, H.nc, d.p, H.d_cids, d.b[b].g, 1.0, 0, st))) return rc;
-            if (H.has_aq &&
-                (rc = gemm_plain(c, H.d_aq, H.lda, H.nc, H.nc, d.q, H.d_cids, d.b[b].g, -1.0, 1, st)))
-                return rc;
-            slots.s[b] = H.ml > 1 ? (int)(H.hcount % H.R) : 0;
+            if (H.ml <= 1) continue;
+            // the buffer that does not hold tail(t) of the step about to start
+            const bool inA = d.b[b].tail_cur >= H.d_tailA && d.b[b].tail_cur < H.d_tailA + (size_t)kBlockT * H.nc * c->ldb;
+            Pblk[b] = inA ? H.d_tailB : H.d_tailA;
+            if ((rc = launch_tail(c, b, T, 2, Pblk[b], st))) return rc;
         }
-        prof_begin(c, 3, st);
-        stage_a_kernel<<<grd, blk, 0, st>>>(d, tn, slots);
-        prof_end(c, st);
-        c->launches++;
-        for (int b = 0; b < c->nbath; ++b)
-            if (c->bath[b].ml > 1) c->bath[b].hcount++;
-        // shared tail of the 2nd/3rd evaluation and of the next step's first one
-        for (int b = 0; b < c->nbath; ++b)
-            if (c->bath[b].ml > 1 && (rc = launch_tail(c, b, 1, 1, d.b[b].tail_next, st))) return rc;
-        // potential force at q' (the only dyn product of the step when unconstrained)
-        if ((rc = gemm_plain(c, c->d_dyn, c->ldn, c->nd, c->nd, d.qn, nullptr, d.fpotn, -1.0, 0, st))) return rc;
-        for (int b = 0; b < c->nbath; ++b) {
-            BathHost& H = c->bath[b];
-            if (H.has_aq &&
-                (rc = gemm_plain(c, H.d_aq, H.lda, H.nc, H.nc, d.qn, H.d_cids, d.b[b].uq, 1.0, 0, st)))
-                return rc;
+        for (int s = s0; s < s0 + T; ++s) {
+            const long long t = t0 + s;
+            const int tn = (int)(t % c->nmd), tn1 = (int)((t + 1) % c->nmd);
+            Slots slots{};
+            // heads of the first force evaluation: g_b = alpha K_b[0] p_c - Aq q_c
+            for (int b = 0; b < c->nbath; ++b) {
+                BathHost& H = c->bath[b];
+                if ((rc = gemm_plain(c, H.d_head, H.lda, H.nc, H.nc, d.p, H.d_cids, d.b[b].g, 1.0, 0, st))) return rc;
+                if (H.has_aq &&
+                    (rc = gemm_plain(c, H.d_aq, H.lda, H.nc, H.nc, d.q, H.d_cids, d.b[b].g, -1.0, 1, st)))
+                    return rc;
+                slots.s[b] = H.ml > 1 ? (int)(H.hcount % H.R) : 0;
+            }
+            prof_begin(c, 3, st);
+            stage_a_kernel<<<grd, blk, 0, st>>>(d, tn, slots);
+            prof_end(c, st);
+            c->launches++;
+            for (int b = 0; b < c->nbath; ++b)
+                if (c->bath[b].ml > 1) c->bath[b].hcount++;
+            // shared tail of the 2nd/3rd evaluation and of the next step's first one: pre-block part
+            // plus the taps k = 1 .. s-s0+1 on the rows appended since the block began
+            for (int b = 0; b < c->nbath; ++b) {
+                if (c->bath[b].ml <= 1) continue;
+                double* row = Pblk[b] + (size_t)(s - s0) * c->bath[b].nc * c->ldb;
+                if ((rc = launch_tail(c, b, 1, 1, row, st, s - s0 + 1, 1))) return rc;
+                d.b[b].tail_next = row;
+            }
+            // potential force at q' (the only dyn product of the step when unconstrained)
+            if ((rc = gemm_plain(c, c->d_dyn, c->ldn, c->nd, c->nd, d.qn, nullptr, d.fpotn, -1.0, 0, st))) return rc;
+            for (int b = 0; b < c->nbath; ++b) {
+                BathHost& H = c->bath[b];
+                if (H.has_aq &&
+                    (rc = gemm_plain(c, H.d_aq, H.lda, H.nc, H.nc, d.qn, H.d_cids, d.b[b].uq, 1.0, 0, st)))
+                    return rc;
+            }
+            if ((rc = gemm_plain(c, c->d_mp, c->ldn, c->nd, c->nd, d.ph, nullptr, d.h, 1.0, 0, st))) return rc;
+            prof_begin(c, 3, st);
+            stage_b_kernel<<<grd, blk, 0, st>>>(d, tn1);
+            prof_end(c, st);
+            if ((rc = gemm_plain(c, c->d_mp, c->ldn, c->nd, c->nd, d.p1, nullptr, d.h, 1.0, 0, st))) return rc;
+            prof_begin(c, 3, st);
+            stage_c_kernel<<<grd, blk, 0, st>>>(d);
+            prof_end(c, st);
+            c->launches += 2;
+            if (c->ncon > 0 && (rc = compute_fpotc(c, st))) return rc;
+            for (int b = 0; b < c->nbath; ++b)
+                if (c->bath[b].ml > 1) d.b[b].tail_cur = d.b[b].tail_next;
         }
-        if ((rc = gemm_plain(c, c->d_mp, c->ldn, c->nd, c->nd, d.ph, nullptr, d.h, 1.0, 0, st))) return rc;
-        prof_begin(c, 3, st);
-        stage_b_kernel<<<grd, blk, 0, st>>>(d, tn1);
-        prof_end(c, st);
-        if ((rc = gemm_plain(c, c->d_mp, c->ldn, c->nd, c->nd, d.p1, nullptr, d.h, 1.0, 0, st))) return rc;
-        prof_begin(c, 3, st);
-        stage_c_kernel<<<grd, blk, 0, st>>>(d);
-        prof_end(c, st);
-        c->launches += 2;
-        if (c->ncon > 0 && (rc = compute_fpotc(c, st))) return rc;
-        for (int b = 0; b < c->nbath; ++b) std::swap(d.b[b].tail_cur, d.b[b].tail_next);
+    }
+    // leave tail(t) at the base of buffer A and buffer B free (the fused path uses them that way)
+    for (int b = 0; b < c->nbath; ++b) {
+        BathHost& H = c->bath[b];
+        if (H.ml <= 1) continue;
+        if (d.b[b].tail_cur != H.d_tailA)
+            PYMD_CUDA_CHECK(cudaMemcpyAsync(H.d_tailA, d.b[b].tail_cur, (size_t)H.nc * c->ldb * sizeof(double),
+                                            cudaMemcpyDeviceToDevice, st));
+        d.b[b].tail_cur = H.d_tailA;
+        d.b[b].tail_next = H.d_tailB;
     }
     PYMD_CUDA_CHECK(cudaGetLastError());
     return PYMD_OK;

@@ -34,7 +34,8 @@
 
 namespace pymd {
 
-int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st);
+int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st, long long wmax = -1,
+                int accumulate = 0);
 
 namespace {
 

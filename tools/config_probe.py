@@ -18,9 +18,12 @@ ap.add_argument("--nmd", type=int, default=256)
 ap.add_argument("--steps", type=int, default=64)
 ap.add_argument("--ebath", type=int, default=1)
 ap.add_argument("--dt", type=float, default=2.0)
+ap.add_argument("--burn", type=int, default=8, help="untimed steps before the timed window (>= ml fills the history)")
+ap.add_argument("--nce", type=int, default=0, help="electron-bath dofs (default: all)")
+ap.add_argument("--label", default="")
 a = ap.parse_args()
 ncl = a.ncl
-j = synth.synth(a.nd, max(ncl, 3), max(ncl, 3), seed=9, nc_e=a.nd if a.ebath else None)
+j = synth.synth(a.nd, max(ncl, 3), max(ncl, 3), seed=9, nc_e=(a.nce or a.nd) if a.ebath else None)
 t0 = time.time()
 m = md(a.dt, a.nmd, 300.0, axyz=j.axyz, harmonic=True, dyn=j.DynMat, savepq=False, batch=a.batch, seed=3)
 m.write_files = False
@@ -36,11 +39,11 @@ for b in m.baths:
     b.gnoi()
 torch.cuda.synchronize()
 setup = time.time() - t0
-m.steps(8)
+m.steps(a.burn)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); m.steps(a.steps); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
-print(json.dumps(dict(nd=a.nd, ncl=ncl, ml=a.ml, ebath=a.ebath, batch=a.batch, ms_per_mdstep=ms / a.steps,
+print(json.dumps(dict(label=a.label, nd=a.nd, ncl=ncl, ml=a.ml, ebath=a.ebath, batch=a.batch, ms_per_mdstep=ms / a.steps,
                       traj_steps_per_s=a.batch * a.steps / ms * 1e3, setup_s=round(setup, 1),
                       finite=bool(np.isfinite(m.p).all()))))
