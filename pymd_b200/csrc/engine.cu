@@ -32,6 +32,8 @@ int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t s
                 int accumulate = 0);
 int fused_supported(const pymd_ctx* c);
 int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t stream);
+int local_supported(const pymd_ctx* c);
+int local_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t stream);
 
 struct Slots {
     int s[PYMD_MAX_BATHS];
@@ -661,10 +663,12 @@ int pymd_step(pymd_ctx* c, long long t0, int nsteps, int mode, void* stream) {
     if (rc) return rc;
     if (nsteps == 0) return PYMD_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (mode == 0) mode = fused_supported(c) ? 2 : 1;
+    if (mode == 0) mode = (fused_supported(c) || local_supported(c)) ? 2 : 1;
     if (mode == 2) {
-        PYMD_REQUIRE(fused_supported(c), "step: the fused path does not support this configuration");
-        return fused_step(c, t0, nsteps, st);
+        // on-chip step kernels: fused.cu (nd <= 64), local.cu (64 < nd <= 96, one bath without memory)
+        if (fused_supported(c)) return fused_step(c, t0, nsteps, st);
+        PYMD_REQUIRE(local_supported(c), "step: the on-chip step kernels do not support this configuration");
+        return local_step(c, t0, nsteps, st);
     }
     return generic_step(c, t0, nsteps, st);
 }

@@ -466,6 +466,7 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
                 }
             }
         }
+        __syncthreads();                        // every warp has read q before round A overwrites it
     }
     const int gend = min(P.nsteps, g0 + FT);
     for (int g = g0; g < gend; ++g) {
@@ -957,6 +958,44 @@ int launch_nt(const FusedParams& fp, size_t smem, int grid, bool hasq, bool hasc
 
 }  // namespace
 
+// Operands shared by the on-chip step kernels (fused.cu, local.cu), built once per finalize():
+// the q-coupled electron operator scattered to nd x nd, and c, D c, AqT c for every constraint vector
+// (-D q(t+1) and AqT q(t+1) follow from the projection coefficients by linearity, without a mat-vec).
+int prepare_scattered_operands(pymd_ctx* c, int aq_bath) {
+    const bool hasq = aq_bath >= 0;
+    if (hasq && !c->d_aqT) {
+        const BathHost& H = c->bath[aq_bath];
+        std::vector<double> aqT((size_t)c->nd * c->ldn, 0.0);
+        for (int i = 0; i < H.nc; ++i)
+            for (int j = 0; j < H.nc; ++j) aqT[(size_t)H.cids[i] * c->ldn + H.cids[j]] = H.aq[(size_t)i * H.nc + j];
+        PYMD_CUDA_CHECK(cudaMalloc(&c->d_aqT, aqT.size() * sizeof(double)));
+        PYMD_CUDA_CHECK(cudaMemcpy(c->d_aqT, aqT.data(), aqT.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (c->ncon > 0 && !c->d_con3) {
+        const int nd = c->nd, nc3 = c->ncon;
+        std::vector<double> c3((size_t)3 * nc3 * nd, 0.0);
+        for (int k = 0; k < nc3; ++k)
+            for (int i = 0; i < nd; ++i) {
+                c3[(size_t)k * nd + i] = c->con[(size_t)k * nd + i];
+                double sd = 0.0;
+                for (int j = 0; j < nd; ++j) sd += c->dyn[(size_t)i * nd + j] * c->con[(size_t)k * nd + j];
+                c3[(size_t)(nc3 + k) * nd + i] = sd;
+            }
+        if (hasq) {
+            const BathHost& H = c->bath[aq_bath];
+            for (int k = 0; k < nc3; ++k)
+                for (int i = 0; i < H.nc; ++i) {
+                    double sa = 0.0;
+                    for (int j = 0; j < H.nc; ++j) sa += H.aq[(size_t)i * H.nc + j] * c->con[(size_t)k * nd + H.cids[j]];
+                    c3[(size_t)(2 * nc3 + k) * nd + H.cids[i]] = sa;
+                }
+        }
+        PYMD_CUDA_CHECK(cudaMalloc(&c->d_con3, c3.size() * sizeof(double)));
+        PYMD_CUDA_CHECK(cudaMemcpy(c->d_con3, c3.data(), c3.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return PYMD_OK;
+}
+
 int fused_supported(const pymd_ctx* c) {
     if (c->nd > NDP || c->ncon > 1 || c->nbath > FB_MAX) return 0;
     int naq = 0;
@@ -982,41 +1021,12 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
     fp.nmd = c->nmd; fp.ncon = c->ncon; fp.dt = c->dt;
     fp.p = d.p; fp.q = d.q; fp.ps = d.ps; fp.qs = d.qs; fp.etot = d.etot; fp.fpotn = d.fpotn; fp.samef = d.samef;
     fp.dyn = c->d_dyn; fp.mp = c->d_mp;
-    // q-coupled operator scattered to nd x nd (built once)
     bool hasq = fp.aq >= 0;
-    if (hasq && !c->d_aqT) {
-        const BathHost& H = c->bath[fp.aq];
-        std::vector<double> aqT((size_t)c->nd * c->ldn, 0.0);
-        for (int i = 0; i < H.nc; ++i)
-            for (int j = 0; j < H.nc; ++j) aqT[(size_t)H.cids[i] * c->ldn + H.cids[j]] = H.aq[(size_t)i * H.nc + j];
-        PYMD_CUDA_CHECK(cudaMalloc(&c->d_aqT, aqT.size() * sizeof(double)));
-        PYMD_CUDA_CHECK(cudaMemcpy(c->d_aqT, aqT.data(), aqT.size() * sizeof(double), cudaMemcpyHostToDevice));
+    {
+        int rc0 = prepare_scattered_operands(c, fp.aq);
+        if (rc0) return rc0;
     }
     fp.aqT = c->d_aqT;
-    if (c->ncon > 0 && !c->d_con3) {
-        // c, D c and AqT c for every constraint vector: -D q(t+1) and AqT q(t+1) follow from the
-        // projection coefficients by linearity, without another mat-vec
-        const int nd = c->nd, nc3 = c->ncon;
-        std::vector<double> c3((size_t)3 * nc3 * nd, 0.0);
-        for (int k = 0; k < nc3; ++k)
-            for (int i = 0; i < nd; ++i) {
-                c3[(size_t)k * nd + i] = c->con[(size_t)k * nd + i];
-                double sd = 0.0;
-                for (int j = 0; j < nd; ++j) sd += c->dyn[(size_t)i * nd + j] * c->con[(size_t)k * nd + j];
-                c3[(size_t)(nc3 + k) * nd + i] = sd;
-            }
-        if (hasq) {
-            const BathHost& H = c->bath[fp.aq];
-            for (int k = 0; k < nc3; ++k)
-                for (int i = 0; i < H.nc; ++i) {
-                    double sa = 0.0;
-                    for (int j = 0; j < H.nc; ++j) sa += H.aq[(size_t)i * H.nc + j] * c->con[(size_t)k * nd + H.cids[j]];
-                    c3[(size_t)(2 * nc3 + k) * nd + H.cids[i]] = sa;
-                }
-        }
-        PYMD_CUDA_CHECK(cudaMalloc(&c->d_con3, c3.size() * sizeof(double)));
-        PYMD_CUDA_CHECK(cudaMemcpy(c->d_con3, c3.data(), c3.size() * sizeof(double), cudaMemcpyHostToDevice));
-    }
     fp.con3 = c->d_con3;
     fp.cmax = 0.0;
     for (int i = 0; i < (c->ncon > 0 ? c->nd : 0); ++i) fp.cmax = std::max(fp.cmax, std::fabs(c->con[i]));

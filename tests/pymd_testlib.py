@@ -19,6 +19,11 @@ CASES = {
                     ebath=False, constraint=False),
     "aubz": dict(nd=60, ncl=15, ncr=15, seed=4, dt=1.0, nmd=64, T=300.0, dT=10.0, ml=100, nw=200, hwcut=0.03,
                  ebath=True, bias=0.5, constraint=True),
+    # Alkane-like (examples/Alkane.py): electron bath only, 64 < nd <= 96 -> csrc/local.cu
+    "alkane": dict(nd=72, ncl=3, ncr=3, seed=8, dt=2.0, nmd=64, T=300.0, dT=0.0, ml=1, nw=50, hwcut=0.03,
+                   ebath=True, bias=0.5, constraint=True, nce=72, leads=False),
+    "alkane_part": dict(nd=93, ncl=3, ncr=3, seed=9, dt=2.0, nmd=64, T=77.0, dT=0.0, ml=1, nw=50, hwcut=0.03,
+                        ebath=True, bias=0.0, constraint=False, nce=30, leads=False),
     "ragged": dict(nd=21, ncl=6, ncr=9, seed=5, dt=4.0, nmd=32, T=77.0, dT=5.0, ml=19, nw=50, hwcut=0.03,
                    ebath=True, bias=0.2, constraint=False, nce=12),
 }
@@ -34,6 +39,8 @@ def make_baths(mod_ph, mod_eb, j, c, **kw):
     if c["ebath"]:
         baths.append(mod_eb(j.cats_e, c["T"], c["dt"], c["nmd"], wmax=1.0, nw=500, bias=c["bias"], efric=j.efric,
                             exim=j.exim, exip=j.exip, zeta1=j.zeta1, zeta2=j.zeta2, **kw))
+    if not c.get("leads", True):
+        return baths
     pl = mod_ph(c["T"] + c["dT"] / 2, j.cats_l, c["hwcut"], c["nw"], c["dt"], c["nmd"], ml=c["ml"], sig=j.SigL,
                 gwl=j.wl, **kw)
     pr = mod_ph(c["T"] - c["dT"] / 2, j.cats_r, c["hwcut"], c["nw"], c["dt"], c["nmd"], ml=c["ml"], sig=j.SigR,

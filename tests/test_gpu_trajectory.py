@@ -496,3 +496,29 @@ def test_randomized_configurations(cuda, seed):
     for n in sorted({0, batch - 1}):
         om, recs = T.run_oracle(c, j, m, xi, r, n, c["nmd"])
         compare(m, recs[0], n, tol=3e-11)
+
+
+@pytest.mark.parametrize("case,batch,nt", [("alkane", 3, "1"), ("alkane", 40, "2"), ("alkane_part", 9, "1"), ("alkane_part", 33, "2")])
+def test_local_bath_kernel_for_nd_up_to_96(cuda, case, batch, nt, monkeypatch):
+    """csrc/local.cu: one memory-less bath (electron bath at bias with a constraint; at zero bias on a subset
+    of the dofs), 64 < nd <= 96, both trajectory tiles, ragged steps() calls, against the oracle and against
+    the per-step pipeline."""
+    monkeypatch.setenv("PYMD_FUSED_NT", nt)
+    c = T.CASES[case]
+    res = {}
+    for mode in (0, 1):
+        m, j = T.device_md(c, batch, step_mode=mode)
+        xi, r = T.draw(c, m, batch, seed=3)
+        m.initialise(r=r)
+        m.ResetHis()
+        for b, bath in enumerate(m.baths):
+            bath.gnoi(xi=xi[0][b])
+        m.ResetSavepq()
+        for n in (1, 7, 30, c["nmd"] - 38):
+            m.steps(n)
+        res[mode] = m
+    m = res[0]
+    assert T.relerr(m.ps, res[1].ps) < 1e-12 and T.relerr(m.p, res[1].p) < 1e-12
+    for n in sorted({0, batch - 1}):
+        om, recs = T.run_oracle(c, j, m, xi, r, n, c["nmd"])
+        compare(m, recs[0], n)
