@@ -250,6 +250,20 @@ int finalize(pymd_ctx* c) {
         int rc;
         if ((rc = upload(&H.d_head, head))) return rc;
         if (H.has_aq && (rc = upload(&H.d_aq, aq))) return rc;
+        {
+            // fragment-ordered copies for the warp-specialised step kernel (register-resident taps)
+            const int MT = H.ncp / 8, KQ = H.ncp / 4;
+            std::vector<double> hdf((size_t)MT * KQ * 32, 0.0), kinf((size_t)kBlockT * MT * KQ * 32, 0.0);
+            for (int i = 0; i < nc; ++i)
+                for (int j = 0; j < nc; ++j) {
+                    const size_t fo = ((size_t)(i / 8) * KQ + j / 4) * 32 + (i % 8) * 4 + j % 4;
+                    hdf[fo] = alpha * H.kernel[(size_t)i * nc + j];
+                    for (int k = 1; k <= kBlockT && k < H.ml; ++k)
+                        kinf[(size_t)(k - 1) * MT * KQ * 32 + fo] = c->dt * H.kernel[((size_t)k * nc + i) * nc + j];
+                }
+            if ((rc = upload(&H.d_hdf, hdf))) return rc;
+            if ((rc = upload(&H.d_kinf, kinf))) return rc;
+        }
         if ((rc = upload_i(&H.d_cids, H.cids))) return rc;
         if ((rc = upload_i(&H.d_inv, inv))) return rc;
         if (H.ml > 1) {
@@ -521,7 +535,7 @@ int pymd_ctx_destroy(pymd_ctx* c) {
     if (!c) return PYMD_OK;
     for (auto& H : c->bath) {
         cudaFree(H.d_cids); cudaFree(H.d_inv); cudaFree(H.d_head); cudaFree(H.d_aq);
-        cudaFree(H.d_krev); cudaFree(H.d_kintra); cudaFree(H.d_ghat); cudaFree(H.d_far); cudaFree(H.d_kmid);
+        cudaFree(H.d_krev); cudaFree(H.d_kintra); cudaFree(H.d_ghat); cudaFree(H.d_far); cudaFree(H.d_kmid); cudaFree(H.d_kinf); cudaFree(H.d_hdf);
     }
     cudaFree(c->d_dyn); cudaFree(c->d_mp); cudaFree(c->d_con); cudaFree(c->d_aqT); cudaFree(c->d_con3); cudaFree(c->ws);
     delete c;

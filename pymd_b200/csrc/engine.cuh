@@ -53,6 +53,8 @@ struct BathHost {
     double* d_kintra = nullptr;   // [kBlockT][nc][nc] dt*K[1..T] for the fused path
     double* d_ghat = nullptr;     // far.cu: transformed kernel as DMMA A fragments
     double* d_far = nullptr;      // far.cu: [kFarS][nc][ldb] far field of the current super-block
+    double* d_kinf = nullptr;     // fused2: dt K[1..kBlockT] as A fragments [k][ncp/8][ncp/4][32]
+    double* d_hdf = nullptr;      // fused2: alpha K[0] as A fragments [ncp/8][ncp/4][32]
     double* d_tailA = nullptr;    // the two [kBlockT][nc][ldb] tail buffers inside the workspace (not owned)
     double* d_tailB = nullptr;
     double* d_kmid = nullptr;     // [kMidK][ncp/8][ncp/4][32] A fragments of dt K[k], k = 2.. (fused mid field)

@@ -62,6 +62,8 @@ struct FusedBath {
     // in-kernel mid field (mid == 1): A fragments of dt K[k], k = 2..2+kMidK-1, and the far field
     const double* kmid;       // [kMidK][ncp/8][ncp/4][32]
     const double* F;          // [kFarS][nc][ldb] rows of the current super-block
+    const double* kinf;       // fused2: dt K[1..8] as A fragments [8][ncp/8][ncp/4][32]
+    const double* hdf;        // fused2: alpha K[0] as A fragments [ncp/8][ncp/4][32]
 };
 
 struct FusedParams {
@@ -76,6 +78,8 @@ struct FusedParams {
     int* samef;
     const double *dyn, *mp, *aqT, *con3;      // con3: [3][ncon][nd] = c, D c, AqT c
     int off_xp0, off_xp1, off_xq, off_curp, off_conp, off_zero, off_conv;
+    int off_opD, off_opQ;     // fused2: dyn / AqT as fragment-ordered shared-memory operands
+    int pair_b[4], pair_mt[4];    // fused2: (bath, m8 tile) owned by each bath warp, -1 = none
     double cmax;              // max_i |c_i| of the (single) constraint vector
     int smem_doubles;
     long long* timing;        // debug: [grid][8] accumulated clock64 deltas per phase (PYMD_FUSED_TIMING)
@@ -158,13 +162,13 @@ __device__ __forceinline__ void matvec2(const double (&a0)[MAXKS], const double 
 // one is multiplied.  From the second block of a launch on, the seven newest rows p_c(t0-1 .. t0-7)
 // are still in the shared-memory block history (slots 7 .. 1) and are multiplied in place, without
 // staging or barriers.  MT x KQ = m8 x k4 fragments of one ncp x ncp tap.
-template <int NT, int MT, int KQ>
+template <int NT, int MT, int KQ, int NTH>
 __device__ __forceinline__ void mid_bath(const FusedParams& P, const FusedBath& B, double* stage, const double* hist,
                                          int nsblk, int g, int col0) {
     constexpr int N = 8 * NT, LD = N + 4, ncp = 8 * MT, nA = MT * KQ;
     constexpr int spst = NDP / ncp;                     // ring rows per stage
     constexpr int per_slot = ncp * (N / 2);             // double2 per ring-row tile
-    constexpr int NPF = (spst * per_slot + FW * 32 - 1) / (FW * 32);
+    constexpr int NPF = (spst * per_slot + NTH - 1) / (NTH);
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
     const size_t ldb = P.ldb;
     const int r0b = P.r0 + g, slotb = (B.slot0 + g) % B.R;
@@ -183,7 +187,7 @@ __device__ __forceinline__ void mid_bath(const FusedParams& P, const FusedBath& 
     auto fetch = [&](int a0) {
 #pragma unroll
         for (int i = 0; i < NPF; ++i) {
-            const int e = tid + i * FW * 32;
+            const int e = tid + i * NTH;
             const int sl = e / per_slot, j = (e % per_slot) / (N / 2), c2 = e % (N / 2);
             pf[i] = make_double2(0.0, 0.0);
             if (e < spst * per_slot && a0 + sl < W) {
@@ -228,7 +232,7 @@ __device__ __forceinline__ void mid_bath(const FusedParams& P, const FusedBath& 
         __syncthreads();                                // previous stage fully consumed
 #pragma unroll
         for (int i = 0; i < NPF; ++i) {
-            const int e = tid + i * FW * 32;
+            const int e = tid + i * NTH;
             const int sl = e / per_slot, j = (e % per_slot) / (N / 2), c2 = e % (N / 2);
             if (e < spst * per_slot) *reinterpret_cast<double2*>(&stage[(sl * ncp + j) * LD + 2 * c2]) = pf[i];
         }
@@ -256,13 +260,13 @@ __device__ __forceinline__ void mid_bath(const FusedParams& P, const FusedBath& 
     }
 }
 
-template <int NT>
+template <int NT, int NTH = FW * 32>
 __device__ __forceinline__ void mid_phase(const FusedParams& P, double* sm, int stage_off, int nsblk, int g, int col0) {
     for (int b = 0; b < P.nbath; ++b) {
         const FusedBath& B = P.b[b];
         if (!B.nonlocal) continue;
-        if (B.ncp == 16) mid_bath<NT, 2, 4>(P, B, sm + stage_off, sm + B.off_hist, nsblk, g, col0);
-        else mid_bath<NT, 1, 2>(P, B, sm + stage_off, sm + B.off_hist, nsblk, g, col0);      // far_supported: ncp is 8 or 16
+        if (B.ncp == 16) mid_bath<NT, 2, 4, NTH>(P, B, sm + stage_off, sm + B.off_hist, nsblk, g, col0);
+        else mid_bath<NT, 1, 2, NTH>(P, B, sm + stage_off, sm + B.off_hist, nsblk, g, col0);      // far_supported: ncp is 8 or 16
     }
     __syncthreads();                                    // P visible to every warp; staging buffer free again
 }
@@ -856,6 +860,565 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
     for (int n = tid; n < N; n += FW * 32) P.samef[col0 + n] = 1;     // the stored force is the force at q(t)
 }
 
+// =====================================================================================================
+// fused2: warp-specialised variant of the fused step kernel for N = 32 trajectories per CTA.
+//   * 8 ROW warps run the three rounds of a step.  Only Mp lives in their registers; dyn and AqT are
+//     fragment-ordered shared-memory operands [m8 tile][k4 step][lane] (one conflict-free LDS.64 each).
+//   * 4 BATH warps each own one (bath, m8 tile) pair: the in-block taps dt K[1..8] and the head alpha K[0]
+//     of that pair are REGISTER fragments (no shared-memory tables), and while the row warps run round A
+//     they produce noise-minus-tail of the next time for their 8 bath rows and the head scalars of the
+//     currents; after the round-A barrier they sum the per-warp current / energy slots and store them.
+//   * barriers: S2 and S1 join all 12 warps; S3 and the constraint barrier are named barriers of the
+//     256 row threads only.
+// Used when every non-direct bath has ncp <= 16 and there are at most 4 (bath, m8 tile) pairs.
+constexpr int RW2 = 8, TW2 = 12, NTH2 = TW2 * 32;
+
+__device__ __forceinline__ void row_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, 384;" ::: "memory"); }
+
+template <bool HASQ, bool HASCON>
+__global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
+    constexpr int NT = 4, N = 32, LD = 36;
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+    const bool roww = w < RW2;
+    const int row = 8 * (w & 7) + lr;
+    const int col0 = blockIdx.x * N;
+    const int nd = P.nd, nb = P.nbath;
+    const size_t ldb = P.ldb;
+    const double dt = P.dt, dt2 = P.dt * P.dt;
+    const bool live = roww && row < nd;
+    const int own = row * LD + 2 * lc;
+
+    // ------------------------------------------------------------------ prologue (all warps)
+    for (int i = tid; i < P.smem_doubles; i += NTH2) sm[i] = 0.0;
+    __syncthreads();
+    for (int e = tid; e < 8 * MAXKS * 32; e += NTH2) {
+        const int mt = e / (MAXKS * 32), k = (e / 32) % MAXKS, ln = e % 32;
+        const int r = 8 * mt + (ln >> 2), cidx = 4 * k + (ln & 3);
+        const bool in = r < nd && cidx < nd;
+        sm[P.off_opD + e] = in ? P.dyn[(size_t)r * P.ldn + cidx] : 0.0;
+        if (HASQ) sm[P.off_opQ + e] = in ? P.aqT[(size_t)r * P.ldn + cidx] : 0.0;
+    }
+    for (int b = 0; b < nb; ++b) {
+        const FusedBath& B = P.b[b];
+        if (B.direct) continue;
+        int* INREM = reinterpret_cast<int*>(sm + B.off_inrem);
+        for (int i = tid; i < B.ncp; i += NTH2)
+            INREM[i] = (P.rem >= 0 && i < B.nc) ? (P.b[P.rem].inv_g[B.cids_g[i]] >= 0) : 0;
+    }
+    if (HASCON)
+        for (int e = tid; e < 3 * P.ncon * nd; e += NTH2) sm[P.off_conv + (e / nd) * NDP + e % nd] = P.con3[e];
+
+    int xpc = P.off_xp0, xpn = P.off_xp1;
+    const int xq = P.off_xq;
+    // noise minus tail at time t0 of the small baths (all threads)
+    {
+        const int tn0 = (int)(P.t0 % P.nmd);
+        for (int b = 0; b < nb; ++b) {
+            const FusedBath& B = P.b[b];
+            if (B.direct) continue;
+            double* NB = sm + B.off_nb;
+            for (int e = tid; e < B.nc * N; e += NTH2) {
+                const int r = e / N, n = e % N;
+                double v = B.noise[((size_t)tn0 * B.nc + r) * ldb + col0 + n];
+                if (B.nonlocal) v -= B.tail_cur[(size_t)r * ldb + col0 + n];
+                NB[r * LD + n] = v;
+            }
+        }
+    }
+    int nbuf = 0;
+    int tn = (int)(P.t0 % P.nmd);
+
+    if (roww) {
+    // ================================================================== ROW WARPS
+    // ---- row-warp state
+    double aM[MAXKS];
+#pragma unroll
+    for (int k = 0; k < MAXKS; ++k) aM[k] = live ? P.mp[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
+    int ip[FB_MAX], nbo[FB_MAX], nbs[FB_MAX];
+    double mrem = 0.0, maq = 0.0;
+#pragma unroll
+    for (int b = 0; b < FB_MAX; ++b) {
+        ip[b] = (b < nb && live) ? P.b[b].inv_g[row] : -1;
+        const bool memb = ip[b] >= 0 && !P.b[b].direct;
+        nbo[b] = memb ? P.b[b].off_nb + ip[b] * LD + 2 * lc : P.off_zero + 2 * lc;
+        nbs[b] = memb ? P.b[b].ncp * LD : 0;
+        if (ip[b] >= 0 && b == P.rem) mrem = 1.0;
+        if (ip[b] >= 0 && b == P.aq) maq = 1.0;
+    }
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int n = 8 * j + 2 * lc;
+            const double2 pv = ld2(&P.p[(size_t)row * ldb + col0 + n]);
+            const double2 qv = ld2(&P.q[(size_t)row * ldb + col0 + n]);
+            st2(&sm[xpc + own + 8 * j], pv.x, pv.y);
+            st2(&sm[xq + own + 8 * j], qv.x, qv.y);
+#pragma unroll
+            for (int b = 0; b < FB_MAX; ++b) {
+                if (ip[b] < 0 || P.b[b].direct) continue;
+                const FusedBath& B = P.b[b];
+                st2(&sm[B.off_hist + ip[b] * LD + n], pv.x, pv.y);
+                if (B.nonlocal) st2(&B.ring[((size_t)B.slot0 * B.ncp + ip[b]) * ldb + col0 + n], pv.x, pv.y);
+            }
+        }
+    }
+    double nzr[NT][2];
+    zero_acc<NT>(nzr);
+    for (int b = 0; b < nb; ++b) {
+        const FusedBath& B = P.b[b];
+        if (B.direct && ip[b] >= 0) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const double2 v = ld2(&B.noise[((size_t)tn * B.nc + ip[b]) * ldb + col0 + 8 * j + 2 * lc]);
+                nzr[j][0] = v.x; nzr[j][1] = v.y;
+            }
+        }
+    }
+    cta_barrier();
+    // acc += (rows of this warp of a fragment-ordered shared-memory operator) . X
+    auto smem_matvec2 = [&](const double* X, double (&a0)[NT][2], double (&a1)[NT][2]) {
+        const double* Ad = sm + P.off_opD + (w * MAXKS) * 32 + lane;
+        const double* Aq = sm + P.off_opQ + (w * MAXKS) * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < MAXKS; ++k) {
+            const double ad = Ad[k * 32];
+            const double aq = HASQ ? Aq[k * 32] : 0.0;
+            const double* xr = X + (4 * k + lc) * LD + lr;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const double bv = xr[8 * j];
+                dmma884(a0[j][0], a0[j][1], ad, bv);
+                if (HASQ) dmma884(a1[j][0], a1[j][1], aq, bv);
+            }
+        }
+    };
+
+    double fpot[NT][2], uq[NT][2], fb[NT][2];
+    zero_acc<NT>(fpot);
+    zero_acc<NT>(uq);
+    zero_acc<NT>(fb);
+    for (int g0 = 0; g0 < P.nsteps; g0 += FT) {
+        if (P.mid) mid_phase<NT, NTH2>(P, sm, P.off_xp1, min(FT, P.nsteps - g0), g0, col0);   // block starts find the head buffers in their initial roles
+        if (g0 == 0) {
+            smem_matvec2(sm + xq, fpot, uq);
+#pragma unroll
+            for (int j = 0; j < NT; ++j) { fpot[j][0] = -fpot[j][0]; fpot[j][1] = -fpot[j][1]; }
+            if (HASCON && P.carry_valid && live) {
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const int n = col0 + 8 * j + 2 * lc;
+                    if (P.samef[n]) fpot[j][0] = P.fpotn[(size_t)row * ldb + n];
+                    if (P.samef[n + 1]) fpot[j][1] = P.fpotn[(size_t)row * ldb + n + 1];
+                }
+            }
+            cta_barrier();
+        }
+        const int gend = min(P.nsteps, g0 + FT);
+        for (int g = g0; g < gend; ++g) {
+            const int s = g - g0;
+            const int tn_cur = tn;
+            const int tn1 = tn + 1 == P.nmd ? 0 : tn + 1;
+            {
+                // ============ round A: first force evaluation at time t, head p(t) ============
+                double hA[NT][2];
+                zero_acc<NT>(hA);
+                matvec1<NT, true>(aM, MAXKS, sm + xpc, LD, hA, lr, lc);
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const int n = 8 * j + 2 * lc;
+                    const double2 pv = live ? ld2(&sm[xpc + own + 8 * j]) : make_double2(0.0, 0.0);
+                    const double2 qv = ld2(&sm[xq + own + 8 * j]);
+                    double f0 = fpot[j][0] + uq[j][0] - hA[j][0];
+                    double f1 = fpot[j][1] + uq[j][1] - hA[j][1];
+                    double v[8];
+                    double c3a = 0.0, c3b = 0.0;
+                    v[0] = pv.x * pv.x;
+                    v[1] = pv.y * pv.y;
+#pragma unroll
+                    for (int b = 0; b < FB_MAX; ++b) {
+                        double2 nv = ld2(&sm[nbo[b] + nbuf * nbs[b] + 8 * j]);
+                        if (b < nb && P.b[b].direct && ip[b] >= 0) nv = make_double2(nzr[j][0], nzr[j][1]);
+                        f0 += nv.x;
+                        f1 += nv.y;
+                        double c0 = nv.x, c1 = nv.y;
+                        if (HASQ && b == P.aq) { c0 += maq * uq[j][0]; c1 += maq * uq[j][1]; }
+                        if (b == P.rem) { c0 -= mrem * hA[j][0]; c1 -= mrem * hA[j][1]; }
+                        if (b < 3) { v[2 + 2 * b] = pv.x * c0; v[3 + 2 * b] = pv.y * c1; }
+                        else { c3a = pv.x * c0; c3b = pv.y * c1; }
+                    }
+                    if (live) {
+                        st2(&sm[xpn + own + 8 * j], pv.x + f0 * dt / 2.0, pv.y + f1 * dt / 2.0);
+                        st2(&sm[xq + own + 8 * j], qv.x + pv.x * dt + f0 * dt2 / 2.0, qv.y + pv.y * dt + f1 * dt2 / 2.0);
+                        if (P.ps) st2(&P.ps[((size_t)tn_cur * nd + row) * ldb + col0 + n], pv.x, pv.y);
+                        if (P.qs) st2(&P.qs[((size_t)tn_cur * nd + row) * ldb + col0 + n], qv.x, qv.y);
+                    }
+                    const double rsum = rs8(v, lr);
+                    const int qn = lr >> 1;              // 0: kinetic energy, 1..3: bath qn-1
+                    if (qn <= nb) sm[P.off_curp + (((qn == 0) ? nb : qn - 1) * TW2 + w) * N + n + (lr & 1)] = rsum;
+                    if (nb > 3) {
+                        c3a = colsum8(c3a); c3b = colsum8(c3b);
+                        if (lr == 0) st2(&sm[P.off_curp + (3 * TW2 + w) * N + n], c3a, c3b);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < FB_MAX; ++b) {
+                    if (b < nb && P.b[b].direct && ip[b] >= 0) {
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) {
+                            const double2 vv = ld2(&P.b[b].noise[((size_t)tn1 * P.b[b].nc + ip[b]) * ldb + col0 + 8 * j + 2 * lc]);
+                            nzr[j][0] = vv.x; nzr[j][1] = vv.y;
+                        }
+                    }
+                }
+            }
+            cta_barrier();                                                      // ---- S2 (all warps)
+            nbuf ^= 1;
+            {
+                { const int tmp = xpc; xpc = xpn; xpn = tmp; }      // xpc: p(t+1/2)
+                // ============ round B: second evaluation at time t+1, head p(t+1/2) ============
+                {
+                    double aDq[NT][2], hB[NT][2];
+                    zero_acc<NT>(aDq);
+                    zero_acc<NT>(hB);
+                    zero_acc<NT>(uq);
+                    smem_matvec2(sm + xq, aDq, uq);
+                    matvec1<NT, true>(aM, MAXKS, sm + xpc, LD, hB, lr, lc);
+                    double p1v[NT][2];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        fpot[j][0] = -aDq[j][0];
+                        fpot[j][1] = -aDq[j][1];
+                        double f0 = fpot[j][0] + uq[j][0], f1 = fpot[j][1] + uq[j][1];
+#pragma unroll
+                        for (int b = 0; b < FB_MAX; ++b) {
+                            double2 nv = ld2(&sm[nbo[b] + nbuf * nbs[b] + 8 * j]);
+                            if (b < nb && P.b[b].direct && ip[b] >= 0) nv = make_double2(nzr[j][0], nzr[j][1]);
+                            f0 += nv.x;
+                            f1 += nv.y;
+                        }
+                        fb[j][0] = f0;
+                        fb[j][1] = f1;
+                        const double2 ph = ld2(&sm[xpc + own + 8 * j]);
+                        p1v[j][0] = ph.x + dt * (f0 - hB[j][0]) / 2.0;
+                        p1v[j][1] = ph.y + dt * (f1 - hB[j][1]) / 2.0;
+                    }
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) st2(&sm[xpn + own + 8 * j], p1v[j][0], p1v[j][1]);
+                    }
+                }
+                row_barrier();                                                  // ---- S3 (row warps)
+                { const int tmp = xpc; xpc = xpn; xpn = tmp; }      // xpc: p1, xpn: p(t+1/2)
+                // ============ round C: third evaluation, head p1 -> p(t+1), constraint ============
+                {
+                    double hC[NT][2];
+                    zero_acc<NT>(hC);
+                    matvec1<NT, true>(aM, MAXKS, sm + xpc, LD, hC, lr, lc);
+                    double pn[NT][2], qn[NT][2];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const double2 ph = ld2(&sm[xpn + own + 8 * j]);
+                        pn[j][0] = live ? ph.x + dt * (fb[j][0] - hC[j][0]) / 2.0 : 0.0;
+                        pn[j][1] = live ? ph.y + dt * (fb[j][1] - hC[j][1]) / 2.0 : 0.0;
+                        if (HASCON) {
+                            const double2 q0 = ld2(&sm[xq + own + 8 * j]);
+                            qn[j][0] = q0.x; qn[j][1] = q0.y;
+                        }
+                    }
+                    if (HASCON) {
+                        const double cv = sm[P.off_conv + row];
+                        const double dv = sm[P.off_conv + NDP + row];
+                        const double av = HASQ ? sm[P.off_conv + 2 * NDP + row] : 0.0;
+                        constexpr int NG = (4 * NT + 7) / 8;
+                        double tot[NG], part[NG];
+#pragma unroll
+                        for (int gg = 0; gg < NG; ++gg) {
+                            double v[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int vi = 8 * gg + i, j = vi >> 2, kind = vi & 3;       // d0, d1, g0, g1 of n-tile j
+                                v[i] = (kind < 2 ? pn[j][kind] : qn[j][kind - 2]) * cv;
+                            }
+                            part[gg] = rs8(v, lr);
+                        }
+#pragma unroll
+                        for (int gg = 0; gg < NG; ++gg) sm[P.off_conp + ((8 * gg + lr) * RW2 + w) * 4 + lc] = part[gg];
+                        row_barrier();                                          // ---- S4 (row warps)
+#pragma unroll
+                        for (int gg = 0; gg < NG; ++gg) {
+                            double sum = 0.0;
+#pragma unroll
+                            for (int ww = 0; ww < RW2; ++ww) sum += sm[P.off_conp + ((8 * gg + lr) * RW2 + ww) * 4 + lc];
+                            tot[gg] = sum;
+                        }
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) {
+                            double d[4];
+#pragma unroll
+                            for (int kind = 0; kind < 4; ++kind) {
+                                const int vi = 4 * j + kind;
+                                d[kind] = __shfl_sync(0xffffffffu, tot[vi >> 3], ((vi & 7) << 2) | lc);
+                            }
+                            pn[j][0] -= d[0] * cv;
+                            pn[j][1] -= d[1] * cv;
+                            qn[j][0] -= d[2] * cv;
+                            qn[j][1] -= d[3] * cv;
+                            if (!(fabs(d[2]) * P.cmax < 10e-10)) fpot[j][0] += d[2] * dv;
+                            if (!(fabs(d[3]) * P.cmax < 10e-10)) fpot[j][1] += d[3] * dv;
+                            if (HASQ) { uq[j][0] -= d[2] * av; uq[j][1] -= d[3] * av; }
+                        }
+                    }
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) {
+                            st2(&sm[xpn + own + 8 * j], pn[j][0], pn[j][1]);
+                            if (HASCON) st2(&sm[xq + own + 8 * j], qn[j][0], qn[j][1]);
+                        }
+#pragma unroll
+                        for (int b = 0; b < FB_MAX; ++b) {
+                            if (ip[b] < 0 || P.b[b].direct) continue;
+                            const FusedBath& B = P.b[b];
+                            if (!B.nonlocal) {
+#pragma unroll
+                                for (int j = 0; j < NT; ++j) st2(&sm[B.off_hist + ip[b] * LD + 8 * j + 2 * lc], pn[j][0], pn[j][1]);
+                            } else if (g + 1 < P.nsteps) {
+                                const int hb = B.off_hist + (((s + 1) & (FT - 1)) * B.ncp + ip[b]) * LD + 2 * lc;
+                                int slot = (B.slot0 + g + 1) % B.R;
+                                double* rp = &B.ring[((size_t)slot * B.ncp + ip[b]) * ldb + col0 + 2 * lc];
+#pragma unroll
+                                for (int j = 0; j < NT; ++j) {
+                                    st2(&sm[hb + 8 * j], pn[j][0], pn[j][1]);
+                                    st2(rp + 8 * j, pn[j][0], pn[j][1]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            cta_barrier();                                                      // ---- S1 (all warps)
+            { const int tmp = xpc; xpc = xpn; xpn = tmp; }                      // xpc: p(t+1)
+            tn = tn1;
+        }
+    }
+    // ------------------------------------------------------------------ epilogue
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int n = 8 * j + 2 * lc;
+            const double2 pv = ld2(&sm[xpc + own + 8 * j]);
+            const double2 qv = ld2(&sm[xq + own + 8 * j]);
+            st2(&P.p[(size_t)row * ldb + col0 + n], pv.x, pv.y);
+            st2(&P.q[(size_t)row * ldb + col0 + n], qv.x, qv.y);
+            st2(&P.fpotn[(size_t)row * ldb + col0 + n], fpot[j][0], fpot[j][1]);
+        }
+    }
+
+    } else {
+    // ================================================================== BATH WARPS
+    // ---- bath-warp state: the pair (bath pb, m8 tile pmt) and its tap / head fragments
+    const int pb = roww ? -1 : P.pair_b[w - RW2], pmt = roww ? 0 : P.pair_mt[w - RW2];
+    double kf[FT][4], hf[4];
+#pragma unroll
+    for (int k = 0; k < FT; ++k)
+#pragma unroll
+        for (int kq = 0; kq < 4; ++kq) kf[k][kq] = 0.0;
+#pragma unroll
+    for (int kq = 0; kq < 4; ++kq) hf[kq] = 0.0;
+    if (pb >= 0) {
+        const FusedBath& B = P.b[pb];
+        const int MT = B.ncp / 8, KQ = B.ncp / 4;
+#pragma unroll
+        for (int kq = 0; kq < 4; ++kq) {
+            if (kq < KQ) {
+                if (pb != P.rem) hf[kq] = B.hdf[((size_t)pmt * KQ + kq) * 32 + lane];
+                if (B.nonlocal) {
+#pragma unroll
+                    for (int k = 0; k < FT; ++k)
+                        if (k < B.ntap) kf[k][kq] = B.kinf[(((size_t)k * MT + pmt) * KQ + kq) * 32 + lane];
+                }
+            }
+        }
+    }
+
+    // L2 prefetch of the noise rows two steps ahead: the 128 bath threads cover the 128-byte lines of all rows
+    cta_barrier();
+    for (int g0 = 0; g0 < P.nsteps; g0 += FT) {
+        if (P.mid) mid_phase<NT, NTH2>(P, sm, P.off_xp1, min(FT, P.nsteps - g0), g0, col0);
+        if (g0 == 0) cta_barrier();
+        const int gend = min(P.nsteps, g0 + FT);
+        for (int g = g0; g < gend; ++g) {
+            const int s = g - g0;
+            const int tn_cur = tn;
+            const int tn1 = tn + 1 == P.nmd ? 0 : tn + 1;
+            {
+                const int tn2 = tn1 + 1 == P.nmd ? 0 : tn1 + 1;
+                int e = tid - RW2 * 32;
+                for (int b = 0; b < nb; ++b) {
+                    const int cnt = P.b[b].nc * 2;
+                    for (; e < cnt; e += (TW2 - RW2) * 32)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.b[b].noise + ((size_t)tn2 * P.b[b].nc + e / 2) * ldb + col0 + (e % 2) * 16));
+                    e -= cnt;
+                }
+            }
+            if (pb >= 0) {
+                // ============ bath warp: noise minus tail at time t+1 and head scalars of (pb, pmt) ============
+                const FusedBath& B = P.b[pb];
+                const int rr = pmt * 8 + lr;
+                const bool valid = rr < B.nc;
+                const int KQ = B.ncp / 4;
+                double2 xi[NT], pt[NT];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    xi[j] = make_double2(0.0, 0.0);
+                    pt[j] = make_double2(0.0, 0.0);
+                    if (valid) {
+                        xi[j] = ld2(&B.noise[((size_t)tn1 * B.nc + rr) * ldb + col0 + 8 * j + 2 * lc]);
+                        if (B.nonlocal) pt[j] = ld2(&B.P[((size_t)s * B.nc + rr) * ldb + col0 + 8 * j + 2 * lc]);
+                    }
+                }
+                double acc[NT][2], acc2[NT][2];
+                zero_acc<NT>(acc);
+                zero_acc<NT>(acc2);
+                if (B.nonlocal) {
+                    const int ntap = min(s + 1, B.ntap);
+                    const double* H0 = sm + B.off_hist + lc * LD + lr;
+#pragma unroll
+                    for (int k = 1; k <= FT; ++k) {
+                        if (k <= ntap) {
+                            const double* H = H0 + (s + 1 - k) * B.ncp * LD;        // p_c(t+1-k)
+#pragma unroll
+                            for (int kq = 0; kq < 4; ++kq) {
+                                if (kq < KQ) {
+#pragma unroll
+                                    for (int j = 0; j < NT; ++j) {
+                                        if (k & 1) dmma884(acc[j][0], acc[j][1], kf[k - 1][kq], H[(4 * kq) * LD + 8 * j]);
+                                        else dmma884(acc2[j][0], acc2[j][1], kf[k - 1][kq], H[(4 * kq) * LD + 8 * j]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const double t0v = pt[j].x + (acc[j][0] + acc2[j][0]), t1v = pt[j].y + (acc[j][1] + acc2[j][1]);
+                        st2(&sm[B.off_nb + ((nbuf ^ 1) * B.ncp + rr) * LD + 8 * j + 2 * lc], xi[j].x - t0v, xi[j].y - t1v);
+                        if (B.nonlocal && g == P.nsteps - 1)
+                            st2(&B.tail_cur[(size_t)rr * ldb + col0 + 8 * j + 2 * lc], t0v, t1v);
+                    }
+                }
+                if (pb != P.rem) {
+                    // head of a small bath: only the scalars p_c.g_b (currents) are needed
+                    const int hs = B.nonlocal ? s : 0;
+                    const int inrem = valid ? reinterpret_cast<const int*>(sm + B.off_inrem)[rr] : 0;
+                    double gh[NT][2];
+                    zero_acc<NT>(gh);
+                    const double* H = sm + B.off_hist + (hs * B.ncp + lc) * LD + lr;
+#pragma unroll
+                    for (int kq = 0; kq < 4; ++kq) {
+                        if (kq < KQ) {
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) dmma884(gh[j][0], gh[j][1], hf[kq], H[(4 * kq) * LD + 8 * j]);
+                        }
+                    }
+#pragma unroll
+                    for (int j2 = 0; j2 < NT; j2 += 2) {
+                        double v[8];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int j = j2 + h;
+                            double s0 = 0.0, s1 = 0.0;
+                            if (valid) {
+                                const double2 pv = ld2(&sm[B.off_hist + (hs * B.ncp + rr) * LD + 8 * j + 2 * lc]);
+                                s0 = pv.x * gh[j][0];
+                                s1 = pv.y * gh[j][1];
+                            }
+                            v[4 * h + 0] = s0; v[4 * h + 1] = s1;
+                            v[4 * h + 2] = inrem ? s0 : 0.0; v[4 * h + 3] = inrem ? s1 : 0.0;
+                        }
+                        const double r = rs8(v, lr);     // lane lr: n-tile j2 + (lr>>2), kind lr&3 (s0, s1, r0, r1)
+                        const int j = j2 + (lr >> 2), kind = lr & 3;
+                        // this warp's own slots: the head enters the bath's current with a minus sign and, for
+                        // dofs shared with the remainder bath, the remainder's with a plus sign
+                        if (kind < 2) sm[P.off_curp + (pb * TW2 + w) * N + 8 * j + 2 * lc + kind] = -r;
+                        else if (P.rem >= 0) sm[P.off_curp + (P.rem * TW2 + w) * N + 8 * j + 2 * lc + kind - 2] = r;
+                    }
+                }
+            }
+            cta_barrier();                                                      // ---- S2 (all warps)
+            nbuf ^= 1;
+            {
+                // currents and kinetic energy of time t: fixed-order sum of the per-warp slots
+                for (int e = tid - RW2 * 32; e < (nb + 1) * N; e += (TW2 - RW2) * 32) {
+                    const int b = e / N, n = e % N;
+                    double sum = 0.0;
+#pragma unroll
+                    for (int ww = 0; ww < TW2; ++ww) sum += sm[P.off_curp + (b * TW2 + ww) * N + n];
+                    if (b < nb) P.b[b].cur[(size_t)tn_cur * ldb + col0 + n] = sum;
+                    else P.etot[(size_t)tn_cur * ldb + col0 + n] = 0.5 * sum;
+                }
+            }
+            cta_barrier();                                                      // ---- S1 (all warps)
+            tn = tn1;
+        }
+    }
+    }
+    for (int n = tid; n < N; n += NTH2) P.samef[col0 + n] = 1;
+}
+
+// shared-memory plan of fused2; returns bytes, or a huge value when the configuration does not qualify
+size_t plan2(const pymd_ctx* c, FusedParams& fp, bool hasq) {
+    constexpr int N = 32, LD = 36;
+    int off = 0;
+    auto take = [&](int n) { int o = off; off += (n + 1) / 2 * 2; return o; };
+    fp.off_xp0 = take(NDP * LD);
+    fp.off_xp1 = take(NDP * LD);
+    fp.off_xq = take(NDP * LD);
+    fp.off_opD = take(8 * MAXKS * 32);
+    fp.off_opQ = hasq ? take(8 * MAXKS * 32) : fp.off_opD;
+    fp.off_zero = take(LD);
+    fp.off_curp = take((c->nbath + 1) * TW2 * N);
+    fp.off_conp = take(((4 * 4 + 7) / 8) * 8 * RW2 * 4);
+    fp.off_conv = take(3 * NDP);
+    int npair = 0;
+    for (int i = 0; i < 4; ++i) fp.pair_b[i] = fp.pair_mt[i] = -1;
+    for (int b = 0; b < c->nbath; ++b) {
+        const BathHost& H = c->bath[b];
+        FusedBath& B = fp.b[b];
+        B.nc = H.nc; B.ncp = H.ncp; B.ml = H.ml; B.nonlocal = H.ml > 1;
+        B.direct = (b == fp.rem && H.ml == 1) ? 1 : 0;
+        B.ldk = H.ncp + 4;
+        B.ntap = H.ml > 1 ? std::min(FT, H.ml - 1) : 0;
+        B.off_cids = B.off_inrem = B.off_hd = B.off_nb = B.off_kin = B.off_hist = 0;
+        if (B.direct) continue;
+        if (H.ncp > 16) return (size_t)1 << 40;
+        for (int mt = 0; mt < H.ncp / 8; ++mt) {
+            if (npair >= 4) return (size_t)1 << 40;
+            fp.pair_b[npair] = b; fp.pair_mt[npair] = mt; ++npair;
+        }
+        B.off_inrem = take(H.ncp / 2 + 1);
+        B.off_nb = take(2 * H.ncp * LD);
+        B.off_hist = take((H.ml > 1 ? FT : 1) * H.ncp * LD);
+    }
+    fp.smem_doubles = off;
+    return (size_t)off * sizeof(double);
+}
+
+template <bool Q, bool C>
+int launch_f2(const FusedParams& fp, size_t smem, int grid, cudaStream_t st) {
+    static bool cfg = false;
+    if (!cfg) {
+        PYMD_CUDA_CHECK(cudaFuncSetAttribute(fused2_kernel<Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        cfg = true;
+    }
+    fused2_kernel<Q, C><<<grid, NTH2, smem, st>>>(fp);
+    PYMD_CUDA_CHECK(cudaGetLastError());
+    return PYMD_OK;
+}
+
 struct Layout {
     FusedParams fp;
     size_t smem_bytes;
@@ -1036,6 +1599,16 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
         B.noise = d.b[b].noise; B.cur = d.b[b].cur; B.ring = d.b[b].ring; B.R = H.R > 0 ? H.R : 1;
         B.tail_cur = d.b[b].tail_cur; B.P = d.b[b].tail_next;
         B.head_g = H.d_head; B.lda = H.lda; B.kin_g = H.d_kintra; B.cids_g = H.d_cids; B.inv_g = H.d_inv;
+        B.kinf = H.d_kinf; B.hdf = H.d_hdf;
+    }
+    // warp-specialised variant (12 warps) when the trajectory tile is 32 and the baths qualify
+    bool use2 = NT == 4 && !(getenv("PYMD_FUSED2") && atoi(getenv("PYMD_FUSED2")) == 0);
+    size_t smem2 = 0;
+    if (use2) {
+        FusedParams t2 = fp;
+        smem2 = plan2(c, t2, hasq);
+        if (smem2 > 227 * 1024) use2 = false;
+        else fp = t2;
     }
     int rc;
     if (!c->tail_valid) {
@@ -1103,6 +1676,11 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
         fp.nsteps = ns;
         fp.carry_valid = c->fpot_valid ? 1 : 0;
         prof_begin(c, 1, st);
+        if (use2) {
+            const bool con = c->ncon > 0;
+            rc = hasq ? (con ? launch_f2<true, true>(fp, smem2, grid, st) : launch_f2<true, false>(fp, smem2, grid, st))
+                      : (con ? launch_f2<false, true>(fp, smem2, grid, st) : launch_f2<false, false>(fp, smem2, grid, st));
+        } else
         switch (NT) {
             case 4: rc = launch_nt<4>(fp, smem, grid, hasq, c->ncon > 0, st); break;
             case 2: rc = launch_nt<2>(fp, smem, grid, hasq, c->ncon > 0, st); break;
