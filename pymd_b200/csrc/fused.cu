@@ -162,7 +162,7 @@ __device__ __forceinline__ void matvec2(const double (&a0)[MAXKS], const double 
 // one is multiplied.  From the second block of a launch on, the seven newest rows p_c(t0-1 .. t0-7)
 // are still in the shared-memory block history (slots 7 .. 1) and are multiplied in place, without
 // staging or barriers.  MT x KQ = m8 x k4 fragments of one ncp x ncp tap.
-template <int NT, int MT, int KQ, int NTH>
+template <int NT, int MT, int KQ, int NTH, bool COMPUTE>
 __device__ __forceinline__ void mid_bath(const FusedParams& P, const FusedBath& B, double* stage, const double* hist,
                                          int nsblk, int g, int col0) {
     constexpr int N = 8 * NT, LD = N + 4, ncp = 8 * MT, nA = MT * KQ;
@@ -176,7 +176,7 @@ __device__ __forceinline__ void mid_bath(const FusedParams& P, const FusedBath& 
     if (Wl > P.hc0 + g) Wl = P.hc0 + g;
     if (Wl > B.ml - 2) Wl = B.ml - 2;
     const int W = (int)Wl;
-    const bool mine = w < nsblk;
+    const bool mine = COMPUTE && w < nsblk;     // COMPUTE = false: this warp only helps staging the ring rows
     double acc[MT][NT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
@@ -260,13 +260,13 @@ __device__ __forceinline__ void mid_bath(const FusedParams& P, const FusedBath& 
     }
 }
 
-template <int NT, int NTH = FW * 32>
+template <int NT, int NTH = FW * 32, bool COMPUTE = true>
 __device__ __forceinline__ void mid_phase(const FusedParams& P, double* sm, int stage_off, int nsblk, int g, int col0) {
     for (int b = 0; b < P.nbath; ++b) {
         const FusedBath& B = P.b[b];
         if (!B.nonlocal) continue;
-        if (B.ncp == 16) mid_bath<NT, 2, 4, NTH>(P, B, sm + stage_off, sm + B.off_hist, nsblk, g, col0);
-        else mid_bath<NT, 1, 2, NTH>(P, B, sm + stage_off, sm + B.off_hist, nsblk, g, col0);      // far_supported: ncp is 8 or 16
+        if (B.ncp == 16) mid_bath<NT, 2, 4, NTH, COMPUTE>(P, B, sm + stage_off, sm + B.off_hist, nsblk, g, col0);
+        else mid_bath<NT, 1, 2, NTH, COMPUTE>(P, B, sm + stage_off, sm + B.off_hist, nsblk, g, col0);      // far_supported: ncp is 8 or 16
     }
     __syncthreads();                                    // P visible to every warp; staging buffer free again
 }
@@ -964,18 +964,25 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
             }
         }
     }
-    double nzr[NT][2];
-    zero_acc<NT>(nzr);
-    for (int b = 0; b < nb; ++b) {
-        const FusedBath& B = P.b[b];
-        if (B.direct && ip[b] >= 0) {
+    // the direct (memory-less remainder) bath's noise row is read at the top of each round that needs it
+    // (prefetched into L2 two steps ahead) instead of being held in registers across rounds
+    const double* dnz = nullptr;
+    size_t dnz_stride = 0;
+    for (int b = 0; b < nb; ++b)
+        if (P.b[b].direct && ip[b] >= 0) {
+            dnz = P.b[b].noise + (size_t)ip[b] * ldb + col0 + 2 * lc;
+            dnz_stride = (size_t)P.b[b].nc * ldb;
+        }
+    auto load_direct = [&](int trow, double (&z)[NT][2]) {
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                const double2 v = ld2(&B.noise[((size_t)tn * B.nc + ip[b]) * ldb + col0 + 8 * j + 2 * lc]);
-                nzr[j][0] = v.x; nzr[j][1] = v.y;
+        for (int j = 0; j < NT; ++j) {
+            z[j][0] = z[j][1] = 0.0;
+            if (dnz) {
+                const double2 v = ld2(dnz + (size_t)trow * dnz_stride + 8 * j);
+                z[j][0] = v.x; z[j][1] = v.y;
             }
         }
-    }
+    };
     cta_barrier();
     // acc += (rows of this warp of a fragment-ordered shared-memory operator) . X
     auto smem_matvec2 = [&](const double* X, double (&a0)[NT][2], double (&a1)[NT][2]) {
@@ -1022,7 +1029,8 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
             const int tn1 = tn + 1 == P.nmd ? 0 : tn + 1;
             {
                 // ============ round A: first force evaluation at time t, head p(t) ============
-                double hA[NT][2];
+                double hA[NT][2], nzr[NT][2];
+                load_direct(tn_cur, nzr);
                 zero_acc<NT>(hA);
                 matvec1<NT, true>(aM, MAXKS, sm + xpc, LD, hA, lr, lc);
 #pragma unroll
@@ -1062,16 +1070,6 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
                         if (lr == 0) st2(&sm[P.off_curp + (3 * TW2 + w) * N + n], c3a, c3b);
                     }
                 }
-#pragma unroll
-                for (int b = 0; b < FB_MAX; ++b) {
-                    if (b < nb && P.b[b].direct && ip[b] >= 0) {
-#pragma unroll
-                        for (int j = 0; j < NT; ++j) {
-                            const double2 vv = ld2(&P.b[b].noise[((size_t)tn1 * P.b[b].nc + ip[b]) * ldb + col0 + 8 * j + 2 * lc]);
-                            nzr[j][0] = vv.x; nzr[j][1] = vv.y;
-                        }
-                    }
-                }
             }
             cta_barrier();                                                      // ---- S2 (all warps)
             nbuf ^= 1;
@@ -1079,7 +1077,8 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
                 { const int tmp = xpc; xpc = xpn; xpn = tmp; }      // xpc: p(t+1/2)
                 // ============ round B: second evaluation at time t+1, head p(t+1/2) ============
                 {
-                    double aDq[NT][2], hB[NT][2];
+                    double aDq[NT][2], hB[NT][2], nzr[NT][2];
+                    load_direct(tn1, nzr);
                     zero_acc<NT>(aDq);
                     zero_acc<NT>(hB);
                     zero_acc<NT>(uq);
@@ -1245,7 +1244,7 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
     // L2 prefetch of the noise rows two steps ahead: the 128 bath threads cover the 128-byte lines of all rows
     cta_barrier();
     for (int g0 = 0; g0 < P.nsteps; g0 += FT) {
-        if (P.mid) mid_phase<NT, NTH2>(P, sm, P.off_xp1, min(FT, P.nsteps - g0), g0, col0);
+        if (P.mid) mid_phase<NT, NTH2, false>(P, sm, P.off_xp1, min(FT, P.nsteps - g0), g0, col0);
         if (g0 == 0) cta_barrier();
         const int gend = min(P.nsteps, g0 + FT);
         for (int g = g0; g < gend; ++g) {
