@@ -176,7 +176,7 @@ __device__ __forceinline__ void mid_bath(const FusedParams& P, const FusedBath& 
     if (Wl > P.hc0 + g) Wl = P.hc0 + g;
     if (Wl > B.ml - 2) Wl = B.ml - 2;
     const int W = (int)Wl;
-    const bool mine = COMPUTE && w < nsblk;     // COMPUTE = false: this warp only helps staging the ring rows
+    const bool mine = COMPUTE && w < nsblk;     // COMPUTE = false (bath warps of fused2): this warp only keeps the barriers
     double acc[MT][NT][2];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
@@ -190,7 +190,7 @@ __device__ __forceinline__ void mid_bath(const FusedParams& P, const FusedBath& 
             const int e = tid + i * NTH;
             const int sl = e / per_slot, j = (e % per_slot) / (N / 2), c2 = e % (N / 2);
             pf[i] = make_double2(0.0, 0.0);
-            if (e < spst * per_slot && a0 + sl < W) {
+            if (COMPUTE && e < spst * per_slot && a0 + sl < W) {
                 int slot = slotb - 1 - a0 - sl;
                 if (slot < 0) slot += B.R;
                 pf[i] = __ldcg(reinterpret_cast<const double2*>(&B.ring[((size_t)slot * ncp + j) * ldb + col0 + 2 * c2]));
@@ -234,7 +234,7 @@ __device__ __forceinline__ void mid_bath(const FusedParams& P, const FusedBath& 
         for (int i = 0; i < NPF; ++i) {
             const int e = tid + i * NTH;
             const int sl = e / per_slot, j = (e % per_slot) / (N / 2), c2 = e % (N / 2);
-            if (e < spst * per_slot) *reinterpret_cast<double2*>(&stage[(sl * ncp + j) * LD + 2 * c2]) = pf[i];
+            if (COMPUTE && e < spst * per_slot) *reinterpret_cast<double2*>(&stage[(sl * ncp + j) * LD + 2 * c2]) = pf[i];
         }
         __syncthreads();
         if (a0 + spst < W) fetch(a0 + spst);
@@ -935,7 +935,7 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
     // ---- row-warp state
     double aM[MAXKS];
 #pragma unroll
-    for (int k = 0; k < MAXKS; ++k) aM[k] = live ? P.mp[(size_t)row * P.ldn + 4 * k + lc] : 0.0;
+    for (int k = 0; k < MAXKS; ++k) aM[k] = (live && 4 * k + lc < nd) ? P.mp[(size_t)row * P.ldn + 4 * k + lc] : 0.0;   // ldn may be < 64
     int ip[FB_MAX], nbo[FB_MAX], nbs[FB_MAX];
     double mrem = 0.0, maq = 0.0;
 #pragma unroll
@@ -1007,7 +1007,7 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
     zero_acc<NT>(uq);
     zero_acc<NT>(fb);
     for (int g0 = 0; g0 < P.nsteps; g0 += FT) {
-        if (P.mid) mid_phase<NT, NTH2>(P, sm, P.off_xp1, min(FT, P.nsteps - g0), g0, col0);   // block starts find the head buffers in their initial roles
+        if (P.mid) mid_phase<NT, RW2 * 32>(P, sm, P.off_xp1, min(FT, P.nsteps - g0), g0, col0);   // block starts find the head buffers in their initial roles
         if (g0 == 0) {
             smem_matvec2(sm + xq, fpot, uq);
 #pragma unroll

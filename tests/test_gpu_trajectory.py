@@ -316,12 +316,16 @@ def test_smoke_case(cuda):
     assert smoke_case.run(verbose=False) < 1e-10
 
 
+@pytest.mark.parametrize("nt", [None, "4"])
 @pytest.mark.parametrize("case,nmd,ml", [("chain39", 512, None), ("aubz", 256, None), ("chain39", 512, 250), ("ragged", 256, 120)])
-def test_far_field_fft_against_direct_product_and_oracle(cuda, case, nmd, ml, monkeypatch):
+def test_far_field_fft_against_direct_product_and_oracle(cuda, case, nmd, ml, nt, monkeypatch):
     """The FFT far field (csrc/far.cu, super-blocks of 32 steps) against the direct block-Toeplitz
     product (PYMD_FAR=0) over several full 97-entry windows, with ragged steps() calls so that
     super-blocks start at arbitrary times; and against the oracle over the whole horizon.  Memories
-    longer than 100 steps (ml = 250, 120) take several 97-row windows per super-block."""
+    longer than 100 steps (ml = 250, 120) take several 97-row windows per super-block.  nt = "4" forces the
+    32-trajectory tile, i.e. the warp-specialised kernel (fused2) where the baths qualify."""
+    if nt:
+        monkeypatch.setenv("PYMD_FUSED_NT", nt)
     c = dict(T.CASES[case]); c["nmd"] = nmd
     if ml:
         c["ml"] = ml
@@ -466,11 +470,13 @@ def test_example_driver_script(cuda, tmp_path, monkeypatch):
 
 
 @pytest.mark.parametrize("seed", range(8))
-def test_randomized_configurations(cuda, seed):
+def test_randomized_configurations(cuda, seed, monkeypatch):
     """Random junction shapes around the path-selection boundaries (nd up to 63, leads of 3..18 dofs so
     that padded sizes 8/16/24 and the nc <= 16 far-field limit are crossed, memories from below the
     far-field minimum to several 97-row windows, with and without electron bath / constraint, odd ensemble
     sizes, ragged steps() calls) against the oracle on two trajectories."""
+    if seed % 2:
+        monkeypatch.setenv("PYMD_FUSED_NT", "4")        # 32-trajectory tiles: fused2 where the baths qualify
     rng = np.random.default_rng(1000 + seed)
     nd = 3 * int(rng.integers(5, 22))
     ncl = 3 * int(rng.integers(1, min(7, nd // 6 + 1)))
