@@ -876,9 +876,9 @@ constexpr int RW2 = 8, TW2 = 12, NTH2 = TW2 * 32;
 __device__ __forceinline__ void row_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, 384;" ::: "memory"); }
 
-template <bool HASQ, bool HASCON>
+template <int NT, bool HASQ, bool HASCON>
 __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
-    constexpr int NT = 4, N = 32, LD = 36;
+    constexpr int N = 8 * NT, LD = N + 4;
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
     const bool roww = w < RW2;
@@ -1255,9 +1255,10 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
                 const int tn2 = tn1 + 1 == P.nmd ? 0 : tn1 + 1;
                 int e = tid - RW2 * 32;
                 for (int b = 0; b < nb; ++b) {
-                    const int cnt = P.b[b].nc * 2;
+                    constexpr int LPR = (N * 8 + 127) / 128;       // 128-byte lines per row tile
+                    const int cnt = P.b[b].nc * LPR;
                     for (; e < cnt; e += (TW2 - RW2) * 32)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.b[b].noise + ((size_t)tn2 * P.b[b].nc + e / 2) * ldb + col0 + (e % 2) * 16));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.b[b].noise + ((size_t)tn2 * P.b[b].nc + e / LPR) * ldb + col0 + (e % LPR) * 16));
                     e -= cnt;
                 }
             }
@@ -1369,8 +1370,8 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
 }
 
 // shared-memory plan of fused2; returns bytes, or a huge value when the configuration does not qualify
-size_t plan2(const pymd_ctx* c, FusedParams& fp, bool hasq) {
-    constexpr int N = 32, LD = 36;
+size_t plan2(const pymd_ctx* c, FusedParams& fp, bool hasq, int NT) {
+    const int N = 8 * NT, LD = N + 4;
     int off = 0;
     auto take = [&](int n) { int o = off; off += (n + 1) / 2 * 2; return o; };
     fp.off_xp0 = take(NDP * LD);
@@ -1380,7 +1381,7 @@ size_t plan2(const pymd_ctx* c, FusedParams& fp, bool hasq) {
     fp.off_opQ = hasq ? take(8 * MAXKS * 32) : fp.off_opD;
     fp.off_zero = take(LD);
     fp.off_curp = take((c->nbath + 1) * TW2 * N);
-    fp.off_conp = take(((4 * 4 + 7) / 8) * 8 * RW2 * 4);
+    fp.off_conp = take(((4 * NT + 7) / 8) * 8 * RW2 * 4);
     fp.off_conv = take(3 * NDP);
     int npair = 0;
     for (int i = 0; i < 4; ++i) fp.pair_b[i] = fp.pair_mt[i] = -1;
@@ -1406,14 +1407,14 @@ size_t plan2(const pymd_ctx* c, FusedParams& fp, bool hasq) {
     return (size_t)off * sizeof(double);
 }
 
-template <bool Q, bool C>
+template <int NT, bool Q, bool C>
 int launch_f2(const FusedParams& fp, size_t smem, int grid, cudaStream_t st) {
     static bool cfg = false;
     if (!cfg) {
-        PYMD_CUDA_CHECK(cudaFuncSetAttribute(fused2_kernel<Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        PYMD_CUDA_CHECK(cudaFuncSetAttribute(fused2_kernel<NT, Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         cfg = true;
     }
-    fused2_kernel<Q, C><<<grid, NTH2, smem, st>>>(fp);
+    fused2_kernel<NT, Q, C><<<grid, NTH2, smem, st>>>(fp);
     PYMD_CUDA_CHECK(cudaGetLastError());
     return PYMD_OK;
 }
@@ -1471,7 +1472,7 @@ int pick_nt(const pymd_ctx* c, FusedParams& fp) {
         const long long ctas = c->ldb / (8 * NT);
         const long long waves = (ctas + 147) / 148;
         const double fill = (double)ctas / (double)(waves * 148);
-        const double eff = NT == 4 ? 1.0 : (NT == 2 ? 0.75 : 0.5);
+        const double eff = NT == 4 ? 1.0 : (NT == 2 ? 0.9 : 0.5);      // measured: 16-wide tiles run the 12-warp kernel at 0.95 of the 32-wide rate
         if (fill * eff > best_score) { best_score = fill * eff; best = NT; }
     }
     if (best) plan(c, best, fp);
@@ -1601,11 +1602,11 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
         B.kinf = H.d_kinf; B.hdf = H.d_hdf;
     }
     // warp-specialised variant (12 warps) when the trajectory tile is 32 and the baths qualify
-    bool use2 = NT == 4 && !(getenv("PYMD_FUSED2") && atoi(getenv("PYMD_FUSED2")) == 0);
+    bool use2 = NT >= 2 && !(getenv("PYMD_FUSED2") && atoi(getenv("PYMD_FUSED2")) == 0);
     size_t smem2 = 0;
     if (use2) {
         FusedParams t2 = fp;
-        smem2 = plan2(c, t2, hasq);
+        smem2 = plan2(c, t2, hasq, NT);
         if (smem2 > 227 * 1024) use2 = false;
         else fp = t2;
     }
@@ -1677,8 +1678,12 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
         prof_begin(c, 1, st);
         if (use2) {
             const bool con = c->ncon > 0;
-            rc = hasq ? (con ? launch_f2<true, true>(fp, smem2, grid, st) : launch_f2<true, false>(fp, smem2, grid, st))
-                      : (con ? launch_f2<false, true>(fp, smem2, grid, st) : launch_f2<false, false>(fp, smem2, grid, st));
+            if (NT == 4)
+                rc = hasq ? (con ? launch_f2<4, true, true>(fp, smem2, grid, st) : launch_f2<4, true, false>(fp, smem2, grid, st))
+                          : (con ? launch_f2<4, false, true>(fp, smem2, grid, st) : launch_f2<4, false, false>(fp, smem2, grid, st));
+            else
+                rc = hasq ? (con ? launch_f2<2, true, true>(fp, smem2, grid, st) : launch_f2<2, true, false>(fp, smem2, grid, st))
+                          : (con ? launch_f2<2, false, true>(fp, smem2, grid, st) : launch_f2<2, false, false>(fp, smem2, grid, st));
         } else
         switch (NT) {
             case 4: rc = launch_nt<4>(fp, smem, grid, hasq, c->ncon > 0, st); break;
