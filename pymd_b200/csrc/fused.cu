@@ -876,7 +876,8 @@ constexpr int RW2 = 8, TW2 = 12, NTH2 = TW2 * 32;
 __device__ __forceinline__ void row_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, 384;" ::: "memory"); }
 
-template <int NT, bool HASQ, bool HASCON>
+// NBX: baths the per-row loops run over (3 when the junction has at most three baths, else FB_MAX)
+template <int NT, bool HASQ, bool HASCON, int NBX>
 __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
     constexpr int N = 8 * NT, LD = N + 4;
     extern __shared__ __align__(16) double sm[];
@@ -936,10 +937,10 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
     double aM[MAXKS];
 #pragma unroll
     for (int k = 0; k < MAXKS; ++k) aM[k] = (live && 4 * k + lc < nd) ? P.mp[(size_t)row * P.ldn + 4 * k + lc] : 0.0;   // ldn may be < 64
-    int ip[FB_MAX], nbo[FB_MAX], nbs[FB_MAX];
+    int ip[NBX], nbo[NBX], nbs[NBX];
     double mrem = 0.0, maq = 0.0;
 #pragma unroll
-    for (int b = 0; b < FB_MAX; ++b) {
+    for (int b = 0; b < NBX; ++b) {
         ip[b] = (b < nb && live) ? P.b[b].inv_g[row] : -1;
         const bool memb = ip[b] >= 0 && !P.b[b].direct;
         nbo[b] = memb ? P.b[b].off_nb + ip[b] * LD + 2 * lc : P.off_zero + 2 * lc;
@@ -956,7 +957,7 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
             st2(&sm[xpc + own + 8 * j], pv.x, pv.y);
             st2(&sm[xq + own + 8 * j], qv.x, qv.y);
 #pragma unroll
-            for (int b = 0; b < FB_MAX; ++b) {
+            for (int b = 0; b < NBX; ++b) {
                 if (ip[b] < 0 || P.b[b].direct) continue;
                 const FusedBath& B = P.b[b];
                 st2(&sm[B.off_hist + ip[b] * LD + n], pv.x, pv.y);
@@ -1045,7 +1046,7 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
                     v[0] = pv.x * pv.x;
                     v[1] = pv.y * pv.y;
 #pragma unroll
-                    for (int b = 0; b < FB_MAX; ++b) {
+                    for (int b = 0; b < NBX; ++b) {
                         double2 nv = ld2(&sm[nbo[b] + nbuf * nbs[b] + 8 * j]);
                         if (b < nb && P.b[b].direct && ip[b] >= 0) nv = make_double2(nzr[j][0], nzr[j][1]);
                         f0 += nv.x;
@@ -1091,7 +1092,7 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
                         fpot[j][1] = -aDq[j][1];
                         double f0 = fpot[j][0] + uq[j][0], f1 = fpot[j][1] + uq[j][1];
 #pragma unroll
-                        for (int b = 0; b < FB_MAX; ++b) {
+                        for (int b = 0; b < NBX; ++b) {
                             double2 nv = ld2(&sm[nbo[b] + nbuf * nbs[b] + 8 * j]);
                             if (b < nb && P.b[b].direct && ip[b] >= 0) nv = make_double2(nzr[j][0], nzr[j][1]);
                             f0 += nv.x;
@@ -1176,7 +1177,7 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
                             if (HASCON) st2(&sm[xq + own + 8 * j], qn[j][0], qn[j][1]);
                         }
 #pragma unroll
-                        for (int b = 0; b < FB_MAX; ++b) {
+                        for (int b = 0; b < NBX; ++b) {
                             if (ip[b] < 0 || P.b[b].direct) continue;
                             const FusedBath& B = P.b[b];
                             if (!B.nonlocal) {
@@ -1411,10 +1412,12 @@ template <int NT, bool Q, bool C>
 int launch_f2(const FusedParams& fp, size_t smem, int grid, cudaStream_t st) {
     static bool cfg = false;
     if (!cfg) {
-        PYMD_CUDA_CHECK(cudaFuncSetAttribute(fused2_kernel<NT, Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        PYMD_CUDA_CHECK(cudaFuncSetAttribute(fused2_kernel<NT, Q, C, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        PYMD_CUDA_CHECK(cudaFuncSetAttribute(fused2_kernel<NT, Q, C, FB_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         cfg = true;
     }
-    fused2_kernel<NT, Q, C><<<grid, NTH2, smem, st>>>(fp);
+    if (fp.nbath <= 3) fused2_kernel<NT, Q, C, 3><<<grid, NTH2, smem, st>>>(fp);
+    else fused2_kernel<NT, Q, C, FB_MAX><<<grid, NTH2, smem, st>>>(fp);
     PYMD_CUDA_CHECK(cudaGetLastError());
     return PYMD_OK;
 }
