@@ -153,6 +153,36 @@ size_t pymd_fft_work_bytes(int n, long long cols);
 int pymd_gemm(const double* a_dev, int lda, const double* x_dev, double* y_dev, int M, int K, int ldb,
               double alpha, int accumulate, void* stream);
 
+/* ---- set-up tables on the device ------------------------
+ * phbath.gamt (phbath.py:221-254): out[k][e] = scale * sum_i coef(tl[k], w[i]) g[i][e] with
+ * coef = 2 cos(t w) for eta_ad == 0, else the damped form
+ * exp(-eta t) [w/(w - i eta) e^{-iwt} + w/(w + i eta) e^{+iwt}].  phbath.gmem passes
+ * scale = w[nw-1]/(pi nw) and g = flinterp(w, gwl, gamma) flattened to ne = nc*nc columns; the
+ * eta_ad re-derivation of gamma (phbath.py:175-189) is the same transform with the roles of the two
+ * grids exchanged.  All pointers dev: tl[ml], w[nw], g[nw][ne], out[ml][ne]. */
+int pymd_gamt(const double* tl_dev, int ml, const double* w_dev, int nw, const double* g_dev, int ne,
+              double eta_ad, double scale, double* out_dev, void* stream);
+
+/* harmonic.Drs / DDos / UU (harmonic.py:37-84) for nw frequencies at once:
+ * D = [(w + i eta)^2 - dyn - se(w)]^-1 (n x n complex, inverted in shared memory, one CTA per
+ * frequency), ddos[f] = -2 w Tr Im D, uu[f] = Tr[D pi(w) D^dagger] (PP = w^2 uu).
+ * dev pointers: wl[nw], dyn[n][n], se and pi [nw][n][n] complex128 (interleaved re, im), ddos[nw],
+ * uu[nw]; pi and uu may both be NULL.  n <= pymd_harmonic_max_n(). */
+int pymd_harmonic_max_n(void);
+int pymd_harmonic(const double* wl_dev, int nw, const double* dyn_dev, const double* se_dev, const double* pi_dev,
+                  int n, double eta, double* ddos_dev, double* uu_dev, void* stream);
+
+/* numpy.linalg.eigh of the noise covariances (noise.py:69, 172) for nf frequencies at once, by cyclic
+ * Jacobi rotations in shared memory (one CTA per matrix).  c: dev [nf][n][n], real part and (Hermitian
+ * case; NULL for real symmetric) imaginary part.  Outputs, eigenvalues ascending as eigh orders them:
+ * lam dev [nf][n]; l = U diag(sqrt(max(lam, 0))) dev [nf][n][n] (re, im) -- the factor
+ * pymd_noise_generate consumes; u (optional, may be NULL) the eigenvectors; sweeps (optional) dev [nf]
+ * ints, Jacobi sweeps used.  Eigenvectors are defined up to a phase, so L differs from the LAPACK one
+ * by a unitary diagonal: L L^H is the same.  n <= pymd_eigh_max_n(complex?). */
+int pymd_eigh_max_n(int cplx);
+int pymd_eigh_factors(const double* cre_dev, const double* cim_dev, int nf, int n, double* lam_dev, double* lre_dev,
+                      double* lim_dev, double* ure_dev, double* uim_dev, int* sweeps_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,16 @@ class BathBase(object):
         return self._device
 
     # -- noise ------------------------------------------------------------------
+    setup_device = None        # True: decompose the noise covariance on the GPU; None: PYMD_SETUP_DEVICE decides
+    setup_keep_vectors = False  # also keep the eigenvectors of an on-device decomposition (spectral_factors().U)
+
+    def _setup_target(self):
+        """(device, strict) for the set-up tables: (None, ...) keeps the host numpy/LAPACK path, whose
+        tables are bit-identical to the reference's."""
+        if self.setup_device is None:
+            return (self._dev() if _noise.setup_on_device() else None), False
+        return (self._dev() if self.setup_device else None), True
+
     def _spectral_factors(self):
         raise NotImplementedError
 

@@ -53,8 +53,10 @@ class ebath(BathBase):
         return (self.T, self.wmax, self.dt, self.nmd, self.bias, self.classical, self.zpmotion, id(self.efric))
 
     def _spectral_factors(self):
+        dev, strict = self._setup_target()
         return _noise.electron_factors(self.efric, self.exim, self.exip, self.bias, self.T, self.wmax,
-                                       self.dt, self.nmd, self.classical, self.zpmotion)
+                                       self.dt, self.nmd, self.classical, self.zpmotion, device=dev, strict=strict,
+                                       keep_vectors=self.setup_keep_vectors)
 
     def gnoi(self, xi=None):
         """Electronic noise for every trajectory (ebath.py:132-148)."""

@@ -78,6 +78,7 @@ class SpectralFactors:
         self.lam, self.U = lam, vec
         self.L = vec * N.sqrt(N.maximum(lam, 0.0))[:, None, :]
         self.complex = N.iscomplexobj(vec)
+        self.shape = self.L.shape
         self._dev = {}                      # device -> (lre, lim): uploaded once, reused by every gnoi()
         self._host = None
 
@@ -114,26 +115,113 @@ class SpectralFactors:
         return self.lam, self.U
 
 
-def phonon_factors(gamma, wl, T, phcut, dt, nmd, classical=False, zpmotion=True):
-    """Covariance delta*equ(w_f)*gamma~(w_f), f = 0..nmd/2 (noise.py:61-66), eigh (noise.py:69)."""
+class DeviceSpectralFactors:
+    """Spectral factors decomposed on the GPU (pymd_eigh_factors, batched Jacobi): the covariances are
+    uploaded once, L stays on the device where pymd_noise_generate reads it, and lam / U / L are copied
+    to the host only when asked for.  Eigenvectors carry an arbitrary phase, so L equals the LAPACK
+    factor up to a unitary diagonal: the noise has the same covariance L L^H, not the same realisation
+    for a given xi -- use the host factors (default) to reproduce reference noise element by element."""
+
+    def __init__(self, amat, device, keep_vectors=False):
+        import torch
+        amat = N.asarray(amat)
+        nf, nc = amat.shape[0], amat.shape[1]
+        self.complex = bool(N.iscomplexobj(amat))
+        self.shape = (nf, nc, nc)
+        self.device = torch.device(device)
+        kw = dict(dtype=torch.float64, device=self.device)
+        cre = torch.as_tensor(N.ascontiguousarray(amat.real), **kw)
+        cim = torch.as_tensor(N.ascontiguousarray(amat.imag), **kw) if self.complex else None
+        self._lam = torch.empty((nf, nc), **kw)
+        self._lre = torch.empty((nf, nc, nc), **kw)
+        self._lim = torch.empty((nf, nc, nc), **kw) if self.complex else None
+        self._ure = torch.empty((nf, nc, nc), **kw) if keep_vectors else None
+        self._uim = torch.empty((nf, nc, nc), **kw) if keep_vectors and self.complex else None
+        self._sweeps = torch.empty(nf, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call("pymd_eigh_factors", cre.data_ptr(), _lib.ptr(cim), nf, nc, self._lam.data_ptr(),
+                      self._lre.data_ptr(), _lib.ptr(self._lim), _lib.ptr(self._ure), _lib.ptr(self._uim),
+                      self._sweeps.data_ptr(), _lib.stream_ptr())
+
+    @staticmethod
+    def supported(amat):
+        return amat.shape[1] <= _lib.load().pymd_eigh_max_n(1 if N.iscomplexobj(amat) else 0)
+
+    def _host(self, re, im):
+        a = re.cpu().numpy()
+        return a + 1j * im.cpu().numpy() if im is not None else a
+
+    @property
+    def lam(self):
+        return self._lam.cpu().numpy()
+
+    @property
+    def L(self):
+        return self._host(self._lre, self._lim)
+
+    @property
+    def U(self):
+        if self._ure is None:
+            raise ValueError("eigenvectors were not kept (keep_vectors=False)")
+        return self._host(self._ure, self._uim)
+
+    @property
+    def sweeps(self):
+        return self._sweeps.cpu().numpy()
+
+    def device_factors(self, dev):
+        import torch
+        if torch.device(dev) == self.device:
+            return self._lre, self._lim
+        return self._lre.to(dev), (self._lim.to(dev) if self._lim is not None else None)
+
+    def drop_device_copy(self):
+        """The factors live on the device; there is no host copy to upload again."""
+
+    def as_oracle(self):
+        return self.lam, self.U
+
+
+def setup_on_device():
+    """PYMD_SETUP_DEVICE=1: decompose the noise covariances (and build gmem tables) on the GPU."""
+    import os
+    return os.environ.get("PYMD_SETUP_DEVICE", "0") == "1"
+
+
+def _decompose(amat, device, strict=True, keep_vectors=False):
+    """``strict``: raise when the matrices do not fit the device kernel (an explicit request); otherwise
+    (PYMD_SETUP_DEVICE=1) such baths keep the LAPACK path."""
+    if device is not None and not DeviceSpectralFactors.supported(amat):
+        if strict:
+            raise ValueError("noise: nc=%d is too large for the on-device eigen-decomposition" % amat.shape[1])
+        device = None
+    if device is not None:
+        return DeviceSpectralFactors(amat, device, keep_vectors)
+    lam, vec = _batched_eigh(amat)
+    return SpectralFactors(lam, vec)
+
+
+def phonon_factors(gamma, wl, T, phcut, dt, nmd, classical=False, zpmotion=True, device=None, strict=True,
+                   keep_vectors=False):
+    """Covariance delta*equ(w_f)*gamma~(w_f), f = 0..nmd/2 (noise.py:61-66), eigh (noise.py:69);
+    ``device``: decompose on that GPU instead of LAPACK."""
     nf = int(nmd / 2) + 1
     dw = 2.0 * N.pi / dt / nmd
     delta = dt * nmd
     w = dw * N.arange(nf)
     amat = (delta * equ(w, phcut, T, classical, zpmotion))[:, None, None] * flinterp(w, wl, N.asarray(gamma))
     amat = 0.5 * (amat + N.conj(N.transpose(amat, (0, 2, 1))))
-    lam, vec = _batched_eigh(amat)
-    return SpectralFactors(lam, vec)
+    return _decompose(amat, device, strict, keep_vectors)
 
 
-def electron_factors(efric, exim, exip, bias, T, ecut, dt, nmd, classical=False, zpmotion=True):
+def electron_factors(efric, exim, exip, bias, T, ecut, dt, nmd, classical=False, zpmotion=True, device=None,
+                     strict=True, keep_vectors=False):
     """Bias-dependent Hermitian covariance (noise.py:156-170), eigh (noise.py:172)."""
     nf = int(nmd / 2) + 1
     dw = 2.0 * N.pi / dt / nmd
     w = dw * N.arange(nf)
     amat = _electron_cov(w, efric, exim, exip, bias, T, ecut, classical, zpmotion, delta=dt * nmd)
-    lam, vec = _batched_eigh(amat)
-    return SpectralFactors(lam, vec)
+    return _decompose(amat, device, strict, keep_vectors)
 
 
 # ------------------------------------------------------------------ device pipeline
@@ -169,7 +257,7 @@ def generate(factors, xi, dt, nmd, out=None):
     """noise[t][i][traj] on the device from spectral factors and white noise xi [nf][nc][ldb]."""
     import torch
     nf, nc, ldb = xi.shape
-    if nf != int(nmd / 2) + 1 or factors.L.shape != (nf, nc, nc):
+    if nf != int(nmd / 2) + 1 or tuple(factors.shape) != (nf, nc, nc):
         raise ValueError("noise.generate: shape mismatch")
     dev = xi.device
     lre, lim = factors.device_factors(dev)

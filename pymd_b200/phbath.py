@@ -1,11 +1,14 @@
 """Phonon bath with the reference's class interface (phbath.py:9-202).
 
 Setup tables (gamma(w), the friction kernel K(t_k)) are computed on the host with the
-reference's formulas; noise generation and the memory-kernel friction inside the time loop
-run on the GPU for the whole ensemble.
+reference's formulas by default (bit-identical tables); ``gmem(device=True)`` or the
+environment variable PYMD_SETUP_DEVICE=1 runs the cosine transform on the GPU
+(csrc/setup.cu) for long kernels.  Noise generation and the memory-kernel friction inside
+the time loop run on the GPU for the whole ensemble.
 """
 import numpy as N
 
+from . import _lib
 from . import noise as _noise
 from ._bathbase import BathBase
 from .functions import flinterp
@@ -80,30 +83,41 @@ class phbath(BathBase):
         src = N.where(wl == 0, N.arange(len(wl)) + 1, N.arange(len(wl)))
         self.gamma = -N.imag(sig[src]) / wl[src][:, None, None]
 
-    def gmem(self):
-        """Friction kernel in time, K[k] = Re gamt(k dt) (phbath.py:161-190)."""
+    def gmem(self, device=None):
+        """Friction kernel in time, K[k] = Re gamt(k dt) (phbath.py:161-190).  ``device``: run the
+        cosine transform in libpymd_b200 (None: only when PYMD_SETUP_DEVICE=1)."""
         if self.ml is None or self.dt is None:
             raise ValueError("phbath.gmem: length of memory kernel not set!")
         if self.local:
             self.ml = 1
             self.kernel = N.asarray(self.gamma)
             return
+        if device is None:
+            device = self.setup_device if self.setup_device is not None else _noise.setup_on_device()
         tl = N.array([self.dt * i for i in range(self.ml)])
-        self.kernel = N.real(gamt(tl, self.wl, self.gwl, self.gamma, self.eta_ad))
+        gw = N.asarray(self.gwl, dtype=float)
+        if device:
+            self.kernel = gamt_device(tl, self.wl, self.gwl, self.gamma, self.eta_ad, self._dev())
+        else:
+            self.kernel = N.real(gamt(tl, self.wl, self.gwl, self.gamma, self.eta_ad))
         if self.eta_ad != 0:
             # gamma re-derived from the damped kernel: dt sum_t K(t) cos(w t)   (phbath.py:175-189)
-            gw = N.asarray(self.gwl, dtype=float)
-            cosm = N.cos(gw[:, None] * tl[None, :])
             self.gammaOld = self.gamma
-            self.gamma = N.real(self.dt * N.tensordot(cosm, self.kernel, axes=(1, 0)))
+            if device:
+                self.gamma = cosine_transform_device(gw, tl, self.kernel, 0.0, 0.5 * self.dt, self._dev())
+            else:
+                cosm = N.cos(gw[:, None] * tl[None, :])
+                self.gamma = N.real(self.dt * N.tensordot(cosm, self.kernel, axes=(1, 0)))
             self._factors = None
 
     def _factor_key(self):
         return (self.T, self.wmax, self.dt, self.nmd, self.classical, self.zpmotion, id(self.gamma))
 
     def _spectral_factors(self):
+        dev, strict = self._setup_target()
         return _noise.phonon_factors(self.gamma, self.gwl, self.T, self.wmax, self.dt, self.nmd,
-                                     self.classical, self.zpmotion)
+                                     self.classical, self.zpmotion, device=dev, strict=strict,
+                                     keep_vectors=self.setup_keep_vectors)
 
     def gnoi(self, xi=None):
         """Regenerate the coloured noise for every trajectory (phbath.py:146-158); ``xi``
@@ -145,3 +159,27 @@ def gamt(tl, wl, gwl, gam, eta_ad=0):
     dec = N.exp(-eta_ad * tl)[:, None]
     c = fm[None, :] * N.exp(-1j * ph) * dec + fp[None, :] * N.exp(+1j * ph) * dec
     return N.real(N.tensordot(c, g, axes=(1, 0)) / nw * w[-1] / N.pi)
+
+
+def cosine_transform_device(tl, w, g, eta_ad, scale, device):
+    """out[k] = scale sum_i coef(tl[k], w[i]) g[i] on the GPU (pymd_gamt); g is (len(w), ...) real,
+    coef = 2 cos(t w) or its damped form.  Returns a host array of shape (len(tl),) + g.shape[1:]."""
+    import torch
+    g = N.ascontiguousarray(N.real(g), dtype=float)
+    ne = int(N.prod(g.shape[1:])) if g.ndim > 1 else 1
+    tl_d = torch.as_tensor(N.ascontiguousarray(tl, dtype=float), device=device)
+    w_d = torch.as_tensor(N.ascontiguousarray(w, dtype=float), device=device)
+    g_d = torch.as_tensor(g.reshape(len(w), ne), device=device)
+    out = torch.empty((len(tl), ne), dtype=torch.float64, device=device)
+    with torch.cuda.device(device):
+        _lib.call("pymd_gamt", _lib.ptr(tl_d), len(tl), _lib.ptr(w_d), len(w), _lib.ptr(g_d), ne,
+                  float(eta_ad), float(scale), _lib.ptr(out), _lib.stream_ptr())
+    return out.cpu().numpy().reshape((len(tl),) + g.shape[1:])
+
+
+def gamt_device(tl, wl, gwl, gam, eta_ad, device):
+    """gamt() with the [ml x nw] x [nw x nc^2] product on the GPU; the interpolated table
+    gamma~(w_i) is still the reference's flinterp, evaluated on the host."""
+    w = N.asarray(wl, dtype=float)
+    g = flinterp(w, gwl, N.asarray(gam))
+    return cosine_transform_device(tl, w, g, eta_ad, w[-1] / N.pi / len(w), device)
