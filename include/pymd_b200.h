@@ -178,10 +178,16 @@ int pymd_harmonic(const double* wl_dev, int nw, const double* dyn_dev, const dou
  * lam dev [nf][n]; l = U diag(sqrt(max(lam, 0))) dev [nf][n][n] (re, im) -- the factor
  * pymd_noise_generate consumes; u (optional, may be NULL) the eigenvectors; sweeps (optional) dev [nf]
  * ints, Jacobi sweeps used.  Eigenvectors are defined up to a phase, so L differs from the LAPACK one
- * by a unitary diagonal: L L^H is the same.  n <= pymd_eigh_max_n(complex?). */
+ * by a unitary diagonal: L L^H is the same.  n <= pymd_eigh_max_n(complex?).
+ * With ncomb > 0 the matrices are not passed but assembled in the kernel from a small table:
+ * c is then dev [ntab][n][n] and C_f = herm(sum_{m<ncomb} coef[f][m] * c[idx[f][m]]), herm(M) = (M + M^H)/2,
+ * idx dev [nf][ncomb] int32, coef dev [nf][ncomb] -- three fixed matrices with frequency-dependent weights
+ * for the electron bath (noise.py:156-170), two neighbouring gamma-table entries with the flinterp weights
+ * for a phonon bath (noise.py:61-66).  ncomb == 0: idx and coef are ignored (may be NULL). */
 int pymd_eigh_max_n(int cplx);
-int pymd_eigh_factors(const double* cre_dev, const double* cim_dev, int nf, int n, double* lam_dev, double* lre_dev,
-                      double* lim_dev, double* ure_dev, double* uim_dev, int* sweeps_dev, void* stream);
+int pymd_eigh_factors(const double* cre_dev, const double* cim_dev, const int* idx_dev, const double* coef_dev, int ncomb,
+                      int nf, int n, double* lam_dev, double* lre_dev, double* lim_dev, double* ure_dev, double* uim_dev,
+                      int* sweeps_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -291,9 +291,15 @@ size_t eigh_smem(int n) {
            (size_t)n * (sizeof(double) + sizeof(int)) + (ET + 2) * sizeof(double) + 64;
 }
 
+// Input: either the matrices themselves (ncomb == 0: cre/cim are [nf][n][n]) or, to avoid building and
+// uploading them, a linear combination of a small table of matrices (cre/cim are [ntab][n][n]):
+//   C_f = herm( sum_{m < ncomb} coef[f][m] * table[idx[f][m]] ),  herm(M) = (M + M^H) / 2
+// -- the electron covariance is three fixed matrices with frequency-dependent weights (noise.py:156-170),
+// the phonon one two neighbouring entries of the gamma table with the flinterp weights (noise.py:61-66).
 template <typename E>
-__global__ void __launch_bounds__(ET) eigh_kernel(const double* __restrict__ cre, const double* __restrict__ cim, int nf,
-                                                  int n, double* __restrict__ lam, double* __restrict__ lre,
+__global__ void __launch_bounds__(ET) eigh_kernel(const double* __restrict__ cre, const double* __restrict__ cim,
+                                                  const int* __restrict__ idx, const double* __restrict__ coef, int ncomb,
+                                                  int nf, int n, double* __restrict__ lam, double* __restrict__ lre,
                                                   double* __restrict__ lim, double* __restrict__ ure,
                                                   double* __restrict__ uim, int* __restrict__ sweeps) {
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -313,7 +319,18 @@ __global__ void __launch_bounds__(ET) eigh_kernel(const double* __restrict__ cre
         const size_t base = (size_t)f * n * n;
         for (int e = tid; e < n * n; e += ET) {
             const int i = e / n, j = e % n;
-            e_make(A[i * ld + j], cre[base + e], CPLX ? cim[base + e] : 0.0);
+            if (ncomb == 0) {
+                e_make(A[i * ld + j], cre[base + e], CPLX ? cim[base + e] : 0.0);
+            } else {
+                double re = 0.0, im = 0.0;
+                for (int m = 0; m < ncomb; ++m) {
+                    const double cf = 0.5 * coef[(size_t)f * ncomb + m];
+                    const size_t tb = (size_t)idx[(size_t)f * ncomb + m] * n * n;
+                    re += cf * (cre[tb + e] + cre[tb + (size_t)j * n + i]);
+                    if (CPLX) im += cf * (cim[tb + e] - cim[tb + (size_t)j * n + i]);
+                }
+                e_make(A[i * ld + j], re, im);
+            }
             e_make(V[i * ld + j], i == j ? 1.0 : 0.0, 0.0);
         }
         __syncthreads();
@@ -412,8 +429,8 @@ __global__ void __launch_bounds__(ET) eigh_kernel(const double* __restrict__ cre
 }
 
 template <typename E>
-int eigh_launch(const double* cre, const double* cim, int nf, int n, double* lam, double* lre, double* lim, double* ure,
-                double* uim, int* sweeps, cudaStream_t st) {
+int eigh_launch(const double* cre, const double* cim, const int* idx, const double* coef, int ncomb, int nf, int n,
+                double* lam, double* lre, double* lim, double* ure, double* uim, int* sweeps, cudaStream_t st) {
     const size_t smem = eigh_smem<E>(n);
     PYMD_CUDA_CHECK(cudaFuncSetAttribute(eigh_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
@@ -422,7 +439,7 @@ int eigh_launch(const double* cre, const double* cim, int nf, int n, double* lam
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
     const int grid = nf < sms * per_sm ? nf : sms * per_sm;
-    eigh_kernel<E><<<grid, ET, smem, st>>>(cre, cim, nf, n, lam, lre, lim, ure, uim, sweeps);
+    eigh_kernel<E><<<grid, ET, smem, st>>>(cre, cim, idx, coef, ncomb, nf, n, lam, lre, lim, ure, uim, sweeps);
     PYMD_CUDA_CHECK(cudaGetLastError());
     return PYMD_OK;
 }
@@ -438,18 +455,23 @@ int pymd_eigh_max_n(int cplx) {
     return n;
 }
 
-int pymd_eigh_factors(const double* cre_dev, const double* cim_dev, int nf, int n, double* lam_dev, double* lre_dev,
-                      double* lim_dev, double* ure_dev, double* uim_dev, int* sweeps_dev, void* stream) {
+int pymd_eigh_factors(const double* cre_dev, const double* cim_dev, const int* idx_dev, const double* coef_dev, int ncomb,
+                      int nf, int n, double* lam_dev, double* lre_dev, double* lim_dev, double* ure_dev, double* uim_dev,
+                      int* sweeps_dev, void* stream) {
     using namespace pymd;
     PYMD_REQUIRE(cre_dev && lam_dev && lre_dev, "eigh_factors: null pointer");
     PYMD_REQUIRE(nf > 0 && n > 0, "eigh_factors: bad shape nf=%d n=%d", nf, n);
+    PYMD_REQUIRE(ncomb >= 0 && (ncomb == 0 || (idx_dev && coef_dev)), "eigh_factors: a combination needs idx and coef");
     const int cplx = cim_dev != nullptr;
     PYMD_REQUIRE(!cplx || lim_dev, "eigh_factors: complex input needs lim");
     PYMD_REQUIRE(n <= pymd_eigh_max_n(cplx), "eigh_factors: n=%d exceeds the shared-memory limit %d", n,
                  pymd_eigh_max_n(cplx));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (cplx) return eigh_launch<double2>(cre_dev, cim_dev, nf, n, lam_dev, lre_dev, lim_dev, ure_dev, uim_dev, sweeps_dev, st);
-    return eigh_launch<double>(cre_dev, nullptr, nf, n, lam_dev, lre_dev, nullptr, ure_dev, nullptr, sweeps_dev, st);
+    if (cplx)
+        return eigh_launch<double2>(cre_dev, cim_dev, idx_dev, coef_dev, ncomb, nf, n, lam_dev, lre_dev, lim_dev, ure_dev,
+                                    uim_dev, sweeps_dev, st);
+    return eigh_launch<double>(cre_dev, nullptr, idx_dev, coef_dev, ncomb, nf, n, lam_dev, lre_dev, nullptr, ure_dev, nullptr,
+                               sweeps_dev, st);
 }
 
 }  // extern "C"

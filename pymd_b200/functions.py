@@ -61,6 +61,28 @@ def flinterp(x, xs, ys):
     return out[0] if N.ndim(x) == 0 else out
 
 
+def flinterp_weights(x, xs):
+    """flinterp as two table rows and weights: flinterp(x, xs, ys) = w0 * ys[i0] + w1 * ys[i1] (up to
+    rounding), with i0 the nearest grid point, i1 its neighbour on the side flinterp uses and
+    (w0, w1) = (1 + c, -c) in the reference's mirrored-slope convention (functions.py:61-78).
+    Returns int32 (n, 2) indices and float (n, 2) weights; lets a kernel assemble interpolated tables
+    without materialising them (pymd_eigh_factors)."""
+    xs = N.asarray(xs, dtype=float)
+    xa = N.atleast_1d(N.asarray(x, dtype=float))
+    n = len(xs)
+    i0 = N.argmin(N.abs(xs[None, :] - xa[:, None]), axis=1)
+    i1 = i0.copy()
+    c = N.zeros(len(xa))
+    if n > 1:
+        inner = (i0 > 0) & (i0 < n - 1)
+        ii = i0[inner]
+        dd = xs[ii] - xa[inner]
+        other = N.where(dd > 0, ii - 1, ii + 1)
+        i1[inner] = other
+        c[inner] = dd / (xs[ii] - xs[other])
+    return N.stack([i0, i1], axis=1).astype(N.int32), N.stack([1.0 + c, -c], axis=1)
+
+
 def rpadleft(bs, b):
     """Shift ``b`` in at the front, drop the last row (functions.py:88-95).  Host utility;
     on the device the history is a ring buffer (pymd_bind_history)."""

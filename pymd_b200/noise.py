@@ -11,7 +11,7 @@ import numpy as N
 
 from . import units as U
 from . import _lib
-from .functions import bose, flinterp
+from .functions import bose, flinterp, flinterp_weights
 from .matrix import chkShape, hermitianize
 
 
@@ -122,16 +122,26 @@ class DeviceSpectralFactors:
     factor up to a unitary diagonal: the noise has the same covariance L L^H, not the same realisation
     for a given xi -- use the host factors (default) to reproduce reference noise element by element."""
 
-    def __init__(self, amat, device, keep_vectors=False):
+    def __init__(self, amat, device, keep_vectors=False, combination=None):
+        """``amat``: the (nf, nc, nc) covariances, or -- with ``combination=(idx, coef)`` -- a small table of
+        matrices from which the kernel assembles C_f = herm(sum_m coef[f, m] amat[idx[f, m]])."""
         import torch
         amat = N.asarray(amat)
-        nf, nc = amat.shape[0], amat.shape[1]
+        nc = amat.shape[1]
         self.complex = bool(N.iscomplexobj(amat))
-        self.shape = (nf, nc, nc)
         self.device = torch.device(device)
         kw = dict(dtype=torch.float64, device=self.device)
         cre = torch.as_tensor(N.ascontiguousarray(amat.real), **kw)
         cim = torch.as_tensor(N.ascontiguousarray(amat.imag), **kw) if self.complex else None
+        idx = coef = None
+        nf, ncomb = amat.shape[0], 0
+        if combination is not None:
+            idx = torch.as_tensor(N.ascontiguousarray(combination[0], dtype=N.int32), device=self.device)
+            coef = torch.as_tensor(N.ascontiguousarray(combination[1], dtype=float), **kw)
+            nf, ncomb = idx.shape
+            if tuple(coef.shape) != (nf, ncomb) or int(idx.max()) >= amat.shape[0] or int(idx.min()) < 0:
+                raise ValueError("DeviceSpectralFactors: bad combination")
+        self.shape = (nf, nc, nc)
         self._lam = torch.empty((nf, nc), **kw)
         self._lre = torch.empty((nf, nc, nc), **kw)
         self._lim = torch.empty((nf, nc, nc), **kw) if self.complex else None
@@ -139,9 +149,9 @@ class DeviceSpectralFactors:
         self._uim = torch.empty((nf, nc, nc), **kw) if keep_vectors and self.complex else None
         self._sweeps = torch.empty(nf, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.call("pymd_eigh_factors", cre.data_ptr(), _lib.ptr(cim), nf, nc, self._lam.data_ptr(),
-                      self._lre.data_ptr(), _lib.ptr(self._lim), _lib.ptr(self._ure), _lib.ptr(self._uim),
-                      self._sweeps.data_ptr(), _lib.stream_ptr())
+            _lib.call("pymd_eigh_factors", cre.data_ptr(), _lib.ptr(cim), _lib.ptr(idx), _lib.ptr(coef), ncomb, nf, nc,
+                      self._lam.data_ptr(), self._lre.data_ptr(), _lib.ptr(self._lim), _lib.ptr(self._ure),
+                      _lib.ptr(self._uim), self._sweeps.data_ptr(), _lib.stream_ptr())
 
     @staticmethod
     def supported(amat):
@@ -188,14 +198,20 @@ def setup_on_device():
     return os.environ.get("PYMD_SETUP_DEVICE", "0") == "1"
 
 
-def _decompose(amat, device, strict=True, keep_vectors=False):
+def _device_ok(tables, device, strict):
     """``strict``: raise when the matrices do not fit the device kernel (an explicit request); otherwise
     (PYMD_SETUP_DEVICE=1) such baths keep the LAPACK path."""
-    if device is not None and not DeviceSpectralFactors.supported(amat):
-        if strict:
-            raise ValueError("noise: nc=%d is too large for the on-device eigen-decomposition" % amat.shape[1])
-        device = None
-    if device is not None:
+    if device is None:
+        return False
+    if DeviceSpectralFactors.supported(tables):
+        return True
+    if strict:
+        raise ValueError("noise: nc=%d is too large for the on-device eigen-decomposition" % tables.shape[1])
+    return False
+
+
+def _decompose(amat, device, strict=True, keep_vectors=False):
+    if _device_ok(amat, device, strict):
         return DeviceSpectralFactors(amat, device, keep_vectors)
     lam, vec = _batched_eigh(amat)
     return SpectralFactors(lam, vec)
@@ -209,7 +225,14 @@ def phonon_factors(gamma, wl, T, phcut, dt, nmd, classical=False, zpmotion=True,
     dw = 2.0 * N.pi / dt / nmd
     delta = dt * nmd
     w = dw * N.arange(nf)
-    amat = (delta * equ(w, phcut, T, classical, zpmotion))[:, None, None] * flinterp(w, wl, N.asarray(gamma))
+    gamma = N.asarray(gamma)
+    if _device_ok(gamma, device, strict):
+        # the kernel assembles delta equ(w_f) [w0 gamma[i0] + w1 gamma[i1]] itself: nothing of size nf x nc x nc
+        # is built or uploaded
+        idx, wt = flinterp_weights(w, wl)
+        coef = (delta * equ(w, phcut, T, classical, zpmotion))[:, None] * wt
+        return DeviceSpectralFactors(gamma, device, keep_vectors, combination=(idx, coef))
+    amat = (delta * equ(w, phcut, T, classical, zpmotion))[:, None, None] * flinterp(w, wl, gamma)
     amat = 0.5 * (amat + N.conj(N.transpose(amat, (0, 2, 1))))
     return _decompose(amat, device, strict, keep_vectors)
 
@@ -220,6 +243,16 @@ def electron_factors(efric, exim, exip, bias, T, ecut, dt, nmd, classical=False,
     nf = int(nmd / 2) + 1
     dw = 2.0 * N.pi / dt / nmd
     w = dw * N.arange(nf)
+    tables = N.array([N.asarray(efric) + 0j, N.asarray(exip) + 0j, 1j * N.asarray(exim)])
+    if _device_ok(tables, device, strict):
+        # _electron_cov regrouped: aw efric + [(awm + awp)/2 - aw] exip + (awm - awp)/2 (i exim)
+        delta = dt * nmd
+        aw = delta * equ(w, ecut, T, classical, zpmotion)
+        awm = delta * equ(U.hbar * w - bias, ecut, T, classical, zpmotion)
+        awp = delta * equ(U.hbar * w + bias, ecut, T, classical, zpmotion)
+        coef = N.stack([aw, 0.5 * (awm + awp) - aw, 0.5 * (awm - awp)], axis=1)
+        idx = N.tile(N.arange(3, dtype=N.int32), (nf, 1))
+        return DeviceSpectralFactors(tables, device, keep_vectors, combination=(idx, coef))
     amat = _electron_cov(w, efric, exim, exip, bias, T, ecut, classical, zpmotion, delta=dt * nmd)
     return _decompose(amat, device, strict, keep_vectors)
 
