@@ -82,6 +82,16 @@ class ebath(BathBase):
 
     # operands of ebath.bforce (ebath.py:191-194) pre-combined for the device:
     #   f = noise - (efric + V zeta2).p_c + V (exim - zeta1).q_c
+    def effective_selfenergy(self, w):
+        """-i w (efric + V zeta2) + V zeta1 - V exim (harmonic.SigE, harmonic.py:86-96)."""
+        from .harmonic import SigE
+        return SigE(w, self.efric, self.exim, self.zeta1, self.zeta2, self.bias)
+
+    def noise_spectrum(self, w):
+        """Spectrum of the generated noise on the grid w (noise.enoisew, noise.py:91-129)."""
+        return _noise.enoisew(w, self.efric, self.exim, self.exip, self.bias, self.T, self.wmax,
+                              self.classical, self.zpmotion)
+
     def _ap_matrix(self):
         return self.efric + self.bias * self.zeta2
 

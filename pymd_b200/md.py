@@ -472,6 +472,30 @@ class md(object):
         self.power = N.stack((w, s1 / self.batch), axis=1)
         self.power2 = N.stack((w, s2 / self.batch), axis=1)
 
+    def HarmonicSpectra(self, wl=None):
+        """Analytic counterpart of ``power2`` for the attached baths (the reference's harmonic.py
+        cross-check, harmonic.py:37-84): D(w) = [(w + i eta)^2 - dyn - sum_b Sigma_b(w)]^-1 with every
+        bath's self-energy as the stepping path implements it (bath.effective_selfenergy) and
+        PP(w) = w^2 Tr[D Pi D^+] with Pi = sum_b noise spectrum; all frequencies in one GPU launch
+        (pymd_harmonic).  ``wl`` defaults to the MD frequencies 0 < w < 1.5 max(hw).
+        Returns dict(w, DDos, UU, PP); in the steady state power2[:, 1] ~ PP on the same grid."""
+        from . import harmonic as H
+        if self.dyn is None:
+            raise ValueError("md.HarmonicSpectra: needs the dynamical matrix")
+        if wl is None:
+            w = 2. * N.pi / self.dt / self.nmd * N.arange(1, self.nmd // 2)
+            wl = w[w < 1.5 * max(self.hw)]
+        wl = N.asarray(wl, dtype=float)
+        nd = self.nph
+        se = N.zeros((len(wl), nd, nd), dtype=complex)
+        pi = N.zeros((len(wl), nd, nd), dtype=complex)
+        for b in self.baths:
+            c = N.asarray(b.cids)
+            se[:, c[:, None], c[None, :]] += b.effective_selfenergy(wl)
+            pi[:, c[:, None], c[None, :]] += b.noise_spectrum(wl)
+        ddos, uu, pp = H.spectra_device(wl, self.dyn, se, pi, self._dev())
+        return dict(w=wl, DDos=ddos, UU=uu, PP=pp)
+
     def Run(self):
         """nrep consecutive segments of nmd steps each: fresh noise per segment, npie pieces
         with a checkpoint after each, running mean of the spectra, kappa/power text outputs

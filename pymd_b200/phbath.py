@@ -119,6 +119,24 @@ class phbath(BathBase):
                                      self.classical, self.zpmotion, device=dev, strict=strict,
                                      keep_vectors=self.setup_keep_vectors)
 
+    def effective_selfenergy(self, w):
+        """Retarded self-energy the time-domain friction actually implements, reconstructed from the
+        discrete, truncated kernel: Sigma(w) = -i w dt sum_k K[k] exp(i w k dt) (no dt for the
+        memory-less Debye bath) -- what harmonic.Drs must be fed for a tight comparison with MD spectra
+        (SURVEY.md section 8c).  (len(w), nc, nc) complex."""
+        w = N.asarray(w, dtype=float)
+        ker = N.asarray(self.kernel, dtype=float)[:self.ml]
+        if self.ml == 1:
+            return -1j * w[:, None, None] * ker[0][None]
+        ph = N.exp(1j * w[:, None] * (self.dt * N.arange(self.ml))[None, :])
+        return -1j * (w * self.dt)[:, None, None] * N.tensordot(ph, ker, axes=(1, 0))
+
+    def noise_spectrum(self, w):
+        """Spectrum of the generated noise on the grid w: equ(w) gamma~(w) (noise.py:16-34, 61-66)."""
+        w = N.asarray(w, dtype=float)
+        return _noise.phnoisew(flinterp(w, self.gwl, N.asarray(self.gamma)), w, self.T, self.wmax,
+                               self.classical, self.zpmotion)
+
     def gnoi(self, xi=None):
         """Regenerate the coloured noise for every trajectory (phbath.py:146-158); ``xi``
         optionally supplies the standard normals, shape (nmd/2+1, nc[, batch])."""

@@ -214,3 +214,35 @@ def test_trajectory_parity_with_device_factors(cuda):
         for b, ob in enumerate(om.baths):
             assert T.relerr(m.baths[b].noise[..., n], ob.noise) < 1e-11
             assert T.relerr(m.baths[b].cur[..., n], ob.cur) < 1e-10
+
+
+def test_md_power2_matches_harmonic_spectrum(cuda):
+    """The always-on self-check of the reference (harmonic.py:70-84, MD power2 ~ PP): 1024 trajectories
+    of the 39-dof chain between two leads, two steady-state segments of 4096 steps, against
+    md.HarmonicSpectra() (self-energy rebuilt from the discrete kernel, one pymd_harmonic launch).
+    Inside the phonon band the band-integrated ratio is 1 within 3 % (statistical error ~0.5 %); the
+    band edge is excluded (the integrator shifts the sharp edge peak by (w dt)^2/24)."""
+    import pymd_testlib as T
+    c = dict(T.CASES["chain39"], nmd=4096)
+    m, j = T.device_md(c, 1024, seed=3)
+    m.initialise()
+    m.ResetHis()
+    acc = 0.0
+    for rep in range(3):
+        for b in m.baths:
+            b.gnoi()
+        m.ResetSavepq(True)
+        m.steps(c["nmd"])
+        if rep > 0:
+            m.GetPower()
+            acc = acc + m.power2[:, 1] / 2.0
+    h = m.HarmonicSpectra()
+    k = np.rint(h["w"] / (2 * np.pi / c["dt"] / c["nmd"])).astype(int)
+    assert np.array_equal(m.power2[k, 0], h["w"])
+    mdp, pp, w = acc[k], h["PP"], h["w"]
+    for lo, hi in ((0.0038, 0.0075), (0.0075, 0.0112), (0.0112, 0.0148), (0.0148, 0.0184)):
+        sel = (w >= lo) & (w < hi)
+        assert abs(mdp[sel].sum() / pp[sel].sum() - 1.0) < 0.03, (lo, hi)
+    sel = w < 0.0184
+    assert abs(mdp[sel].sum() / pp[sel].sum() - 1.0) < 0.02
+    assert np.all(h["DDos"][w < 0.0184] > 0)

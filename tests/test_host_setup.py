@@ -155,3 +155,41 @@ def test_gamt_vs_oracle_large_table():
     wl = [0.06 * i / 60 for i in range(60)]
     tl = [4.0 * i for i in range(12)]
     assert relmax(gamt(tl, wl, j.wl[1:], gam), O.gamt(tl, wl, j.wl[1:], gam)) < 1e-13
+
+
+def test_flinterp_weights_reproduce_flinterp():
+    """flinterp as two table rows and weights (what pymd_eigh_factors assembles in the kernel)."""
+    from pymd_b200.functions import flinterp, flinterp_weights
+    rng = np.random.default_rng(0)
+    xs = np.sort(rng.uniform(0, 1, 20))
+    ys = rng.standard_normal((20, 3, 3))
+    x = np.concatenate([xs, rng.uniform(-0.2, 1.2, 400), 0.5 * (xs[1:] + xs[:-1])])
+    idx, wt = flinterp_weights(x, xs)
+    assert idx.dtype == np.int32 and idx.shape == wt.shape == (len(x), 2)
+    got = wt[:, 0, None, None] * ys[idx[:, 0]] + wt[:, 1, None, None] * ys[idx[:, 1]]
+    ref = np.array([O.flinterp(v, xs, ys) for v in x])
+    assert relmax(got, ref) < 1e-14 and relmax(flinterp(x, xs, ys), ref) < 1e-15
+    i1, w1 = flinterp_weights([0.3], [0.0])                # one-point table (Debye bath)
+    assert i1.tolist() == [[0, 0]] and w1[0, 0] == 1.0 and w1[0, 1] == 0.0
+
+
+def test_bath_selfenergy_and_noise_spectrum_helpers():
+    """What md.HarmonicSpectra feeds the harmonic kernel: the discrete-kernel self-energy of a lead,
+    the wide-band one of the electron bath (harmonic.SigE), and the noise spectra."""
+    j = synth.synth(12, 3, 3, seed=1)
+    b = phbath(300.0, j.cats_l, 0.03, 40, 8.0, 64, ml=8, sig=j.SigL, gwl=j.wl)
+    b.gmem()
+    w = np.linspace(0.001, 0.02, 5)
+    se = b.effective_selfenergy(w)
+    for i, wv in enumerate(w):
+        ref = sum(-1j * wv * b.dt * b.kernel[k] * np.exp(1j * wv * k * b.dt) for k in range(b.ml))
+        assert relmax(se[i], ref) < 1e-14
+    gam = np.array([O.flinterp(v, b.gwl, b.gamma) for v in w])
+    assert relmax(b.noise_spectrum(w), O.phnoisew(gam, w, 300.0, b.wmax)) < 1e-15
+    e = ebath(j.cats_e, 100.0, 1.0, 64, wmax=1.0, nw=500, bias=0.3, efric=j.efric, exim=j.exim, exip=j.exip,
+              zeta1=j.zeta1, zeta2=j.zeta2)
+    assert relmax(e.effective_selfenergy(w), O.SigE(w, j.efric, j.exim, j.zeta1, j.zeta2, 0.3)) < 1e-15
+    assert relmax(e.noise_spectrum(w), O.enoisew(w, j.efric, j.exim, j.exip, 0.3, 100.0, 1.0)) < 1e-14
+    d = phbath(300.0, [0], 0.03, 40, 8.0, 64)
+    d.gmem()
+    assert relmax(d.effective_selfenergy(w), -1j * w[:, None, None] * d.kernel[0][None]) < 1e-15
