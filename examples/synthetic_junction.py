@@ -53,6 +53,8 @@ def main():
     ap.add_argument("--nmd", type=int, default=1024)
     ap.add_argument("--nrep", type=int, default=1)
     ap.add_argument("--outdir", default="run_synthetic")
+    ap.add_argument("--harmonic-check", action="store_true",
+                    help="also write harmonic.<T>.run<j>.dat: analytic PP next to the MD power2")
     a = ap.parse_args()
     os.makedirs(a.outdir, exist_ok=True)
     j = write_inputs(a.outdir)
@@ -69,6 +71,7 @@ def main():
     mdrun = md(dt, nmd, T, axyz=j.axyz, harmonic=True, dyn=dyn, nrep=a.nrep, npie=4,
                batch=a.batch, seed=2024)                               # batch/seed: the only new arguments
     mdrun.outdir = a.outdir
+    mdrun.harmonic_check = a.harmonic_check
     ecats = range(mdrun.na)
     eb = ebath(ecats, T, mdrun.dt, mdrun.nmd, wmax=1.0, nw=500, bias=eV, efric=eta, exim=xim, exip=xip,
                zeta1=zeta1, zeta2=zeta2)

@@ -49,6 +49,7 @@ class md(object):
         self.record_fhis = record_fhis
         self.write_files = True
         self.outdir = "."
+        self.harmonic_check = False     # Run() also writes harmonic.<T>.run<j>.dat: w, analytic PP, MD power2
         self._device = device
         self.SetXyz(axyz)
         self.syslist = self.na = self.nph = None
@@ -486,6 +487,8 @@ class md(object):
             w = 2. * N.pi / self.dt / self.nmd * N.arange(1, self.nmd // 2)
             wl = w[w < 1.5 * max(self.hw)]
         wl = N.asarray(wl, dtype=float)
+        if len(wl) == 0:
+            raise ValueError("md.HarmonicSpectra: no MD frequency below 1.5 max(hw); the run is too short")
         nd = self.nph
         se = N.zeros((len(wl), nd, nd), dtype=complex)
         pi = N.zeros((len(wl), nd, nd), dtype=complex)
@@ -542,6 +545,13 @@ class md(object):
                     if lim is not None and not arr[i, 0] < lim:
                         break
                     f.write("%f     %f \n" % (arr[i, 0], arr[i, 1]))
+        if self.harmonic_check and self._savepq:
+            # the reference's cross-check (harmonic.py:70-84: MD power2 ~ PP) beside the spectra
+            self.harmonic = h = self.HarmonicSpectra()
+            k = N.rint(h["w"] / (2. * N.pi / self.dt / self.nmd)).astype(int)
+            with open(os.path.join(self.outdir, "harmonic.%s.run%d.dat" % (self.T, j)), "w") as f:
+                for i in range(len(k)):
+                    f.write("%f     %e     %e \n" % (h["w"][i], h["PP"][i], self.power2[k[i], 1]))
 
     def _ckpt_name(self, j):
         """Single trajectories checkpoint into the reference's own container, ``MD<j>.nc`` (NetCDF-3 with the

@@ -469,6 +469,29 @@ def test_example_driver_script(cuda, tmp_path, monkeypatch):
     assert e.DynMat.shape == (48, 48) and np.allclose(e.DynMat, e.DynMat.T)
 
 
+def test_example_driver_with_device_setup_and_harmonic_check(cuda, tmp_path, monkeypatch):
+    """The same script with PYMD_SETUP_DEVICE=1 (friction kernels from pymd_gamt, spectral factors from the
+    Jacobi kernel) and --harmonic-check (analytic PP written next to power2 by pymd_harmonic)."""
+    import importlib.util
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("synthetic_junction2", os.path.join(root, "examples", "synthetic_junction.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = str(tmp_path / "run")
+    monkeypatch.setenv("PYMD_SETUP_DEVICE", "1")
+    monkeypatch.setattr(sys, "argv", ["synthetic_junction.py", "--batch", "40", "--nmd", "2048", "--outdir", out,
+                                      "--harmonic-check"])
+    m = mod.main()
+    assert m.t == 2048 and np.isfinite(m.p).all() and np.isfinite(m.power2).all()
+    assert all(type(b.spectral_factors()).__name__ == "DeviceSpectralFactors" for b in m.baths)
+    tab = np.loadtxt(os.path.join(out, "harmonic.300.0.run0.dat"))
+    assert tab.ndim == 2 and tab.shape[1] == 3 and len(tab) == len(m.harmonic["w"]) > 0
+    assert np.isfinite(tab).all() and (tab[:, 1] >= 0).all() and (tab[:, 2] >= 0).all()
+    assert np.allclose(tab[:, 1], m.harmonic["PP"], rtol=1e-6)
+
+
 @pytest.mark.parametrize("seed", range(8))
 def test_randomized_configurations(cuda, seed, monkeypatch):
     """Random junction shapes around the path-selection boundaries (nd up to 63, leads of 3..18 dofs so
