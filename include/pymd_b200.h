@@ -183,11 +183,15 @@ int pymd_harmonic(const double* wl_dev, int nw, const double* dyn_dev, const dou
  * c is then dev [ntab][n][n] and C_f = herm(sum_{m<ncomb} coef[f][m] * c[idx[f][m]]), herm(M) = (M + M^H)/2,
  * idx dev [nf][ncomb] int32, coef dev [nf][ncomb] -- three fixed matrices with frequency-dependent weights
  * for the electron bath (noise.py:156-170), two neighbouring gamma-table entries with the flinterp weights
- * for a phonon bath (noise.py:61-66).  ncomb == 0: idx and coef are ignored (may be NULL). */
+ * for a phonon bath (noise.py:61-66).  ncomb == 0: idx and coef are ignored (may be NULL).
+ * Matrices too large to hold twice in shared memory (n > 83 complex, > 118 real) keep the eigenvector
+ * accumulator in a global scratch: work dev of pymd_eigh_work_bytes(nf, n, complex?) bytes (0: not needed,
+ * work may be NULL). */
 int pymd_eigh_max_n(int cplx);
+size_t pymd_eigh_work_bytes(int nf, int n, int cplx);
 int pymd_eigh_factors(const double* cre_dev, const double* cim_dev, const int* idx_dev, const double* coef_dev, int ncomb,
                       int nf, int n, double* lam_dev, double* lre_dev, double* lim_dev, double* ure_dev, double* uim_dev,
-                      int* sweeps_dev, void* stream);
+                      int* sweeps_dev, void* work_dev, void* stream);
 
 #ifdef __cplusplus
 }

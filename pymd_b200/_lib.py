@@ -54,7 +54,8 @@ PROTOTYPES = {
     "pymd_harmonic_max_n": (C.c_int, []),
     "pymd_eigh_max_n": (C.c_int, [C.c_int]),
     "pymd_eigh_factors": (C.c_int, [c_dp, c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
-                                    c_dp]),
+                                    c_dp, c_dp]),
+    "pymd_eigh_work_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "pymd_harmonic": (C.c_int, [c_dp, C.c_int, c_dp, c_dp, c_dp, C.c_int, C.c_double, c_dp, c_dp, c_dp]),
 }
 

@@ -284,12 +284,16 @@ __device__ __forceinline__ void rot_rows(double c, double2 s, double2& x, double
 
 constexpr int ET = 256, EMAXSWEEP = 40;
 
+// vglob: the eigenvector accumulator lives in a global scratch (one n x n tile per CTA, L1/L2 resident)
+// instead of shared memory -- for matrices too large to keep both there.
 template <typename E>
-size_t eigh_smem(int n) {
+size_t eigh_smem(int n, bool vglob) {
     const int ne = n + (n & 1);
-    return 2 * (size_t)n * (n + 1) * sizeof(E) + (size_t)(ne / 2) * (sizeof(E) + sizeof(double) + 2 * sizeof(int)) +
+    return (vglob ? 1 : 2) * (size_t)n * (n + 1) * sizeof(E) +
+           (size_t)(ne / 2) * (sizeof(E) + sizeof(double) + 2 * sizeof(int)) +
            (size_t)n * (sizeof(double) + sizeof(int)) + (ET + 2) * sizeof(double) + 64;
 }
+constexpr size_t kSmemMax = 227 * 1024;
 
 // Input: either the matrices themselves (ncomb == 0: cre/cim are [nf][n][n]) or, to avoid building and
 // uploading them, a linear combination of a small table of matrices (cre/cim are [ntab][n][n]):
@@ -301,12 +305,15 @@ __global__ void __launch_bounds__(ET) eigh_kernel(const double* __restrict__ cre
                                                   const int* __restrict__ idx, const double* __restrict__ coef, int ncomb,
                                                   int nf, int n, double* __restrict__ lam, double* __restrict__ lre,
                                                   double* __restrict__ lim, double* __restrict__ ure,
-                                                  double* __restrict__ uim, int* __restrict__ sweeps) {
+                                                  double* __restrict__ uim, int* __restrict__ sweeps, E* vwork) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int ld = n + 1, ne = n + (n & 1), np = ne / 2, tid = threadIdx.x;
     E* A = reinterpret_cast<E*>(smraw);
-    E* V = A + (size_t)n * ld;
-    E* rs = V + (size_t)n * ld;                                   // s e^{i phi} per pair
+    // V is kept TRANSPOSED (V[j * ldv + i] = component i of vector j): a rotation of two vectors runs over
+    // contiguous elements, conflict-free in shared memory and coalesced in the global scratch
+    const int ldv = vwork ? n : ld;
+    E* V = vwork ? vwork + (size_t)blockIdx.x * n * n : A + (size_t)n * ld;
+    E* rs = (vwork ? A : V) + (size_t)n * ld;                     // s e^{i phi} per pair
     double* rc = reinterpret_cast<double*>(rs + np);              // c per pair
     double* ev = rc + np;                                         // eigenvalues
     double* red = ev + n;                                         // [ET + 2]
@@ -331,7 +338,7 @@ __global__ void __launch_bounds__(ET) eigh_kernel(const double* __restrict__ cre
                 }
                 e_make(A[i * ld + j], re, im);
             }
-            e_make(V[i * ld + j], i == j ? 1.0 : 0.0, 0.0);
+            e_make(V[i * ldv + j], i == j ? 1.0 : 0.0, 0.0);
         }
         __syncthreads();
         int sweep = 0;
@@ -386,7 +393,7 @@ __global__ void __launch_bounds__(ET) eigh_kernel(const double* __restrict__ cre
                     const int k = e / n, i = e % n, p = rp[k], q = rq[k];
                     if (p < 0) continue;
                     rot_cols(rc[k], rs[k], A[i * ld + p], A[i * ld + q]);
-                    rot_cols(rc[k], rs[k], V[i * ld + p], V[i * ld + q]);
+                    rot_cols(rc[k], rs[k], V[p * ldv + i], V[q * ldv + i]);
                 }
                 __syncthreads();
                 for (int e = tid; e < np * n; e += ET) {              // rows of A
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(ET) eigh_kernel(const double* __restrict__ cre
         __syncthreads();
         for (int e = tid; e < n * n; e += ET) {
             const int i = e / n, j = e % n, col = rank[j];
-            const E v = V[i * ld + j];
+            const E v = V[j * ldv + i];
             const double sq = sqrt(fmax(ev[j], 0.0));
             lre[base + (size_t)i * n + col] = sq * e_re(v);
             if (CPLX) lim[base + (size_t)i * n + col] = sq * e_im(v);
@@ -428,18 +435,26 @@ __global__ void __launch_bounds__(ET) eigh_kernel(const double* __restrict__ cre
     }
 }
 
+// CTAs of a launch (each owns one global V tile when the matrices do not fit shared memory twice)
+template <typename E>
+int eigh_grid(int nf, int n, bool vglob) {
+    const size_t smem = eigh_smem<E>(n, vglob);
+    int per_sm = (int)(kSmemMax / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+    return nf < 148 * per_sm ? nf : 148 * per_sm;
+}
+
 template <typename E>
 int eigh_launch(const double* cre, const double* cim, const int* idx, const double* coef, int ncomb, int nf, int n,
-                double* lam, double* lre, double* lim, double* ure, double* uim, int* sweeps, cudaStream_t st) {
-    const size_t smem = eigh_smem<E>(n);
+                double* lam, double* lre, double* lim, double* ure, double* uim, int* sweeps, void* work,
+                cudaStream_t st) {
+    const bool vglob = eigh_smem<E>(n, false) > kSmemMax;
+    PYMD_REQUIRE(!vglob || work, "eigh_factors: n=%d needs the scratch of pymd_eigh_work_bytes()", n);
+    const size_t smem = eigh_smem<E>(n, vglob);
     PYMD_CUDA_CHECK(cudaFuncSetAttribute(eigh_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0, sms = 148;
-    PYMD_CUDA_CHECK(cudaGetDevice(&dev));
-    PYMD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
-    const int grid = nf < sms * per_sm ? nf : sms * per_sm;
-    eigh_kernel<E><<<grid, ET, smem, st>>>(cre, cim, idx, coef, ncomb, nf, n, lam, lre, lim, ure, uim, sweeps);
+    const int grid = eigh_grid<E>(nf, n, vglob);
+    eigh_kernel<E><<<grid, ET, smem, st>>>(cre, cim, idx, coef, ncomb, nf, n, lam, lre, lim, ure, uim, sweeps,
+                                           vglob ? static_cast<E*>(work) : nullptr);
     PYMD_CUDA_CHECK(cudaGetLastError());
     return PYMD_OK;
 }
@@ -451,13 +466,20 @@ extern "C" {
 
 int pymd_eigh_max_n(int cplx) {
     int n = 1;
-    while ((cplx ? pymd::eigh_smem<double2>(n + 1) : pymd::eigh_smem<double>(n + 1)) <= 227 * 1024) ++n;
+    while ((cplx ? pymd::eigh_smem<double2>(n + 1, true) : pymd::eigh_smem<double>(n + 1, true)) <= pymd::kSmemMax) ++n;
     return n;
+}
+
+size_t pymd_eigh_work_bytes(int nf, int n, int cplx) {
+    using namespace pymd;
+    if (nf <= 0 || n <= 0 || n > pymd_eigh_max_n(cplx)) return 0;
+    if (cplx) return eigh_smem<double2>(n, false) > kSmemMax ? (size_t)eigh_grid<double2>(nf, n, true) * n * n * sizeof(double2) : 0;
+    return eigh_smem<double>(n, false) > kSmemMax ? (size_t)eigh_grid<double>(nf, n, true) * n * n * sizeof(double) : 0;
 }
 
 int pymd_eigh_factors(const double* cre_dev, const double* cim_dev, const int* idx_dev, const double* coef_dev, int ncomb,
                       int nf, int n, double* lam_dev, double* lre_dev, double* lim_dev, double* ure_dev, double* uim_dev,
-                      int* sweeps_dev, void* stream) {
+                      int* sweeps_dev, void* work_dev, void* stream) {
     using namespace pymd;
     PYMD_REQUIRE(cre_dev && lam_dev && lre_dev, "eigh_factors: null pointer");
     PYMD_REQUIRE(nf > 0 && n > 0, "eigh_factors: bad shape nf=%d n=%d", nf, n);
@@ -469,9 +491,9 @@ int pymd_eigh_factors(const double* cre_dev, const double* cim_dev, const int* i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (cplx)
         return eigh_launch<double2>(cre_dev, cim_dev, idx_dev, coef_dev, ncomb, nf, n, lam_dev, lre_dev, lim_dev, ure_dev,
-                                    uim_dev, sweeps_dev, st);
+                                    uim_dev, sweeps_dev, work_dev, st);
     return eigh_launch<double>(cre_dev, nullptr, idx_dev, coef_dev, ncomb, nf, n, lam_dev, lre_dev, nullptr, ure_dev, nullptr,
-                               sweeps_dev, st);
+                               sweeps_dev, work_dev, st);
 }
 
 }  // extern "C"

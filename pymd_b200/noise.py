@@ -148,10 +148,14 @@ class DeviceSpectralFactors:
         self._ure = torch.empty((nf, nc, nc), **kw) if keep_vectors else None
         self._uim = torch.empty((nf, nc, nc), **kw) if keep_vectors and self.complex else None
         self._sweeps = torch.empty(nf, dtype=torch.int32, device=self.device)
+        wb = _lib.load().pymd_eigh_work_bytes(nf, nc, 1 if self.complex else 0)
+        work = torch.empty(wb, dtype=torch.uint8, device=self.device) if wb else None
         with torch.cuda.device(self.device):
             _lib.call("pymd_eigh_factors", cre.data_ptr(), _lib.ptr(cim), _lib.ptr(idx), _lib.ptr(coef), ncomb, nf, nc,
                       self._lam.data_ptr(), self._lre.data_ptr(), _lib.ptr(self._lim), _lib.ptr(self._ure),
-                      _lib.ptr(self._uim), self._sweeps.data_ptr(), _lib.stream_ptr())
+                      _lib.ptr(self._uim), self._sweeps.data_ptr(), _lib.ptr(work), _lib.stream_ptr())
+            if work is not None:
+                torch.cuda.current_stream().synchronize()      # the scratch is freed on return
 
     @staticmethod
     def supported(amat):

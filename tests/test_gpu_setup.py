@@ -131,8 +131,11 @@ def check_factors(fac, amat, tol=2e-13):
 
 
 @pytest.mark.parametrize("n,cplx", [(1, False), (2, True), (5, False), (15, False), (15, True), (39, True),
-                                     (60, True), (64, False), (81, False), (83, True), (118, False)])
+                                     (60, True), (64, False), (81, False), (83, True), (118, False),
+                                     (84, True), (96, True), (118, True), (119, False), (150, False)])
 def test_eigh_factors_random_matrices(cuda, n, cplx):
+    """n <= 83 complex / 118 real: matrix and eigenvectors in shared memory; above (up to 118 / 167) the
+    eigenvectors accumulate in a global scratch tile per CTA."""
     from pymd_b200.noise import DeviceSpectralFactors
     rng = np.random.default_rng(n)
     nf = 40
@@ -173,8 +176,8 @@ def test_eigh_factors_of_bath_covariances(cuda):
     dl = ed.L @ np.conj(np.transpose(ed.L, (0, 2, 1)))
     assert np.abs(dl - hl).max() <= 1e-13 * scale
     with pytest.raises(ValueError):
-        PN._decompose(np.zeros((2, 90, 90), dtype=complex), cuda)
-    assert isinstance(PN._decompose(np.zeros((2, 90, 90), dtype=complex), cuda, strict=False), PN.SpectralFactors)
+        PN._decompose(np.zeros((2, 130, 130), dtype=complex), cuda)
+    assert isinstance(PN._decompose(np.zeros((2, 130, 130), dtype=complex), cuda, strict=False), PN.SpectralFactors)
 
 
 def test_trajectory_parity_with_device_factors(cuda):

@@ -76,10 +76,12 @@ def main():
     from pymd_b200 import noise as PN
     j = synth.synth(60, 15, 15, seed=2)
     gam = -np.imag(j.SigL[1:]) / j.wl[1:, None, None]
+    j3 = synth.synth(96, 27, 27, seed=9)
     j4 = synth.synth(510, 81, 81, seed=4)
     gam4 = -np.imag(j4.SigL[1:]) / j4.wl[1:, None, None]
     cases = [("ebath nc=60 complex", lambda d: PN.electron_factors(j.efric, j.exim, j.exip, 0.5, 300.0, 1.0, 1.0, 32768, device=d)),
              ("phbath nc=15 real", lambda d: PN.phonon_factors(gam, j.wl[1:], 300.0, 0.03, 1.0, 32768, device=d)),
+             ("ebath nc=96 complex (config 3)", lambda d: PN.electron_factors(j3.efric, j3.exim, j3.exip, 0.5, 300.0, 1.0, 2.0, 16384, device=d)),
              ("phbath nc=81 real", lambda d: PN.phonon_factors(gam4, j4.wl[1:], 300.0, 0.03, 15.0, 8192, device=d))]
     for name, fn in cases:
         t0 = time.perf_counter()
