@@ -57,6 +57,32 @@ __device__ __forceinline__ void butterfly<8>(double2* v) {
     }
 }
 
+// 16 = 4 x 4: DFT4 over b of x[a + 4 b], twiddle W16^{a q}, DFT4 over a -> X[q + 4 p]
+template <>
+__device__ __forceinline__ void butterfly<16>(double2* v) {
+    const double h = 0.70710678118654752440, c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;
+    double2 t[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        double2 u[4] = {v[a], v[a + 4], v[a + 8], v[a + 12]};
+        butterfly<4>(u);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) t[a][q] = u[q];
+    }
+    const double2 w1 = make_double2(c1, -s1), w2 = make_double2(h, -h), w3 = make_double2(s1, -c1);
+    const double2 w6 = make_double2(-h, -h), w9 = make_double2(-c1, s1);
+    t[1][1] = cmul(t[1][1], w1); t[1][2] = cmul(t[1][2], w2); t[1][3] = cmul(t[1][3], w3);
+    t[2][1] = cmul(t[2][1], w2); t[2][2] = mul_mi(t[2][2]);   t[2][3] = cmul(t[2][3], w6);
+    t[3][1] = cmul(t[3][1], w3); t[3][2] = cmul(t[3][2], w6); t[3][3] = cmul(t[3][3], w9);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        double2 u[4] = {t[0][q], t[1][q], t[2][q], t[3][q]};
+        butterfly<4>(u);
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) v[q + 4 * pp] = u[pp];
+    }
+}
+
 template <int R>
 __global__ void __launch_bounds__(128) fft_pass_kernel(const void* __restrict__ src, void* __restrict__ dst,
                                                        int n, int Ns, long long cols, int conj_in, int conj_out,
@@ -196,6 +222,96 @@ __global__ void __launch_bounds__(32 * R, 512 / (32 * R)) fft_pass2_kernel(const
     }
 }
 
+// Fused radix-128 pass: 128 = 8 (r1, the thread row) x 16 (r2, in registers).  blockDim = (32 columns, 8):
+// thread (x, r1) transforms inputs r1 + 8 r2 (r2 < 16) with one radix-16 butterfly, the 8 x 16 intermediate
+// goes through shared memory with the inner twiddles W_128^{r1 q2}, then the thread transforms q2 = ty and
+// q2 = ty + 8 over r1 (two radix-8 butterflies) and stores outputs q2 + 16 q1.  With it 2^14 = 128 x 128 is two
+// sweeps over HBM instead of three (64 x 64 x 4), 2^13 = 128 x 64 likewise.
+template <int LM, int SM>
+__global__ void __launch_bounds__(256, 1) fft_pass128_kernel(const void* __restrict__ src, void* __restrict__ dst, int n,
+                                                             int Ns, long long cols, int conj_in, int conj_out,
+                                                             const double2* __restrict__ tw, int twN, long long src_ld,
+                                                             long long dst_ld, double scale, long long dst_cw,
+                                                             long long dst_cs) {
+    constexpr int R1 = 8, R2 = 16, RR = 128;
+    extern __shared__ __align__(16) double2 ex128[];        // [RR][32]
+    const int j = blockIdx.y;
+    const int k = j % Ns;
+    const int nr = n / RR;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tw0 = ty * k * (twN / (Ns * RR)), twd = R1 * k * (twN / (Ns * RR));
+    const int twi = ty * (twN / RR);
+    const long long cstride = (long long)gridDim.x * 32;
+    const long long srow = LM == LOAD_C ? 1 : 2;
+    const long long sbase = (long long)(j + (long long)ty * nr) * srow * src_ld + tx;
+    const long long sstep = (long long)R1 * nr * srow * src_ld;
+    const long long drow = SM == STORE_C ? 1 : 2;
+    const long long dbase = ((long long)(j / Ns) * Ns * RR + k + (long long)ty * Ns) * drow * dst_ld;   // q2 = ty, q1 = 0
+    const long long dhalf = (long long)R1 * Ns * drow * dst_ld;                                          // q2 += 8
+    const long long dstep = (long long)R2 * Ns * drow * dst_ld;                                          // q1 += 1
+    auto issue = [&](double2 (&d)[R2], long long c0) {
+        const bool ok = c0 + tx < cols;
+#pragma unroll
+        for (int r2 = 0; r2 < R2; ++r2) {
+            d[r2] = make_double2(0.0, 0.0);
+            if (ok) {
+                if (LM == LOAD_C) {
+                    d[r2] = __ldcs(static_cast<const double2*>(src) + sbase + r2 * sstep + c0);
+                } else {
+                    const double* xr = static_cast<const double*>(src) + sbase + r2 * sstep + c0;
+                    d[r2] = make_double2(__ldcs(xr), __ldcs(xr + src_ld));
+                }
+            }
+        }
+    };
+    // one CTA per SM with the next tile's 16 loads per thread in flight (measured faster than two CTAs of 128
+    // registers without the prefetch: 7.35 vs 7.88 ms for 2^14 x 21120 columns)
+    double2 v[R2], nx[R2];
+    long long c0 = (long long)blockIdx.x * 32;
+    issue(nx, c0);
+    for (; c0 < cols; c0 += cstride) {
+        const long long col = c0 + tx;
+        const bool ok = col < cols;
+#pragma unroll
+        for (int r2 = 0; r2 < R2; ++r2) v[r2] = nx[r2];
+        if (c0 + cstride < cols) issue(nx, c0 + cstride);
+#pragma unroll
+        for (int r2 = 0; r2 < R2; ++r2) {
+            if (conj_in) v[r2].y = -v[r2].y;
+            if (Ns > 1 && (r2 > 0 || ty > 0)) v[r2] = cmul(v[r2], tw[tw0 + r2 * twd]);
+        }
+        butterfly<16>(v);
+        __syncthreads();                                // previous tile consumed
+#pragma unroll
+        for (int q2 = 0; q2 < R2; ++q2)
+            ex128[(ty * R2 + q2) * 32 + tx] = (q2 > 0 && ty > 0) ? cmul(v[q2], tw[q2 * twi]) : v[q2];
+        __syncthreads();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            double2 u[R1];
+#pragma unroll
+            for (int r1 = 0; r1 < R1; ++r1) u[r1] = ex128[(r1 * R2 + ty + 8 * hf) * 32 + tx];
+            butterfly<8>(u);                            // u[q1]: output (ty + 8 hf) + 16 q1
+            if (ok) {
+                const double si = conj_out ? -scale : scale;
+                if (SM == STORE_C) {
+                    double2* dp = static_cast<double2*>(dst) + dbase + hf * dhalf + col;
+#pragma unroll
+                    for (int q1 = 0; q1 < R1; ++q1) __stcs(dp + q1 * dstep, make_double2(scale * u[q1].x, si * u[q1].y));
+                } else {
+                    const long long dc = dst_cw ? (col / dst_cw) * dst_cs + col % dst_cw : col;
+                    double* dp = static_cast<double*>(dst) + dbase + hf * dhalf + dc;
+#pragma unroll
+                    for (int q1 = 0; q1 < R1; ++q1) {
+                        dp[q1 * dstep] = scale * u[q1].x;
+                        dp[q1 * dstep + dst_ld] = si * u[q1].y;
+                    }
+                }
+            }
+        }
+    }
+}
+
 struct TwKey {
     int dev, N;
     bool operator<(const TwKey& o) const { return dev < o.dev || (dev == o.dev && N < o.N); }
@@ -204,6 +320,38 @@ std::map<TwKey, double2*> g_tw;
 std::mutex g_tw_mu;
 
 }  // namespace
+
+// Radices of the passes, fused ones (128, 64, 16) first.  Fewest sweeps over HBM wins; among plans with the same
+// number of sweeps the 64/16 passes are preferred.
+int fft_plan(int n, int* radices) {
+    static const int cand[6] = {64, 16, 8, 4, 2, 128};
+    int best[32], pick[32];                       // indexed by log2 of the remaining length
+    best[0] = 0;
+    int lg = 0;
+    while ((1 << lg) < n) ++lg;
+    for (int l = 1; l <= lg; ++l) {
+        best[l] = 1 << 20;
+        for (int c = 0; c < 6; ++c) {
+            int lr = 0;
+            while ((1 << lr) < cand[c]) ++lr;
+            if (lr <= l && best[l - lr] + 1 < best[l]) { best[l] = best[l - lr] + 1; pick[l] = cand[c]; }
+        }
+    }
+    int np = 0, l = lg;
+    while (l > 0) {
+        radices[np++] = pick[l];
+        int lr = 0;
+        while ((1 << lr) < pick[l]) ++lr;
+        l -= lr;
+    }
+    std::sort(radices, radices + np, [](int a, int b) { return a > b; });
+    return np;
+}
+
+int fft_num_passes(int n) {
+    int r[32];
+    return fft_plan(n, r);
+}
 
 const double2* twiddle_table(int N) {
     int dev = 0;
@@ -230,11 +378,8 @@ int fft_columns(const void* src, void* dst, double2* bufA, double2* bufB, const 
     PYMD_REQUIRE(p.cols > 0, "fft: no columns");
     const double2* tw = twiddle_table(p.n);
     PYMD_REQUIRE(tw, "fft: twiddle table allocation failed");
-    int radices[32], np = 0, rem = p.n;
-    while (rem >= 64) { radices[np++] = 64; rem /= 64; }
-    if (rem == 32) { radices[np++] = 16; rem = 2; }
-    if (rem == 16) { radices[np++] = 16; rem = 1; }
-    if (rem > 1) radices[np++] = rem;
+    int radices[32];
+    const int np = fft_plan(p.n, radices);
     PYMD_REQUIRE(np == 1 || (bufA && (np == 2 || bufB)), "fft: work buffers required");
     int Ns = 1;
     const void* cur = src;
@@ -249,7 +394,29 @@ int fft_columns(const void* src, void* dst, double2* bufA, double2* bufB, const 
         const long long cw = last ? p.dst_cw : 0, cs = last ? p.dst_cs : 0;
         // ifft(x) = conj(fft(conj(x))): conjugate on the first load and on the last store
         const int ci = (p.sign > 0 && first) ? 1 : 0, co = (p.sign > 0 && last) ? 1 : 0;
-        if (R >= 16) {
+        if (R == 128) {
+            long long xb = (p.cols + 31) / 32;
+            if (xb > 148) xb = 148;
+            PYMD_REQUIRE(p.n / R <= 65535, "fft: length %d too long for the fused pass", p.n);
+            dim3 grid((unsigned)xb, p.n / R);
+            constexpr int smem128 = 128 * 32 * sizeof(double2);
+#define PYMD_FFT128(LMODE, SMODE)                                                                                     \
+    do {                                                                                                              \
+        static bool cfg = false;                                                                                      \
+        if (!cfg) {                                                                                                   \
+            PYMD_CUDA_CHECK(cudaFuncSetAttribute(fft_pass128_kernel<LMODE, SMODE>,                                    \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem128));              \
+            cfg = true;                                                                                               \
+        }                                                                                                             \
+        fft_pass128_kernel<LMODE, SMODE><<<grid, dim3(32, 8), smem128, stream>>>(cur, out, p.n, Ns, p.cols, ci, co, tw, \
+                                                                                 p.n, sld, dld, sc, cw, cs);          \
+    } while (0)
+            if (lm == LOAD_C && sm == STORE_C) PYMD_FFT128(LOAD_C, STORE_C);
+            else if (lm == LOAD_C) PYMD_FFT128(LOAD_C, STORE_REAL_ROWS);
+            else if (sm == STORE_C) PYMD_FFT128(LOAD_REAL_PAIRS, STORE_C);
+            else PYMD_FFT128(LOAD_REAL_PAIRS, STORE_REAL_ROWS);
+#undef PYMD_FFT128
+        } else if (R >= 16) {
             long long xb = (p.cols + 31) / 32;
             if (xb > 148) xb = 148;                     // half a wave of column tiles per butterfly index
             PYMD_REQUIRE(p.n / R <= 65535, "fft: length %d too long for the fused pass", p.n);

@@ -26,6 +26,9 @@ struct FftPlan {
     long long dst_cw = 0, dst_cs = 0;
 };
 
+// number of passes (launches) fft_columns uses for a length-n transform
+int fft_num_passes(int n);
+
 // Runs all passes.  `src` is read by the first pass only (never written unless it aliases a
 // work buffer); intermediates ping-pong between bufA and bufB (each n*cols complex);
 // the result of the last pass lands in `dst` (complex [n][cols] for STORE_C).

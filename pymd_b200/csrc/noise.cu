@@ -255,15 +255,6 @@ int launch_shape(const double* lre, const double* lim, const double* xi, int nmd
     return PYMD_OK;
 }
 
-int fft_num_passes(int n) {                 // must mirror the plan of fft_columns (fft.cu)
-    int np = 0;
-    while (n >= 64) { ++np; n /= 64; }
-    if (n == 32) { ++np; n = 2; }
-    if (n == 16) { ++np; n = 1; }
-    if (n > 1) ++np;
-    return np;
-}
-
 }  // namespace pymd
 
 using namespace pymd;

@@ -107,6 +107,23 @@ def test_noise_pipeline_matches_oracle(cuda, case, batch):
             assert T.relerr(got[:, :, n], om.baths[b].noise) < 1e-12, (b, n)
 
 
+@pytest.mark.parametrize("nmd", [256, 4096, 16384, 32768])
+def test_noise_pipeline_long_records(cuda, nmd):
+    """Record lengths whose half-length FFT plans contain the fused radix-128 pass (128; 128 x 16;
+    128 x 64; 128 x 128), real-pair loads and real-row stores included."""
+    c = dict(T.CASES["ph2"], nmd=nmd)
+    batch = 2
+    m, j = T.device_md(c, batch)
+    xi, _ = T.draw(c, m, batch, seed=5)
+    om = T.oracle_md(c, j)
+    for b, bath in enumerate(m.baths):
+        bath.gnoi(xi=xi[0][b])
+        got = bath.noise.reshape(nmd, bath.nc, batch)
+        fac = bath.spectral_factors().as_oracle()
+        om.baths[b].gnoi(xi=xi[0][b][:, :, 1], factors=fac)
+        assert T.relerr(got[:, :, 1], om.baths[b].noise) < 1e-12, b
+
+
 def test_noise_with_reference_draw_order(cuda, golden):
     """The reference's own noise (golden, drawn sequentially from the legacy numpy RNG with
     no draw where an eigenvalue is <= 0): replay its draws into xi[f, i] and regenerate on the
@@ -130,7 +147,8 @@ def test_noise_with_reference_draw_order(cuda, golden):
         assert T.relerr(bath.noise, g["noise0_%d" % b]) < 1e-9
 
 
-@pytest.mark.parametrize("nmd,nd,batch", [(16, 6, 1), (64, 12, 5), (1024, 39, 33)])
+@pytest.mark.parametrize("nmd,nd,batch", [(16, 6, 1), (64, 12, 5), (1024, 39, 33), (256, 6, 3), (4096, 6, 3),
+                                          (16384, 3, 2), (32768, 3, 2)])
 def test_powerspec_matches_oracle(cuda, nmd, nd, batch):
     import torch
     from pymd_b200.spectrum import ensemble_powerspec, powerspec, powerspec2
