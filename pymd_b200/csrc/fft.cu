@@ -222,19 +222,20 @@ __global__ void __launch_bounds__(32 * R, 512 / (32 * R)) fft_pass2_kernel(const
     }
 }
 
-// Fused radix-128 pass: 128 = 8 (r1, the thread row) x 16 (r2, in registers).  blockDim = (32 columns, 8):
-// thread (x, r1) transforms inputs r1 + 8 r2 (r2 < 16) with one radix-16 butterfly, the 8 x 16 intermediate
-// goes through shared memory with the inner twiddles W_128^{r1 q2}, then the thread transforms q2 = ty and
-// q2 = ty + 8 over r1 (two radix-8 butterflies) and stores outputs q2 + 16 q1.  With it 2^14 = 128 x 128 is two
-// sweeps over HBM instead of three (64 x 64 x 4), 2^13 = 128 x 64 likewise.
+// Fused radix-128 pass: 128 = 16 (r1, the thread row) x 8 (r2, in registers).  blockDim = (32 columns, 16):
+// thread (x, r1) transforms inputs r1 + 16 r2 (r2 < 8) with one radix-8 butterfly; the 16 x 8 intermediate goes
+// through shared memory with the inner twiddles W_128^{r1 q2}; the length-16 transforms over r1 are then split
+// over two threads each (radix-2 decimation in frequency: thread row ty = q2 + 8 h forms x[r] +- x[r+8], times
+// W_16^r for h = 1, and runs a radix-8 butterfly), so all 16 warps stay busy and thread row ty stores outputs
+// ty + 16 m.  With it 2^14 = 128 x 128 is two sweeps over HBM instead of three (64 x 64 x 4), 2^13 = 128 x 64.
 template <int LM, int SM>
-__global__ void __launch_bounds__(256, 1) fft_pass128_kernel(const void* __restrict__ src, void* __restrict__ dst, int n,
+__global__ void __launch_bounds__(512, 1) fft_pass128_kernel(const void* __restrict__ src, void* __restrict__ dst, int n,
                                                              int Ns, long long cols, int conj_in, int conj_out,
                                                              const double2* __restrict__ tw, int twN, long long src_ld,
                                                              long long dst_ld, double scale, long long dst_cw,
                                                              long long dst_cs) {
-    constexpr int R1 = 8, R2 = 16, RR = 128;
-    extern __shared__ __align__(16) double2 ex128[];        // [RR][32]
+    constexpr int R1 = 16, R2 = 8, RR = 128;
+    extern __shared__ __align__(16) double2 ex128[];        // [r1 * 8 + q2][32]
     const int j = blockIdx.y;
     const int k = j % Ns;
     const int nr = n / RR;
@@ -246,9 +247,9 @@ __global__ void __launch_bounds__(256, 1) fft_pass128_kernel(const void* __restr
     const long long sbase = (long long)(j + (long long)ty * nr) * srow * src_ld + tx;
     const long long sstep = (long long)R1 * nr * srow * src_ld;
     const long long drow = SM == STORE_C ? 1 : 2;
-    const long long dbase = ((long long)(j / Ns) * Ns * RR + k + (long long)ty * Ns) * drow * dst_ld;   // q2 = ty, q1 = 0
-    const long long dhalf = (long long)R1 * Ns * drow * dst_ld;                                          // q2 += 8
-    const long long dstep = (long long)R2 * Ns * drow * dst_ld;                                          // q1 += 1
+    const long long dbase = ((long long)(j / Ns) * Ns * RR + k + (long long)ty * Ns) * drow * dst_ld;   // output ty + 16 m
+    const long long dstep = (long long)R1 * Ns * drow * dst_ld;
+    const int q2 = ty & 7, hodd = ty >> 3;
     auto issue = [&](double2 (&d)[R2], long long c0) {
         const bool ok = c0 + tx < cols;
 #pragma unroll
@@ -264,8 +265,6 @@ __global__ void __launch_bounds__(256, 1) fft_pass128_kernel(const void* __restr
             }
         }
     };
-    // one CTA per SM with the next tile's 16 loads per thread in flight (measured faster than two CTAs of 128
-    // registers without the prefetch: 7.35 vs 7.88 ms for 2^14 x 21120 columns)
     double2 v[R2], nx[R2];
     long long c0 = (long long)blockIdx.x * 32;
     issue(nx, c0);
@@ -280,32 +279,43 @@ __global__ void __launch_bounds__(256, 1) fft_pass128_kernel(const void* __restr
             if (conj_in) v[r2].y = -v[r2].y;
             if (Ns > 1 && (r2 > 0 || ty > 0)) v[r2] = cmul(v[r2], tw[tw0 + r2 * twd]);
         }
-        butterfly<16>(v);
+        butterfly<8>(v);                                // v[q2'] over r2
         __syncthreads();                                // previous tile consumed
 #pragma unroll
-        for (int q2 = 0; q2 < R2; ++q2)
-            ex128[(ty * R2 + q2) * 32 + tx] = (q2 > 0 && ty > 0) ? cmul(v[q2], tw[q2 * twi]) : v[q2];
+        for (int q = 0; q < R2; ++q)
+            ex128[(ty * R2 + q) * 32 + tx] = (q > 0 && ty > 0) ? cmul(v[q], tw[q * twi]) : v[q];
         __syncthreads();
+        {
+            const double h = 0.70710678118654752440, c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            double2 u[R1];
+            for (int r = 0; r < 8; ++r) {
+                const double2 lo = ex128[(r * R2 + q2) * 32 + tx], hi = ex128[((r + 8) * R2 + q2) * 32 + tx];
+                v[r] = hodd ? csub(lo, hi) : cadd(lo, hi);
+            }
+            if (hodd) {                                  // times W_16^r
+                v[1] = cmul(v[1], make_double2(c1, -s1));
+                v[2] = make_double2(h * (v[2].x + v[2].y), h * (v[2].y - v[2].x));
+                v[3] = cmul(v[3], make_double2(s1, -c1));
+                v[4] = mul_mi(v[4]);
+                v[5] = cmul(v[5], make_double2(-s1, -c1));
+                v[6] = make_double2(h * (v[6].y - v[6].x), -h * (v[6].x + v[6].y));
+                v[7] = cmul(v[7], make_double2(-c1, -s1));
+            }
+            butterfly<8>(v);                            // v[m]: output (q2 + 8 hodd) + 16 m = ty + 16 m
+        }
+        if (ok) {
+            const double si = conj_out ? -scale : scale;
+            if (SM == STORE_C) {
+                double2* dp = static_cast<double2*>(dst) + dbase + col;
 #pragma unroll
-            for (int r1 = 0; r1 < R1; ++r1) u[r1] = ex128[(r1 * R2 + ty + 8 * hf) * 32 + tx];
-            butterfly<8>(u);                            // u[q1]: output (ty + 8 hf) + 16 q1
-            if (ok) {
-                const double si = conj_out ? -scale : scale;
-                if (SM == STORE_C) {
-                    double2* dp = static_cast<double2*>(dst) + dbase + hf * dhalf + col;
+                for (int m = 0; m < 8; ++m) __stcs(dp + m * dstep, make_double2(scale * v[m].x, si * v[m].y));
+            } else {
+                const long long dc = dst_cw ? (col / dst_cw) * dst_cs + col % dst_cw : col;
+                double* dp = static_cast<double*>(dst) + dbase + dc;
 #pragma unroll
-                    for (int q1 = 0; q1 < R1; ++q1) __stcs(dp + q1 * dstep, make_double2(scale * u[q1].x, si * u[q1].y));
-                } else {
-                    const long long dc = dst_cw ? (col / dst_cw) * dst_cs + col % dst_cw : col;
-                    double* dp = static_cast<double*>(dst) + dbase + hf * dhalf + dc;
-#pragma unroll
-                    for (int q1 = 0; q1 < R1; ++q1) {
-                        dp[q1 * dstep] = scale * u[q1].x;
-                        dp[q1 * dstep + dst_ld] = si * u[q1].y;
-                    }
+                for (int m = 0; m < 8; ++m) {
+                    dp[m * dstep] = scale * v[m].x;
+                    dp[m * dstep + dst_ld] = si * v[m].y;
                 }
             }
         }
@@ -408,7 +418,7 @@ int fft_columns(const void* src, void* dst, double2* bufA, double2* bufB, const 
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem128));              \
             cfg = true;                                                                                               \
         }                                                                                                             \
-        fft_pass128_kernel<LMODE, SMODE><<<grid, dim3(32, 8), smem128, stream>>>(cur, out, p.n, Ns, p.cols, ci, co, tw, \
+        fft_pass128_kernel<LMODE, SMODE><<<grid, dim3(32, 16), smem128, stream>>>(cur, out, p.n, Ns, p.cols, ci, co, tw, \
                                                                                  p.n, sld, dld, sc, cw, cs);          \
     } while (0)
             if (lm == LOAD_C && sm == STORE_C) PYMD_FFT128(LOAD_C, STORE_C);
