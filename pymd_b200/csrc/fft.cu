@@ -57,32 +57,6 @@ __device__ __forceinline__ void butterfly<8>(double2* v) {
     }
 }
 
-// 16 = 4 x 4: DFT4 over b of x[a + 4 b], twiddle W16^{a q}, DFT4 over a -> X[q + 4 p]
-template <>
-__device__ __forceinline__ void butterfly<16>(double2* v) {
-    const double h = 0.70710678118654752440, c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;
-    double2 t[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        double2 u[4] = {v[a], v[a + 4], v[a + 8], v[a + 12]};
-        butterfly<4>(u);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) t[a][q] = u[q];
-    }
-    const double2 w1 = make_double2(c1, -s1), w2 = make_double2(h, -h), w3 = make_double2(s1, -c1);
-    const double2 w6 = make_double2(-h, -h), w9 = make_double2(-c1, s1);
-    t[1][1] = cmul(t[1][1], w1); t[1][2] = cmul(t[1][2], w2); t[1][3] = cmul(t[1][3], w3);
-    t[2][1] = cmul(t[2][1], w2); t[2][2] = mul_mi(t[2][2]);   t[2][3] = cmul(t[2][3], w6);
-    t[3][1] = cmul(t[3][1], w3); t[3][2] = cmul(t[3][2], w6); t[3][3] = cmul(t[3][3], w9);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        double2 u[4] = {t[0][q], t[1][q], t[2][q], t[3][q]};
-        butterfly<4>(u);
-#pragma unroll
-        for (int pp = 0; pp < 4; ++pp) v[q + 4 * pp] = u[pp];
-    }
-}
-
 template <int R>
 __global__ void __launch_bounds__(128) fft_pass_kernel(const void* __restrict__ src, void* __restrict__ dst,
                                                        int n, int Ns, long long cols, int conj_in, int conj_out,
@@ -406,7 +380,8 @@ int fft_columns(const void* src, void* dst, double2* bufA, double2* bufB, const 
         const int ci = (p.sign > 0 && first) ? 1 : 0, co = (p.sign > 0 && last) ? 1 : 0;
         if (R == 128) {
             long long xb = (p.cols + 31) / 32;
-            if (xb > 148) xb = 148;
+            if (xb > 74) xb = 74;                       // one CTA per SM: two butterfly indices per wave, twice the tiles
+                                                        // per CTA for the register prefetch (6.9 vs 7.2 ms for 2^14 x 21120)
             PYMD_REQUIRE(p.n / R <= 65535, "fft: length %d too long for the fused pass", p.n);
             dim3 grid((unsigned)xb, p.n / R);
             constexpr int smem128 = 128 * 32 * sizeof(double2);
