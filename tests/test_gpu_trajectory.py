@@ -492,6 +492,29 @@ def test_example_driver_with_device_setup_and_harmonic_check(cuda, tmp_path, mon
     assert np.allclose(tab[:, 1], m.harmonic["PP"], rtol=1e-6)
 
 
+def test_thermal_conductance_example_matches_landauer(cuda, tmp_path, monkeypatch):
+    """examples/thermal_conductance.py (the reference's thermal.py flow: leads at T +- dT/2, kappa from the
+    lead currents, thermal.py:183-201) with the per-temperature set-up on the GPU: for a harmonic junction
+    the quantum Langevin conductance must reproduce Landauer's formula evaluated with the same discrete
+    memory kernels.  1024 trajectories, two steady-state segments: statistical error 1.6 %, measured
+    deviation -6.6 % (noise spectrum and truncated friction kernel are not an exact
+    fluctuation-dissipation pair, as in the reference); asserted to 12 %."""
+    import importlib.util
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("thermal_conductance", os.path.join(root, "examples", "thermal_conductance.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = str(tmp_path / "thermal")
+    monkeypatch.setattr(sys, "argv", ["thermal_conductance.py", "--temps", "150", "--batch", "1024", "--outdir", out])
+    rows = mod.main()
+    T_, kappa, err, kland = rows[0]
+    assert kland > 0 and kappa > 0 and err < 0.03 * kland
+    assert abs(kappa / kland - 1.0) < 0.12
+    assert os.path.isfile(os.path.join(out, "kappa.150.0.dat"))
+
+
 @pytest.mark.parametrize("seed", range(8))
 def test_randomized_configurations(cuda, seed, monkeypatch):
     """Random junction shapes around the path-selection boundaries (nd up to 63, leads of 3..18 dofs so
