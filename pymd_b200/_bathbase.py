@@ -70,7 +70,8 @@ class BathBase(object):
 
     def spectral_factors(self):
         """Cached (lam, U, L) of the noise covariance; recomputed when T/bias/dt/nmd change."""
-        key = self._factor_key()
+        dev, _ = self._setup_target()
+        key = (self._factor_key(), None if dev is None else str(dev), self.setup_keep_vectors)
         if self._factors is None or self._factors_key != key:
             self._factors = self._spectral_factors()
             self._factors_key = key

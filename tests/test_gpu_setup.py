@@ -189,9 +189,9 @@ def test_trajectory_parity_with_device_factors(cuda):
     B = 3
     m, j = T.device_md(c, B)
     for bath in m.baths:
-        bath.setup_device = True
+        bath.spectral_factors()                       # host factors are cached ...
+        bath.setup_device = True                      # ... and dropped when the set-up target changes
         bath.setup_keep_vectors = True
-        bath._factors = None
         if getattr(bath, "ml", 1) > 1:
             host_kernel = np.array(bath.kernel)
             bath.gmem()
