@@ -193,3 +193,38 @@ def test_bath_selfenergy_and_noise_spectrum_helpers():
     d = phbath(300.0, [0], 0.03, 40, 8.0, 64)
     d.gmem()
     assert relmax(d.effective_selfenergy(w), -1j * w[:, None, None] * d.kernel[0][None]) < 1e-15
+
+
+def test_langevin_current_formula_reduces_to_landauer():
+    """examples/thermal_conductance.py: the stationary current of the linear Langevin equation,
+    J_b = 2 int dw/2pi Re Tr[i w D (S_b + S D^+ Sigma_b^+)], conserves energy (J_L + J_R = 0) and equals
+    Landauer's formula when the noise spectra are the fluctuation-dissipation partners
+    S_b = (n_b + 1/2) Gamma_b of the friction kernels; with the spectra the baths really generate it
+    differs by a few per cent (the number the GPU test compares the MD ensemble with)."""
+    import importlib.util
+    import os
+    import types
+    from pymd_b200.functions import bose
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("thermal_conductance_cpu", os.path.join(root, "examples", "thermal_conductance.py"))
+    tc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tc)
+    j = synth.synth(12, 3, 3, seed=4)
+    phl = phbath(160.0, j.cats_l, 0.03, 200, 8.0, 1024, ml=100, sig=j.SigL, gwl=j.wl)
+    phr = phbath(140.0, j.cats_r, 0.03, 200, 8.0, 1024, ml=100, sig=j.SigR, gwl=j.wl)
+    for b in (phl, phr):
+        b.gmem()
+    m = types.SimpleNamespace(baths=[phl, phr], nph=12, dyn=j.DynMat)     # what the two functions read from md
+    jland, w, trans = tc.landauer_current(m, 160.0, 140.0, nw=1500)
+    assert jland > 0 and trans.max() < 3.0 + 1e-6 and trans.min() > -1e-9   # three channels at most
+    jl, jr = tc.langevin_current(m, nw=1500)
+    assert abs(jl + jr) < 1e-12 * abs(jl)
+    assert 0.0 < abs(0.5 * (jl - jr) / jland - 1.0) < 0.15                  # not an exact FDT pair
+    for b in (phl, phr):                                                    # make it one
+        def fdt(wv, b=b):
+            s = b.effective_selfenergy(wv)
+            gam = 1j * (s - np.conj(np.transpose(s, (0, 2, 1))))
+            return (bose(wv, b.T) + 0.5)[:, None, None] * gam
+        b.noise_spectrum = fdt
+    jl, jr = tc.langevin_current(m, nw=1500)
+    assert abs(0.5 * (jl - jr) / jland - 1.0) < 1e-10 and abs(jl + jr) < 1e-12 * abs(jl)
