@@ -147,6 +147,9 @@ int pymd_powerspec(const double* traj_dev, int nmd, int nd, int ldb, int nvalid,
 int pymd_fft_columns(double* data_dev, int n, long long cols, int sign, void* work_dev, void* stream);
 /* bytes of scratch pymd_fft_columns needs */
 size_t pymd_fft_work_bytes(int n, long long cols);
+/* sweeps over HBM (kernel launches) of a length-n transform: the plan combines fused radix-128/64/16
+ * passes and radix-8/4/2 passes for the fewest sweeps (1 up to n = 128 except 32, 2 up to 2^14, 3 up to 2^17); -1 if n is not a power of two */
+int pymd_fft_num_passes(int n);
 
 /* General tensor-core product used by tests and by setup-on-device:
  * Y[M][ldb] = alpha * A_host-uploaded... (device pointers, A row-major [M][lda], lda % 32 == 0) */

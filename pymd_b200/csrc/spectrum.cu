@@ -131,6 +131,11 @@ int pymd_powerspec(const double* traj, int nmd, int nd, int ldb, int nvalid, dou
 
 size_t pymd_fft_work_bytes(int n, long long cols) { return 2 * (size_t)n * cols * sizeof(double2); }
 
+int pymd_fft_num_passes(int n) {
+    if (n < 2 || (n & (n - 1)) != 0) return -1;
+    return fft_num_passes(n);
+}
+
 int pymd_fft_columns(double* data, int n, long long cols, int sign, void* work, void* stream) {
     PYMD_REQUIRE(data && work, "fft_columns: null argument");
     PYMD_REQUIRE(sign == 1 || sign == -1, "fft_columns: sign must be +1 or -1");

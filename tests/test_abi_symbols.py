@@ -48,3 +48,25 @@ def test_errors_are_reported_not_swallowed():
     assert rc < 0 and b"multiple of 32" in lib.pymd_last_error()
     with pytest.raises(_lib.PymdError):
         _lib.call("pymd_ctx_create", 0, 32, 1, 1.0, 16, 0, ctypes.byref(ctx))
+
+
+def test_fft_plan_lengths():
+    """Host-side planning of the column FFT: fewest sweeps over HBM (fused radix-128/64/16 passes first)."""
+    from pymd_b200 import _lib
+    lib = _lib.load()
+    want = {2: 1, 4: 1, 8: 1, 16: 1, 32: 2, 64: 1, 128: 1, 256: 2, 1024: 2, 2048: 2, 4096: 2, 8192: 2, 16384: 2,
+            32768: 3, 65536: 3, 131072: 3}
+    for n, np_ in want.items():
+        assert lib.pymd_fft_num_passes(n) == np_, n
+    assert lib.pymd_fft_num_passes(0) == -1 and lib.pymd_fft_num_passes(96) == -1
+
+
+def test_setup_kernel_size_limits():
+    """Shared-memory limits of the set-up kernels (host-side queries, no GPU needed)."""
+    from pymd_b200 import _lib
+    lib = _lib.load()
+    assert lib.pymd_harmonic_max_n() >= 96                   # config 3's nd
+    assert lib.pymd_eigh_max_n(1) >= 96 and lib.pymd_eigh_max_n(0) >= 118
+    assert lib.pymd_eigh_work_bytes(100, 60, 1) == 0         # fits shared memory twice: no scratch
+    assert lib.pymd_eigh_work_bytes(100, 96, 1) == 100 * 96 * 96 * 16
+    assert lib.pymd_eigh_work_bytes(100, 500, 1) == 0        # unsupported size: nothing to allocate
