@@ -77,7 +77,10 @@ class BathBase(object):
             self._factors_key = key
         return self._factors
 
-    def _gnoi(self, xi=None):
+    def _gnoi(self, xi=None, segment=None):
+        """``segment``: index of the md.Run segment the noise is for; selects the Philox stream, so that the
+        realisation depends only on (seed, bath, segment, trajectory) and a resumed run repeats the uninterrupted
+        one.  Hand-driven loops (segment=None) count the calls instead."""
         import torch
         if self.dt is None or self.nmd is None:
             raise ValueError("%s.gnoi: the md information dt and nmd are not set!" % type(self).__name__)
@@ -87,13 +90,14 @@ class BathBase(object):
         if xi is None:
             if self._seed is None:
                 self._seed = int(N.random.randint(0, 2 ** 31 - 1))
+            sid = self._ngnoi if segment is None else int(segment)
             x = _noise.white_noise(nf, self.nc, self.ldb, self._seed,
-                                   ((self._index + 1) << 16) ^ self._ngnoi, self._traj0, dev)
+                                   ((self._index + 1) << 16) ^ (sid & 0xFFFF), self._traj0, dev)
             if self.batch < self.ldb:
                 x[:, :, self.batch:] = 0.0          # padding trajectories stay at rest
         else:
             x = _noise._as_device_xi(xi, nf, self.nc, self.batch, self.ldb, dev)
-        self._ngnoi += 1
+        self._ngnoi = self._ngnoi + 1 if segment is None else int(segment) + 1
         if self._noise_dev is None or tuple(self._noise_dev.shape) != (self.nmd, self.nc, self.ldb):
             self._noise_dev = torch.empty((self.nmd, self.nc, self.ldb), dtype=torch.float64, device=dev)
         _noise.generate(fac, x, self.dt, self.nmd, out=self._noise_dev)

@@ -82,7 +82,9 @@ struct FusedParams {
     int pair_b[4], pair_mt[4];    // fused2: (bath, m8 tile) owned by each bath warp, -1 = none
     double cmax;              // max_i |c_i| of the (single) constraint vector
     int smem_doubles;
-    long long* timing;        // debug: [grid][8] accumulated clock64 deltas per phase (PYMD_FUSED_TIMING)
+#ifdef PYMD_FUSED_TIMING
+    long long* timing;        // [32] accumulated clock64 deltas per phase (tools/build_timing.sh builds only)
+#endif
     FusedBath b[FB_MAX];
 };
 
@@ -930,6 +932,13 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
     }
     int nbuf = 0;
     int tn = (int)(P.t0 % P.nmd);
+#ifdef PYMD_FUSED_TIMING
+    long long t2acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t2last = clock64();
+#define TICK2(i) { const long long _n = clock64(); t2acc[i] += _n - t2last; t2last = _n; }
+#else
+#define TICK2(i)
+#endif
 
     if (roww) {
     // ================================================================== ROW WARPS
@@ -1008,7 +1017,9 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
     zero_acc<NT>(uq);
     zero_acc<NT>(fb);
     for (int g0 = 0; g0 < P.nsteps; g0 += FT) {
+        TICK2(7)
         if (P.mid) mid_phase<NT, RW2 * 32>(P, sm, P.off_xp1, min(FT, P.nsteps - g0), g0, col0);   // block starts find the head buffers in their initial roles
+        TICK2(6)
         if (g0 == 0) {
             smem_matvec2(sm + xq, fpot, uq);
 #pragma unroll
@@ -1034,6 +1045,7 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
                 load_direct(tn_cur, nzr);
                 zero_acc<NT>(hA);
                 matvec1<NT, true>(aM, MAXKS, sm + xpc, LD, hA, lr, lc);
+                TICK2(0)
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
                     const int n = 8 * j + 2 * lc;
@@ -1072,7 +1084,9 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
                     }
                 }
             }
+            TICK2(1)
             cta_barrier();                                                      // ---- S2 (all warps)
+            TICK2(5)
             nbuf ^= 1;
             {
                 { const int tmp = xpc; xpc = xpn; xpn = tmp; }      // xpc: p(t+1/2)
@@ -1085,6 +1099,7 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
                     zero_acc<NT>(uq);
                     smem_matvec2(sm + xq, aDq, uq);
                     matvec1<NT, true>(aM, MAXKS, sm + xpc, LD, hB, lr, lc);
+                    TICK2(2)
                     double p1v[NT][2];
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
@@ -1109,13 +1124,16 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
                         for (int j = 0; j < NT; ++j) st2(&sm[xpn + own + 8 * j], p1v[j][0], p1v[j][1]);
                     }
                 }
+                TICK2(3)
                 row_barrier();                                                  // ---- S3 (row warps)
+                TICK2(5)
                 { const int tmp = xpc; xpc = xpn; xpn = tmp; }      // xpc: p1, xpn: p(t+1/2)
                 // ============ round C: third evaluation, head p1 -> p(t+1), constraint ============
                 {
                     double hC[NT][2];
                     zero_acc<NT>(hC);
                     matvec1<NT, true>(aM, MAXKS, sm + xpc, LD, hC, lr, lc);
+                    TICK2(4)
                     double pn[NT][2], qn[NT][2];
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
@@ -1145,7 +1163,9 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
                         }
 #pragma unroll
                         for (int gg = 0; gg < NG; ++gg) sm[P.off_conp + ((8 * gg + lr) * RW2 + w) * 4 + lc] = part[gg];
+                        TICK2(3)
                         row_barrier();                                          // ---- S4 (row warps)
+                        TICK2(5)
 #pragma unroll
                         for (int gg = 0; gg < NG; ++gg) {
                             double sum = 0.0;
@@ -1197,11 +1217,17 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
                     }
                 }
             }
+            TICK2(3)
             cta_barrier();                                                      // ---- S1 (all warps)
+            TICK2(5)
             { const int tmp = xpc; xpc = xpn; xpn = tmp; }                      // xpc: p(t+1)
             tn = tn1;
         }
     }
+#ifdef PYMD_FUSED_TIMING
+    if (P.timing && lane == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(&P.timing[i]), (unsigned long long)t2acc[i]);
+#endif
     // ------------------------------------------------------------------ epilogue
     if (live) {
 #pragma unroll
@@ -1245,8 +1271,10 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
     // L2 prefetch of the noise rows two steps ahead: the 128 bath threads cover the 128-byte lines of all rows
     cta_barrier();
     for (int g0 = 0; g0 < P.nsteps; g0 += FT) {
+        TICK2(7)
         if (P.mid) mid_phase<NT, NTH2, false>(P, sm, P.off_xp1, min(FT, P.nsteps - g0), g0, col0);
         if (g0 == 0) cta_barrier();
+        TICK2(6)
         const int gend = min(P.nsteps, g0 + FT);
         for (int g = g0; g < gend; ++g) {
             const int s = g - g0;
@@ -1349,7 +1377,9 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
                     }
                 }
             }
+            TICK2(0)
             cta_barrier();                                                      // ---- S2 (all warps)
+            TICK2(5)
             nbuf ^= 1;
             {
                 // currents and kinetic energy of time t: fixed-order sum of the per-warp slots
@@ -1362,10 +1392,16 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
                     else P.etot[(size_t)tn_cur * ldb + col0 + n] = 0.5 * sum;
                 }
             }
+            TICK2(1)
             cta_barrier();                                                      // ---- S1 (all warps)
+            TICK2(5)
             tn = tn1;
         }
     }
+#ifdef PYMD_FUSED_TIMING
+    if (P.timing && lane == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(&P.timing[16 + i]), (unsigned long long)t2acc[i]);
+#endif
     }
     for (int n = tid; n < N; n += NTH2) P.samef[col0 + n] = 1;
 }
@@ -1622,8 +1658,8 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
     const int grid = c->ldb / (8 * NT);
 #ifdef PYMD_FUSED_TIMING
     static long long* d_timing = nullptr;
-    if (!d_timing) { cudaMalloc(&d_timing, 10 * sizeof(long long)); }
-    cudaMemsetAsync(d_timing, 0, 10 * sizeof(long long), st);
+    if (!d_timing) { cudaMalloc(&d_timing, 32 * sizeof(long long)); }
+    cudaMemsetAsync(d_timing, 0, 32 * sizeof(long long), st);
     fp.timing = d_timing;
 #endif
     fp.nosplit = (getenv("PYMD_FUSED_SPLIT") && atoi(getenv("PYMD_FUSED_SPLIT")) == 0) ? 1 : 0;
@@ -1704,8 +1740,21 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
     }
 #ifdef PYMD_FUSED_TIMING
     {
-        long long h[10];
+        long long h[32];
         cudaMemcpy(h, fp.timing, sizeof(h), cudaMemcpyDeviceToHost);
+        if (use2) {
+            // only the LAST launch of this call (the counters are cleared per call, accumulated over its launches)
+            const double nr = (double)grid * RW2 * nsteps, nbw = (double)grid * (TW2 - RW2) * nsteps;
+            const char* rn[8] = {"A.matvec", "A.elem", "B.matvec", "B.elem/C.elem", "C.matvec", "barrier-wait", "mid", "pre-mid"};
+            const char* bn[8] = {"bath.work", "bath.reduce", "-", "-", "-", "barrier-wait", "mid(parked)", "pre-mid"};
+            double tr = 0, tb = 0;
+            fprintf(stderr, "[fused2 timing] row warps, cycles per warp-step:");
+            for (int i = 0; i < 8; ++i) { fprintf(stderr, " %s=%.0f", rn[i], h[i] / nr); tr += h[i] / nr; }
+            fprintf(stderr, " total=%.0f\n[fused2 timing] bath warps:", tr);
+            for (int i = 0; i < 8; ++i) if (bn[i][0] != '-') { fprintf(stderr, " %s=%.0f", bn[i], h[16 + i] / nbw); tb += h[16 + i] / nbw; }
+            fprintf(stderr, " total=%.0f\n", tb);
+            return PYMD_OK;
+        }
         const double nw = (double)grid * FW * nsteps;
         const char* nm[10] = {"A.matvec", "A.elementwise", "A.items", "barrier-wait", "B.matvec", "B.elementwise", "C.matvec", "C.elementwise", "mid", "pre-mid"};
         double tot = 0; for (int i = 0; i < 10; ++i) tot += h[i] / nw;

@@ -187,8 +187,18 @@ class md(object):
                 "outside the GPU stepping path; attach a dynamical matrix instead")
         if self.nph is None:
             raise ValueError("md: number of degrees of freedom unknown (give axyz, syslist or dyn)")
+        key = self._operand_key()
+        saved = None
         if self._ctx is not None:
-            return
+            if key == self._ctx_key:
+                return
+            # an operand changed after the context was built (ebath.setbias, a re-run gmem()/SetMemlen, a new
+            # constraint): the reference reads bias, kernel and constraint live on every force call
+            # (ebath.py:191-194, phbath.py:197-201, md.py:355-358), so rebuild the device operands and keep
+            # the velocity history
+            saved = self._history_dev()
+            self._drop_ctx()
+        self._ctx_key = key
         import torch
         lib = _lib.load()
         dev = self._dev()
@@ -231,6 +241,33 @@ class md(object):
             if self.record_fhis:
                 self._fhis[b] = self._zeros(self.nmd, bath.nc, ldb)
         self._savepq_alloc()
+        if saved:
+            for b, buf in saved.items():
+                bath = self.baths[b]
+                if bath.ml > 1 and tuple(buf.shape) == (bath.ml, bath.nc, ldb):
+                    _lib.call("pymd_history_set", ctx, b, buf.data_ptr(), int(bath.ml), _lib.stream_ptr())
+
+    def _operand_key(self):
+        """Everything pymd_bath_set / pymd_set_constraints copied into the context.  Arrays are identified by
+        object (gmem() and CheckEmat() make new ones); the small constraint matrix by value."""
+        con = None if self.constraint is None else N.asarray(self.constraint, dtype=N.float64).tobytes()
+        baths = tuple((id(b), b.nc, int(b.ml), id(b.kernel), getattr(b, "bias", None), id(getattr(b, "efric", None)),
+                       id(getattr(b, "exim", None)), id(getattr(b, "zeta1", None)), id(getattr(b, "zeta2", None)))
+                      for b in self.baths)
+        return (self.nph, self.ldb, float(self.dt), int(self.nmd), con, baths, bool(self.record_fhis))
+
+    def _history_dev(self):
+        """Device copies [ml][nc][ldb] (newest first) of every non-local bath's history, keyed by bath."""
+        out = {}
+        for b, bath in enumerate(self.baths):
+            if bath.ml > 1 and b in self._rings:
+                try:
+                    buf = self._zeros(bath.ml, bath.nc, self.ldb)
+                    _lib.call("pymd_history_get", self._ctx, b, buf.data_ptr(), int(bath.ml), _lib.stream_ptr())
+                    out[b] = buf
+                except _lib.PymdError:
+                    pass            # the ring no longer matches (ml grew): the history starts again from zero
+        return out
 
     def _savepq_alloc(self):
         if self._savepq and self.nph is not None:
@@ -342,7 +379,16 @@ class md(object):
 
     @property
     def fbaths(self):
-        return [None] * len(self.baths)
+        """Bath forces at the current state (md.py:380 leaves the last evaluated ones in md.fbaths): the first
+        force evaluation of the next step, for trajectory 0 of an ensemble.  Diagnostic, evaluated on demand."""
+        if self._ctx is None or any(b._noise_dev is None for b in self.baths):
+            return [None] * len(self.baths)
+        phis = self._history() if self.batch == 1 else self._history()[..., 0]
+        p = self.p if self.batch == 1 else self.p[..., 0]
+        q = self.q if self.batch == 1 else self.q[..., 0]
+        qhis = N.zeros_like(phis)
+        phis[0], qhis[0] = p, q
+        return [b.bforce(self.t, phis, qhis) for b in self.baths]
 
     @property
     def phis(self):
@@ -380,10 +426,10 @@ class md(object):
         e = 0.5 * (self._p[:, :self.batch] ** 2).sum(0).cpu().numpy()
         return float(e[0]) if self.batch == 1 else e
 
-    def initialise(self, r=None):
+    def initialise(self, r=None, stream=None):
         """Quantum initial displacements/velocities from the eigenmodes (md.py:253-290).
         ``r``: optional uniforms in [0,1), shape (nph,) or (nph, batch); by
-        default one Philox stream per trajectory."""
+        default one Philox stream per trajectory (``stream``: which one; default a per-object call counter)."""
         import torch
         self._ensure()
         self.t = 0
@@ -400,9 +446,11 @@ class md(object):
         rdev = self._zeros(nd, self.ldb)
         if r is None:
             seed = self.seed if self.seed is not None else int(N.random.randint(0, 2 ** 31 - 1))
-            _lib.call("pymd_philox_uniform", rdev.data_ptr(), nd, self.ldb, int(seed), 0xFFFF0000 + self._ninit,
+            sid = self._ninit if stream is None else int(stream)
+            _lib.call("pymd_philox_uniform", rdev.data_ptr(), nd, self.ldb, int(seed), 0xFFFF0000 + (sid & 0xFFFF),
                       self.traj0, _lib.stream_ptr())
-            self._ninit += 1
+            if stream is None:
+                self._ninit += 1
         else:
             ra = N.asarray(r, dtype=N.float64)
             if ra.shape == (nd,):
@@ -503,7 +551,7 @@ class md(object):
         """nrep consecutive segments of nmd steps each: fresh noise per segment, npie pieces
         with a checkpoint after each, running mean of the spectra, kappa/power text outputs
         (md.py:523-652)."""
-        self.initialise()
+        self.initialise(stream=0)
         self.ResetHis()
         self.curmean = N.zeros((self.nrep, len(self.baths)))
         for j in range(self.nrep):
@@ -515,7 +563,8 @@ class md(object):
                 ipie = state
             else:
                 for b in self.baths:
-                    b.gnoi()
+                    # noise realisation = f(seed, bath, segment): a resumed run draws what the uninterrupted one would
+                    b._gnoi(segment=j) if hasattr(b, "_gnoi") else b.gnoi()
                 self.ResetSavepq(self._savepq)
             for i in range(ipie + 1, self.npie):
                 self.steps(self.nmd // self.npie)
@@ -547,7 +596,7 @@ class md(object):
                     f.write("%f     %f \n" % (arr[i, 0], arr[i, 1]))
         if self.harmonic_check and self._savepq:
             # the reference's cross-check (harmonic.py:70-84: MD power2 ~ PP) beside the spectra
-            self.harmonic = h = self.HarmonicSpectra()
+            self.harmonic_spectra = h = self.HarmonicSpectra()
             k = N.rint(h["w"] / (2. * N.pi / self.dt / self.nmd)).astype(int)
             with open(os.path.join(self.outdir, "harmonic.%s.run%d.dat" % (self.T, j)), "w") as f:
                 for i in range(len(k)):
@@ -559,17 +608,44 @@ class md(object):
         reference's schema has no dimension for and go to ``MD<j>.npz``."""
         return os.path.join(self.outdir, ("MD%d.nc" if self.batch == 1 else "MD%d.npz") % j)
 
+    # ensembles whose full checkpoint (noise, saved trajectories, currents) would exceed this many bytes write a
+    # state-only checkpoint at the END of each segment instead of the reference's everything-after-every-piece
+    checkpoint_bytes_limit = 2 << 30
+
+    def _full_checkpoint_bytes(self):
+        per_traj = sum(b.nc + 1 for b in self.baths) + 1 + (2 * self.nph if self._savepq else 0)
+        if self.record_fhis:
+            per_traj += sum(b.nc for b in self.baths)
+        return 8 * self.nmd * per_traj * self.batch
+
     def dump(self, ipie, id):
-        """Checkpoint with the reference's variable names (md.py:654-705)."""
+        """Checkpoint with the reference's variable names (md.py:654-705).  The reference rewrites noise, saved
+        trajectories and currents after every piece; for a large ensemble that is hundreds of GB per dump, so
+        above ``checkpoint_bytes_limit`` only the end of a segment is checkpointed, and only what chaining the
+        next segment and skipping a finished one need (p, q, t, ipie, phis, power, power2, per-trajectory mean
+        currents and kinetic energy).  The noise of a segment is a pure function of (seed, bath, segment,
+        trajectory), so nothing else has to be stored to continue the run."""
         if not self.write_files:
             return
-        d = dict(power=self.power, power2=self.power2, energy=self.etot, p=self.p, q=self.q,
+        light = self.batch > 1 and self._full_checkpoint_bytes() > self.checkpoint_bytes_limit
+        if light and ipie + 1 < self.npie:
+            return
+        d = dict(power=self.power, power2=self.power2, p=self.p, q=self.q,
                  t=N.array([self.t]), ipie=N.array([ipie]), phis=self._history())
-        if self._savepq:
-            d["ps"], d["qs"] = self.ps, self.qs
-        for i, b in enumerate(self.baths):
-            d["noise%d" % i] = b.noise
-            d["cur%d" % i] = b.cur
+        if light:
+            d["light"] = N.array([1])
+            d["energy_mean"] = self._etot[:, :self.batch].mean(0).cpu().numpy()
+            for i, b in enumerate(self.baths):
+                d["curmean%d" % i] = b._cur_dev[:, :self.batch].mean(0).cpu().numpy()
+        else:
+            d["energy"] = self.etot
+            if self._savepq:
+                d["ps"], d["qs"] = self.ps, self.qs
+            for i, b in enumerate(self.baths):
+                d["noise%d" % i] = b.noise
+                d["cur%d" % i] = b.cur
+                if self.record_fhis and i in self._fhis:
+                    d["fhis%d" % i] = self._host(self._fhis[i])         # (nmd, nc[, batch]): the bath's dofs only
         name = self._ckpt_name(id)
         tmp = name + ".tmp" + os.path.splitext(name)[1]
         if self.batch == 1:
@@ -601,9 +677,9 @@ class md(object):
             for i, b in enumerate(self.baths):
                 put("noise%d" % i, d["noise%d" % i], ("nnmd", "n%d" % i))
                 put("cur%d" % i, d["cur%d" % i], ("nnmd",))
-                if self.record_fhis and i in self._fhis:
-                    full = N.zeros((self.nmd, self.nph))
-                    full[:, N.asarray(b.cids)] = N.asarray(self.fhis[i]).reshape(self.nmd, -1)
+                if "fhis%d" % i in d:
+                    full = N.zeros((self.nmd, self.nph))                # the reference's (nnmd, nph) layout
+                    full[:, N.asarray(b.cids)] = N.asarray(d["fhis%d" % i]).reshape(self.nmd, b.nc)
                     put("fhis%d" % i, full, ("nnmd", "nph"))
             if "ps" in d:
                 put("ps", d["ps"], ("nnmd", "nph"))
@@ -651,7 +727,13 @@ class md(object):
                 self.power, self.power2 = d["power"], d["power2"]
                 for i, b in enumerate(self.baths):
                     b.noise = d["noise%d" % i]
+                    b._ngnoi = j + 1
                     self._upload(b._alloc_cur(), d["cur%d" % i])
+                    if self.record_fhis and i in self._fhis and "fhis%d" % i in d:
+                        fh = N.asarray(d["fhis%d" % i])
+                        if fh.shape[:2] == (self.nmd, self.nph):        # MD<j>.nc stores the scattered layout
+                            fh = fh[:, N.asarray(b.cids)]
+                        self._upload(self._fhis[i], fh)
                 self.ResetSavepq(self._savepq)
                 if self._savepq and "ps" in d:
                     self._upload(self._ps, d["ps"])

@@ -26,12 +26,40 @@ CASES = {
                         ebath=True, bias=0.0, constraint=False, nce=30, leads=False),
     "ragged": dict(nd=21, ncl=6, ncr=9, seed=5, dt=4.0, nmd=32, T=77.0, dT=5.0, ml=19, nw=50, hwcut=0.03,
                    ebath=True, bias=0.2, constraint=False, nce=12),
+    # ---- BASELINE.json shapes (round-1 verdict: untested) ----
+    # config 3 exactly (examples/Alkane.py:19-24,154-155 as BASELINE states it): nd = 96, electron bath on all
+    # 96 dofs at bias 0.5, T = 0, one constraint -> csrc/local.cu at its upper size limit
+    "cfg3": dict(nd=96, ncl=3, ncr=3, seed=12, dt=2.0, nmd=64, T=0.0, dT=0.0, ml=1, nw=50, hwcut=0.03,
+                 ebath=True, bias=0.5, constraint=True, nce=96, leads=False),
+    # config 4 as shipped (examples/Au6_3x3.py:34-40,197-199,226,259): nd = 42, electron bath on 42 dofs,
+    # two 15-dof leads, ml = 100, dt = 15
+    "cfg4": dict(nd=42, ncl=15, ncr=15, seed=14, dt=15.0, nmd=128, T=300.0, dT=20.0, ml=100, nw=200, hwcut=0.03,
+                 ebath=True, bias=0.3, constraint=False, nce=42),
+    # nd > 96 with memory baths (the general path): sweep point and a reduced config-4 stretch shape
+    "nd129": dict(nd=129, ncl=30, ncr=30, seed=15, dt=4.0, nmd=64, T=300.0, dT=20.0, ml=200, nw=200, hwcut=0.03,
+                  ebath=False, constraint=False),
+    "cfg4s": dict(nd=150, ncl=81, ncr=81, seed=16, dt=8.0, nmd=64, T=150.0, dT=10.0, ml=300, nw=200, hwcut=0.03,
+                  ebath=False, constraint=True),
+    "nd129e": dict(nd=129, ncl=30, ncr=27, seed=17, dt=2.0, nmd=64, T=77.0, dT=5.0, ml=120, nw=100, hwcut=0.03,
+                   ebath=True, bias=0.4, constraint=True, nce=129),
+    # several non-orthogonal, unnormalised constraint vectors (md.py:739-762 takes every dot product with the
+    # un-projected vector; example_runlammps.py:61-65 uses six)
+    "con3": dict(nd=12, ncl=3, ncr=3, seed=21, dt=1.0, nmd=32, T=100.0, dT=0.0, ml=6, nw=30, hwcut=0.03,
+                 ebath=True, bias=0.3, constraint=False, nconstr=3),
+    "con6": dict(nd=60, ncl=15, ncr=15, seed=4, dt=1.0, nmd=64, T=300.0, dT=10.0, ml=100, nw=200, hwcut=0.03,
+                 ebath=True, bias=0.5, constraint=False, nconstr=6),
+    "con6_local": dict(nd=72, ncl=3, ncr=3, seed=8, dt=2.0, nmd=64, T=300.0, dT=0.0, ml=1, nw=50, hwcut=0.03,
+                       ebath=True, bias=0.5, constraint=False, nce=72, leads=False, nconstr=6),
 }
 
 
 def junction(c):
-    return synth.synth(c["nd"], c["ncl"], c["ncr"], seed=c["seed"], constraint=c["constraint"],
-                       nc_e=c.get("nce"))
+    j = synth.synth(c["nd"], c["ncl"], c["ncr"], seed=c["seed"], constraint=c["constraint"],
+                    nc_e=c.get("nce"))
+    if c.get("nconstr"):
+        rng = np.random.default_rng(c["seed"] + 99)
+        j.constr = 3.0 * rng.standard_normal((c["nconstr"], c["nd"]))      # non-orthogonal (overlaps ~ nd^-1/2), not normalised
+    return j
 
 
 def make_baths(mod_ph, mod_eb, j, c, **kw):

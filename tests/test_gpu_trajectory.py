@@ -487,9 +487,9 @@ def test_example_driver_with_device_setup_and_harmonic_check(cuda, tmp_path, mon
     assert m.t == 2048 and np.isfinite(m.p).all() and np.isfinite(m.power2).all()
     assert all(type(b.spectral_factors()).__name__ == "DeviceSpectralFactors" for b in m.baths)
     tab = np.loadtxt(os.path.join(out, "harmonic.300.0.run0.dat"))
-    assert tab.ndim == 2 and tab.shape[1] == 3 and len(tab) == len(m.harmonic["w"]) > 0
+    assert tab.ndim == 2 and tab.shape[1] == 3 and len(tab) == len(m.harmonic_spectra["w"]) > 0
     assert np.isfinite(tab).all() and (tab[:, 1] >= 0).all() and (tab[:, 2] >= 0).all()
-    assert np.allclose(tab[:, 1], m.harmonic["PP"], rtol=1e-6)
+    assert np.allclose(tab[:, 1], m.harmonic_spectra["PP"], rtol=1e-6)
 
 
 def test_thermal_conductance_example_matches_landauer(cuda, tmp_path, monkeypatch):
@@ -575,3 +575,61 @@ def test_local_bath_kernel_for_nd_up_to_96(cuda, case, batch, nt, monkeypatch):
     for n in sorted({0, batch - 1}):
         om, recs = T.run_oracle(c, j, m, xi, r, n, c["nmd"])
         compare(m, recs[0], n)
+
+
+def _parity_run(case, batch, mode, seed, chunks, trajs, tol=TOL, monkeypatch=None):
+    c = T.CASES[case]
+    m, j = T.device_md(c, batch, step_mode=mode)
+    xi, r = T.draw(c, m, batch, seed=seed)
+    m.initialise(r=r)
+    m.ResetHis()
+    for b, bath in enumerate(m.baths):
+        bath.gnoi(xi=xi[0][b])
+    m.ResetSavepq()
+    done = 0
+    for n in chunks:
+        n = min(n, c["nmd"] - done)
+        if n:
+            m.steps(n)
+            done += n
+    m.steps(c["nmd"] - done)
+    for n in trajs:
+        om, recs = T.run_oracle(c, j, m, xi, r, n, c["nmd"])
+        compare(m, recs[0], n, tol=tol)
+        pn = m.p if batch > 1 else m.p[..., None]
+        qn = m.q if batch > 1 else m.q[..., None]
+        assert T.relerr(pn[..., n], om.p) < tol and T.relerr(qn[..., n], om.q) < tol
+        hist = m.phis if batch > 1 else m.phis[..., None]
+        for bath in m.baths:
+            if bath.ml > 1:
+                assert T.relerr(hist[..., n][:bath.ml][:, bath.cids], om.phis[:bath.ml][:, bath.cids]) < tol
+    return m
+
+
+@pytest.mark.parametrize("case,batch,mode", [("cfg3", 2, 0), ("cfg3", 40, 0), ("cfg3", 3, 1),
+                                               ("cfg4", 2, 0), ("cfg4", 33, 2), ("cfg4", 3, 1)])
+def test_baseline_config_shapes(cuda, case, batch, mode):
+    """BASELINE.json configs 3 and 4 in their exact shapes: config 3 = nd 96 (the upper limit of csrc/local.cu),
+    electron bath on all 96 dofs at bias 0.5, T = 0, one constraint; config 4 as shipped = nd 42, electron bath
+    on 42 dofs, two 15-dof leads with ml = 100, dt = 15.  Auto path selection, the forced on-chip kernels and the
+    per-step pipeline against the oracle."""
+    _parity_run(case, batch, mode, seed=41, chunks=[1, 9, 31], trajs=sorted({0, batch - 1}))
+
+
+@pytest.mark.parametrize("case,batch", [("nd129", 2), ("nd129", 34), ("cfg4s", 2), ("nd129e", 3)])
+def test_large_junctions_with_memory_baths(cuda, case, batch):
+    """nd > 96 with memory baths (the general path; BASELINE configs 4-stretch and 5): nd = 129 with two 30-dof
+    leads and ml = 200, a reduced config-4 stretch shape (nd = 150, two 81-dof leads, ml = 300, one constraint)
+    and nd = 129 with an electron bath on all dofs at bias plus ragged leads -- 64 steps against the oracle."""
+    _parity_run(case, batch, 0, seed=43, chunks=[3, 8, 20], trajs=sorted({0, batch - 1}))
+
+
+@pytest.mark.parametrize("case,batch,mode", [("con3", 3, 0), ("con3", 3, 1), ("con6", 2, 0), ("con6", 35, 1),
+                                               ("con6_local", 9, 0)])
+def test_several_constraint_vectors(cuda, case, batch, mode):
+    """md.ApplyConstraint with 3 and 6 non-orthogonal, unnormalised vectors (md.py:739-762: every dot product is
+    taken with the un-projected vector, so the result is NOT the orthogonal projection; reproduced as is), on a
+    junction that would otherwise take the fused kernel, one that would take local.cu, and through the per-step
+    pipeline explicitly; also through md.initialise (constraints applied after every mode, md.py:284-285)."""
+    m = _parity_run(case, batch, mode, seed=47, chunks=[2, 7, 13], trajs=sorted({0, batch - 1}))
+    assert np.asarray(m.constraint).shape[0] == T.CASES[case]["nconstr"]
