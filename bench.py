@@ -1,20 +1,21 @@
 #!/usr/bin/env python3
 """Benchmark of the generalized-Langevin stepping path (BASELINE.json metric: trajectory-steps/s).
 
-  python bench.py --gpus N --steps K --warmup W              # our CUDA path, one rank per GPU
-  python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path on host cores
+  python bench.py --gpus N --steps K --warmup W                 # our CUDA path, one rank per GPU
+  python bench.py --impl reference --gpus N --steps K ...       # the reference's CPU path on host cores
+  python bench.py --config cfg3|cfg4|cfg4s|sweep:<nd>,<ml>,<B>[,<nc>]   # the other BASELINE.json configurations
 
-Workload (configs[1] of BASELINE.json, "cfg2"): AuBZ-like junction, nd = 60 system dofs, electron
-bath on all 60 dofs at finite bias (all five coupling matrices), left/right phonon baths on 15 dofs
-each with a 100-step memory kernel, one constraint vector, dt = 1, nmd = 2^15, an ensemble of 4096
-trajectories per GPU (weak scaling).  Synthetic junction (pymd_b200/synth.py): the reference's
-inputs (EPH.nc, ...) do not ship.
+Default workload (configs[1] of BASELINE.json, "cfg2"): AuBZ-like junction, nd = 60 system dofs, electron
+bath on all 60 dofs at finite bias (all five coupling matrices), left/right phonon baths on 15 dofs each with a
+100-step memory kernel, one constraint vector, dt = 1, nmd = 2^15, an ensemble of 4096 trajectories per GPU
+(weak scaling).  Synthetic junction (pymd_b200/synth.py): the reference's inputs (EPH.nc, ...) do not ship.
 
-One bench "step" = one piece of 256 md.vv steps for the whole resident ensemble (md.Run advances in
-pieces of nmd/npie steps, npie = 128, reference md.py:595-598).  `value` = trajectory-steps/s with
-the coloured noise already resident in HBM; `e2e` = the same metric through the md/phbath/ebath
-class API from host inputs: upload of the spectral factors, noise generation, 2^15 steps with
-trajectories saved, power spectra, device->host read of spectra and currents, (+ NCCL all-reduce).
+One bench "step" = `md_steps_per_step` consecutive md.vv steps for the whole resident ensemble, chosen so that a
+step takes ~0.15 s (8192 md steps for cfg2): with the driver's --steps 20 the timed region is seconds long and
+the clock sampler sees sustained FP64 load.  `value` = trajectory-steps/s with the coloured noise already
+resident in HBM; `e2e` = the same metric through the md/phbath/ebath class API from host inputs: upload of the
+spectral factors, noise generation, nmd steps with trajectories saved, power spectra, device->host read of
+spectra and currents (+ NCCL all-reduce), with a breakdown of where the time goes.
 """
 import os
 
@@ -35,8 +36,112 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 _emit = print
-CFG = dict(nd=60, ncl=15, ncr=15, seed=4, dt=1.0, T=300.0, dT=10.0, ml=100, nw=200, hwcut=0.03, bias=0.5)
-PIECE = 256
+CPU_ARM = "one trajectory per host core on a 256-row noise table (the md.vv loop cost depends neither on nmd nor on the ensemble size)"
+
+
+# ----------------------------------------------------------------------------- workloads
+def workload(name, gpus):
+    """BASELINE.json configurations as synthetic junctions.  Returns a dict with the
+    junction shape, the md parameters and the ensemble layout (weak: `batch` per GPU; strong: `total` split)."""
+    base = dict(seed=4, T=300.0, dT=10.0, nw=200, hwcut=0.03, bias=0.5, constraint=True, nce=None, leads=True,
+                scaling="weak", nmd_e2e=None)
+    if name == "cfg2":
+        c = dict(base, name="cfg2", nd=60, ncl=15, ncr=15, nce=60, ml=100, dt=1.0, nmd=2 ** 15, batch=4096,
+                 text="cfg2 AuBZ-like junction: nd=60, electron bath nc=60 at bias 0.5 eV (5 matrices), "
+                      "2 phonon baths nc=15 ml=100, 1 constraint, dt=1")
+    elif name == "cfg3":
+        # examples/Alkane.py as BASELINE states it: electron bath only, all 96 dofs, finite bias, T = 0,
+        # 8192 trajectories over the GPUs of the box (strong scaling: 1024 per GPU on 8)
+        c = dict(base, name="cfg3", nd=96, ncl=3, ncr=3, nce=96, leads=False, ml=1, dt=2.0, nmd=2 ** 14, T=0.0, dT=0.0,
+                 seed=12, scaling="strong", total=8192, batch=8192 // max(gpus, 1),
+                 text="cfg3 Alkane-like junction: nd=96, electron bath on all 96 dofs at bias 0.5 eV, T=0, 1 constraint, "
+                      "dt=2, 8192 trajectories in total")
+    elif name == "cfg4":
+        c = dict(base, name="cfg4", nd=42, ncl=15, ncr=15, nce=42, ml=100, dt=15.0, nmd=2 ** 13, batch=4096, seed=14,
+                 bias=0.3, dT=20.0, constraint=False,
+                 text="cfg4 Au6_3x3 junction as shipped: nd=42, electron bath nc=42, 2 phonon baths nc=15 ml=100, dt=15")
+    elif name == "cfg4s":
+        c = dict(base, name="cfg4s", nd=510, ncl=81, ncr=81, nce=None, ml=2000, dt=8.0, nmd=2 ** 12, batch=1024, seed=16,
+                 T=150.0, constraint=False,
+                 text="cfg4 stretch (BASELINE: large nd, Nmem=2000): nd=510, 2 phonon baths nc=81 ml=2000, dt=8")
+    elif name.startswith("sweep:"):
+        f = [int(x) for x in name.split(":")[1].split(",")]
+        nd, ml, B = f[0] // 3 * 3, f[1], f[2]
+        nc = f[3] if len(f) > 3 else max(3, (nd // 4) // 3 * 3)
+        c = dict(base, name=name, nd=nd, ncl=nc, ncr=nc, nce=None, ml=ml, dt=1.0, nmd=2 ** 12, batch=B, seed=9,
+                 constraint=False,
+                 text="config-5 sweep point: nd=%d, 2 phonon baths nc=%d ml=%d, nmd=4096" % (nd, nc, ml))
+    else:
+        raise SystemExit("unknown --config %s" % name)
+    return c
+
+
+def algorithmic(c):
+    """algorithmic flops and compulsory HBM bytes per trajectory-step of workload c."""
+    nd, ml = c["nd"], c["ml"]
+    ncs = [c["ncl"], c["ncr"]] if c["leads"] else []
+    heads = sum(3 * 2 * n * n for n in ncs)
+    taps = sum(2 * (ml - 1) * n * n for n in ncs) if ml > 1 else 0
+    if ml == 1 and ncs:
+        heads, taps = 0, 0
+    local = 0
+    if c["nce"]:
+        local = 6 * (2 if c["bias"] != 0 else 1) * c["nce"] ** 2
+    total = 2 * nd * nd + heads + taps + local
+    nbath = len(ncs) + (1 if c["nce"] else 0)
+    s_alg = 8 * (sum(ncs) + (c["nce"] or 0) + nbath + 1)
+    out = dict(total=total, dyn=2 * nd * nd, heads=heads, taps=taps, local=local, bytes=s_alg)
+    if c["name"] == "cfg2":
+        S, nc = 32, c["ncl"]
+        near = (S + 1) / 2.0 + 1.0                     # average number of taps inside the 32-step super-block
+        out["tail"] = 2 * (2 * nc * nc * (ml - 1 - near))          # taps older than the super-block: far field
+        out["fused"] = total - out["tail"]
+        # executed by the far kernel per trajectory-step: two real FFTs of length 128 per bath dof
+        # (2.5 n log2 n each) and 65 complex nc x nc products (8 flops per complex multiply-add)
+        out["far_executed"] = 2 * (2 * nc * 2.5 * 128 * 7 + 65 * 8 * nc * nc) / S
+    return out
+
+
+def default_piece(c):
+    """md steps per bench step: a power of two sized so that one step takes roughly 0.15 s (estimated from the
+    algorithmic flops at 30 TFLOP/s; both arms derive it from the configuration alone): 8192 for cfg2."""
+    fl = algorithmic(c)["total"] * c["batch"]
+    est = 0.15 * 30e12 / max(fl, 1.0)
+    piece = 2 ** int(round(np.log2(max(est, 1.0))))
+    return int(min(max(piece, 32), max(c["nmd"], 32)))
+
+
+def build(c, batch, traj0, savepq, seed, mode=0, nmd=None):
+    from pymd_b200 import synth
+    from pymd_b200.ebath import ebath
+    from pymd_b200.md import md
+    from pymd_b200.phbath import phbath
+    nmd = nmd or c["nmd"]
+    j = synth.synth(c["nd"], c["ncl"], c["ncr"], seed=c["seed"], constraint=c["constraint"], nc_e=c["nce"])
+    m = md(c["dt"], nmd, c["T"], axyz=j.axyz, harmonic=True, dyn=j.DynMat, savepq=savepq,
+           constr=None if j.constr is None else j.constr.copy(), batch=batch, seed=seed, traj0=traj0, step_mode=mode)
+    m.write_files = False
+    baths = []
+    if c["nce"]:
+        baths.append(ebath(j.cats_e, c["T"], c["dt"], nmd, wmax=1.0, nw=500, bias=c["bias"], efric=j.efric, exim=j.exim,
+                           exip=j.exip, zeta1=j.zeta1, zeta2=j.zeta2))
+    if c["leads"]:
+        pl = phbath(c["T"] + c["dT"] / 2, j.cats_l, c["hwcut"], c["nw"], c["dt"], nmd, ml=c["ml"], sig=j.SigL, gwl=j.wl)
+        pr = phbath(c["T"] - c["dT"] / 2, j.cats_r, c["hwcut"], c["nw"], c["dt"], nmd, ml=c["ml"], sig=j.SigR, gwl=j.wl)
+        pl.gmem(); pr.gmem()
+        baths += [pl, pr]
+    for b in baths:
+        m.AddBath(b)
+    return m
+
+
+def workload_config(a, c, piece):
+    nbytes = 8 * sum(x for x in ([c["nce"] or 0] + ([c["ncl"], c["ncr"]] if c["leads"] else []))) * c["batch"]
+    return dict(workload=c["text"] + ", nmd=%d" % c["nmd"], config=c["name"], batch_per_gpu=c["batch"],
+                md_steps_per_step=piece, nmd=c["nmd"], savepq=False,
+                l2="inputs exceed L2: every md step streams %.1f MB of noise rows per GPU (%.1f GB resident), 126 MB L2"
+                   % (nbytes / 2 ** 20, nbytes * c["nmd"] / 2 ** 30),
+                cpu_arm=CPU_ARM)
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
@@ -54,18 +159,22 @@ def _cpu_modules():
     return "port", O.md, O.phbath, O.ebath
 
 
-def _cpu_system(nmd_cpu, seed):
+def _cpu_system(c, nmd_cpu, seed):
     from pymd_b200 import synth
     kind, MD, PH, EB = _cpu_modules()
-    c = CFG
-    j = synth.synth(c["nd"], c["ncl"], c["ncr"], seed=c["seed"], constraint=True)
-    m = MD(c["dt"], nmd_cpu, c["T"], axyz=j.axyz, harmonic=True, dyn=j.DynMat, savepq=False, constr=j.constr.copy())
-    eb = EB(j.cats_e, c["T"], c["dt"], nmd_cpu, wmax=1.0, nw=500, bias=c["bias"], efric=j.efric, exim=j.exim,
-            exip=j.exip, zeta1=j.zeta1, zeta2=j.zeta2)
-    pl = PH(c["T"] + c["dT"] / 2, j.cats_l, c["hwcut"], c["nw"], c["dt"], nmd_cpu, ml=c["ml"], sig=j.SigL, gwl=j.wl)
-    pr = PH(c["T"] - c["dT"] / 2, j.cats_r, c["hwcut"], c["nw"], c["dt"], nmd_cpu, ml=c["ml"], sig=j.SigR, gwl=j.wl)
-    pl.gmem(); pr.gmem()
-    for b in (eb, pl, pr):
+    j = synth.synth(c["nd"], c["ncl"], c["ncr"], seed=c["seed"], constraint=c["constraint"], nc_e=c["nce"])
+    m = MD(c["dt"], nmd_cpu, c["T"], axyz=j.axyz, harmonic=True, dyn=j.DynMat, savepq=False,
+           constr=None if j.constr is None else j.constr.copy())
+    baths = []
+    if c["nce"]:
+        baths.append(EB(j.cats_e, c["T"], c["dt"], nmd_cpu, wmax=1.0, nw=500, bias=c["bias"], efric=j.efric, exim=j.exim,
+                        exip=j.exip, zeta1=j.zeta1, zeta2=j.zeta2))
+    if c["leads"]:
+        pl = PH(c["T"] + c["dT"] / 2, j.cats_l, c["hwcut"], c["nw"], c["dt"], nmd_cpu, ml=c["ml"], sig=j.SigL, gwl=j.wl)
+        pr = PH(c["T"] - c["dT"] / 2, j.cats_r, c["hwcut"], c["nw"], c["dt"], nmd_cpu, ml=c["ml"], sig=j.SigR, gwl=j.wl)
+        pl.gmem(); pr.gmem()
+        baths += [pl, pr]
+    for b in baths:
         m.AddBath(b)
     np.random.seed(seed)
     for b in m.baths:
@@ -76,43 +185,46 @@ def _cpu_system(nmd_cpu, seed):
 
 
 def _cpu_worker(args):
-    """One host core: `warm` untimed then `nsteps` timed md.vv steps of ONE trajectory."""
-    nsteps, warm, nmd_cpu, seed = args
-    kind, m = _cpu_system(nmd_cpu, seed)
+    """One host core: `warm` untimed then as many timed md.vv steps of ONE trajectory as fit in `budget` seconds
+    (at least `nmin`)."""
+    c, nmin, warm, budget, nmd_cpu, seed = args
+    kind, m = _cpu_system(c, nmd_cpu, seed)
     for _ in range(warm):
         m.vv()
     t0 = time.perf_counter()
-    for _ in range(nsteps):
+    n = 0
+    while n < nmin or (time.perf_counter() - t0 < budget and n < 1 << 20):
         m.vv()
-    return kind, nsteps, time.perf_counter() - t0
+        n += 1
+    return kind, n, time.perf_counter() - t0
 
 
-def cpu_throughput(nsteps, warm, cores=None, nmd_cpu=256):
+def cpu_throughput(c, nmin, warm, budget, cores=None, nmd_cpu=256):
     """Aggregate trajectory-steps/s of one reference process per host core."""
     import multiprocessing as mp
     cores = cores or min(os.cpu_count() or 1, 64)
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(nsteps, warm, nmd_cpu, 1000 + i) for i in range(cores)])
+        res = pool.map(_cpu_worker, [(c, nmin, warm, budget, nmd_cpu, 1000 + i) for i in range(cores)])
     kind = res[0][0]
-    tmax = max(r[2] for r in res)
-    return dict(value=sum(r[1] for r in res) / tmax, cores=cores, kind=kind, seconds=tmax,
-                per_core=float(np.mean([r[1] / r[2] for r in res])))
+    return dict(value=sum(r[1] / r[2] for r in res), cores=cores, kind=kind, seconds=max(r[2] for r in res),
+                steps_per_core=int(np.mean([r[1] for r in res])), per_core=float(np.mean([r[1] / r[2] for r in res])))
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    total = a.steps + a.warmup
-    piece = max(8, min(64, 3000 // max(total, 1)))
-    r = cpu_throughput(a.steps * piece, a.warmup * piece)
-    sample = ("%d md.vv steps of one trajectory per core after %d warm-up steps, cfg2 shape, noise table nmd=256 "
-              "(the loop cost does not depend on nmd)" % (a.steps * piece, a.warmup * piece))
+    c = workload(a.config, a.gpus)
+    heavy = c["nd"] > 100 or c["ml"] > 200
+    r = cpu_throughput(c, 2 if heavy else 8 * max(a.steps, 1), 1 if heavy else 8 * a.warmup, budget=min(60.0, 1.0 * max(a.steps, 1)))
+    sample = ("%d md.vv steps of one trajectory per core (one process per core, %d cores) after warm-up; %s"
+              % (r["steps_per_core"], r["cores"], CPU_ARM))
+    piece = a.piece or default_piece(c)
     out = dict(impl="reference", metric="trajectory_steps_per_s", value=r["value"], unit="trajectory-steps/s",
                n_gpus=a.gpus, steps=a.steps, warmup=a.warmup, ms_per_step=r["seconds"] * 1e3 / max(a.steps, 1),
-               higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-               config=workload_config(a), gpu_launches=0,
+               higher_is_better=True, scaling=c["scaling"], vs_baseline=None, dtype="f64", data="synthetic",
+               config=workload_config(a, c, piece), gpu_launches=0,
                cpu_baseline=dict(value=r["value"], unit="trajectory-steps/s", cores=r["cores"], kind=r["kind"],
                                  sample=sample, per_core=r["per_core"]),
                e2e=dict(value=r["value"], unit="trajectory-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -120,34 +232,6 @@ def run_reference(a):
 
 
 # ----------------------------------------------------------------------------- our arm
-def workload_config(a):
-    return dict(workload="cfg2 AuBZ-like junction: nd=60, electron bath nc=60 at bias 0.5 eV (5 matrices), "
-                         "2 phonon baths nc=15 ml=100, 1 constraint, dt=1, nmd=%d" % a.nmd,
-                batch_per_gpu=a.batch, md_steps_per_step=PIECE, nmd=a.nmd, savepq=False,
-                l2="inputs exceed L2: each step streams %d MB of noise rows (%.0f GB resident), 126 MB L2"
-                   % (PIECE * 90 * a.batch * 8 // 2 ** 20, a.nmd * 90 * a.batch * 8 / 2 ** 30))
-
-
-def build(batch, nmd, traj0, savepq, seed, mode=0):
-    from pymd_b200 import synth
-    from pymd_b200.ebath import ebath
-    from pymd_b200.md import md
-    from pymd_b200.phbath import phbath
-    c = CFG
-    j = synth.synth(c["nd"], c["ncl"], c["ncr"], seed=c["seed"], constraint=True)
-    m = md(c["dt"], nmd, c["T"], axyz=j.axyz, harmonic=True, dyn=j.DynMat, savepq=savepq, constr=j.constr.copy(),
-           batch=batch, seed=seed, traj0=traj0, step_mode=mode, npie=nmd // PIECE)
-    m.write_files = False
-    eb = ebath(j.cats_e, c["T"], c["dt"], nmd, wmax=1.0, nw=500, bias=c["bias"], efric=j.efric, exim=j.exim,
-               exip=j.exip, zeta1=j.zeta1, zeta2=j.zeta2)
-    pl = phbath(c["T"] + c["dT"] / 2, j.cats_l, c["hwcut"], c["nw"], c["dt"], nmd, ml=c["ml"], sig=j.SigL, gwl=j.wl)
-    pr = phbath(c["T"] - c["dT"] / 2, j.cats_r, c["hwcut"], c["nw"], c["dt"], nmd, ml=c["ml"], sig=j.SigR, gwl=j.wl)
-    pl.gmem(); pr.gmem()
-    for b in (eb, pl, pr):
-        m.AddBath(b)
-    return m
-
-
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -177,29 +261,76 @@ class ClockSampler(threading.Thread):
         if not rows:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
         sm = sorted(float(r[0]) for r in rows)
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "", 1).isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
-        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(rows[0][1]), reasons=reasons, samples=len(rows))
+        return dict(sm_mhz=sm[len(sm) // 2], sm_min_mhz=sm[0], sm_max_mhz=float(rows[0][1]), reasons=reasons, samples=len(rows),
+                    power_w_max=max(pw) if pw else None)
 
 
-def algorithmic_flops():
-    """flops per trajectory-step.  `total` is the survey's F_alg (one (ml-1)-tap
-    convolution per non-local bath evaluated directly, three K[0] heads, one dyn product, 3x2 electron
-    operators).  The split says which kernel covers which taps: the fused step kernel does the operators,
-    the heads and every tap that meets history of the current 32-step super-block (in-block taps from
-    shared memory, earlier blocks of the super-block from the HBM ring); the far-field kernel covers the
-    remaining taps by FFT, so the flops it EXECUTES (far_executed) are well below its algorithmic share."""
-    c = CFG
-    nd, nc, ml, nce = c["nd"], 15, c["ml"], c["nd"]
-    S = 32
-    near = (S + 1) / 2.0 + 1.0                             # average number of taps inside the super-block
-    far = 2 * (2 * nc * nc * (ml - 1 - near))              # two phonon baths, taps older than the super-block
-    fused = 2 * nd * nd + 6 * 2 * nce * nce + 2 * (3 * 2 * nc * nc + 2 * nc * nc * near)
-    total = 2 * nd * nd + 2 * (2 * (ml + 2) * nc * nc) + 6 * 2 * nce * nce
-    # executed by the far kernel per trajectory and super-block: two real FFTs of length 128 per bath
-    # dof (2.5 n log2 n each) and 65 complex nc x nc products (8 flops per complex multiply-add)
-    far_exec = 2 * (2 * nc * 2.5 * 128 * 7 + 65 * 8 * nc * nc) / S
-    return dict(total=total, tail=far, fused=fused, far_executed=far_exec)
+def _peaks():
+    p = os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")
+    p64 = max(r["tflops"] for r in json.load(open(p))["dmma"]) if os.path.exists(p) else 37.0
+    m = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm = json.load(open(m)).get("hbm_gbs", 6549.1) if os.path.exists(m) else 6549.1
+    return p64, hbm
+
+
+def shard_check(c, a, rank, world, dev):
+    """GPU-side N-GPU invariance: (1) every rank also steps the first 32 trajectories of rank
+    (r+1) mod N and compares them BIT FOR BIT with that rank's own result (one all-gather); (2) a fixed global
+    ensemble of 8192 trajectories split N ways gives the same averaged currents / kinetic energy / power2 as the
+    values computed the same way for any N (they are printed; the N = 1 line is the reference)."""
+    import torch
+    import torch.distributed as dist
+    nmd_s, nst, nsh = 256, 64, 32
+    per = c["batch"]
+
+    def run(batch, traj0, steps, savepq):
+        m = build(c, batch, traj0, savepq, a.seed + 7, a.mode, nmd=nmd_s)
+        m.initialise(stream=0); m.ResetHis()
+        for b in m.baths:
+            b._gnoi(segment=0)
+        if savepq:
+            m.ResetSavepq(True)
+        m.steps(steps)
+        return m
+
+    own = run(per, rank * per, nst, False)
+    mine = torch.stack((own._p[:, :nsh], own._q[:, :nsh])).contiguous()
+    del own
+    nb = run(nsh, ((rank + 1) % world) * per, nst, False)
+    theirs = torch.stack((nb._p[:, :nsh], nb._q[:, :nsh])).contiguous()
+    del nb
+    res = dict(tile="same kernel as the full ensemble is not guaranteed for 32 trajectories; compared at rounding and bitwise")
+    if world > 1:
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        ref = gathered[(rank + 1) % world]
+    else:
+        ref = mine
+    bitwise = bool(torch.equal(ref, theirs))
+    dev_rel = float((ref - theirs).abs().max() / ref.abs().max())
+    flags = torch.tensor([1.0 if bitwise else 0.0, dev_rel], dtype=torch.float64, device=dev)
+    if world > 1:
+        allf = [torch.empty_like(flags) for _ in range(world)]
+        dist.all_gather(allf, flags)
+        bitwise = all(bool(f[0].item() == 1.0) for f in allf)
+        dev_rel = max(float(f[1].item()) for f in allf)
+    res.update(shard_check="bitwise" if bitwise else "rounding", max_rel_dev=dev_rel, trajectories=nsh, md_steps=nst)
+    # fixed global ensemble split N ways
+    from pymd_b200 import ensemble
+    tot = 8192
+    loc = tot // world
+    g = run(loc, rank * loc, nmd_s, True)
+    g.GetPower()
+    av = ensemble.ensemble_average(g, tot)
+    res["global_8192"] = dict(cur_nW=[float(x) for x in av["cur"]], ekin=av["ekin"],
+                              power2_sum=float(av["power2"][:, 1].sum()), power2_max=float(av["power2"][:, 1].max()),
+                              note="identical for every N up to the summation order of the all-reduce (compare with the N=1 line)")
+    del g
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_ours(a):
@@ -234,22 +365,31 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    B, nmd = a.batch, a.nmd
-    peaks = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peaks.json"))) if os.path.exists(
-        os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")) else None
-    p64 = max(r["tflops"] for r in peaks["dmma"]) if peaks else 37.0
+    c = workload(a.config, world)
+    if a.batch:
+        c["batch"] = a.batch
+    if a.nmd:
+        c["nmd"] = a.nmd
+    B, nmd = c["batch"], c["nmd"]
+    p64, hbm = _peaks()
+    fl = algorithmic(c)
 
     # ------------------------------------------------------------ resident-ensemble throughput
     t_setup = time.time()
-    m = build(B, nmd, rank * B, False, a.seed, a.mode)
+    m = build(c, B, rank * B, False, a.seed, a.mode)
     m.initialise()
     m.ResetHis()
     for b in m.baths:
         b.gnoi()
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
+    # history filled and one bench step sized to ~0.15 s (a power of two of md steps, at most nmd)
+    burn = min(max(c["ml"], 32), nmd)
+    m.steps(burn)
+    torch.cuda.synchronize()
+    piece = a.piece or default_piece(c)
     for _ in range(a.warmup):
-        m.steps(PIECE)
+        m.steps(piece)
     torch.cuda.synchronize()
     barrier()
     sampler = ClockSampler(local)
@@ -261,7 +401,7 @@ def run_ours(a):
     barrier()
     e0.record()
     for _ in range(a.steps):
-        m.steps(PIECE)
+        m.steps(piece)
     e1.record()
     torch.cuda.synchronize()
     barrier()
@@ -269,87 +409,80 @@ def run_ours(a):
     launches = _lib.load().pymd_launch_count(m._ctx) - l0
     clocks = sampler.finish()
     finite = bool(torch.isfinite(m._p).all().item())
-    value = B * world * PIECE * a.steps / (ms * 1e-3)
+    value = B * world * piece * a.steps / (ms * 1e-3)
 
     # per-kernel device time of the same loop, CUDA events on the launching stream
     import ctypes
     _lib.call("pymd_profile_enable", m._ctx, 1)
-    m.steps(PIECE)
+    pp = min(piece, 256 if c["nd"] <= 100 else 32)
+    m.steps(pp)
     ms4 = (ctypes.c_double * 8)()
     cnt4 = (ctypes.c_longlong * 8)()
     _lib.call("pymd_profile_read", m._ctx, ctypes.addressof(ms4), ctypes.addressof(cnt4))
     _lib.call("pymd_profile_enable", m._ctx, 0)
     names = ["tail_gemm", "fused_step", "other_gemm", "stage_kernels", "far_fft"]
     kern = {names[i]: dict(ms=ms4[i], launches=int(cnt4[i])) for i in range(5) if cnt4[i]}
-    fl = algorithmic_flops()
     tot_ms = sum(v["ms"] for v in kern.values())
-    roof = None
+    # algorithmic flops each kernel class covers (per trajectory-step)
+    if "fused_step" in kern and "far_fft" in kern and "fused" in fl:
+        cover = dict(fused_step=fl["fused"], far_fft=fl["tail"])
+    elif "fused_step" in kern:
+        cover = dict(fused_step=fl["total"] - (fl["taps"] if "tail_gemm" in kern else 0), tail_gemm=fl["taps"])
+    else:
+        cover = dict(tail_gemm=fl["taps"], other_gemm=fl["total"] - fl["taps"])
     per_kernel = {}
-    for key, fkey in (("fused_step", "fused"), ("tail_gemm", "tail"), ("far_fft", "tail")):
-        if key in kern:
-            k = kern[key]
-            ach = fl[fkey] * B * PIECE / (k["ms"] * 1e-3) / 1e12
-            per_kernel[key] = dict(achieved=ach, frac=ach / p64, share_of_step=k["ms"] / tot_ms,
-                                   us_per_launch=1e3 * k["ms"] / k["launches"], launches_per_step=k["launches"])
-            if key == "far_fft":
+    for key, k in kern.items():
+        d = dict(share_of_step=k["ms"] / tot_ms, us_per_launch=1e3 * k["ms"] / k["launches"],
+                 launches_per_md_step=k["launches"] / pp)
+        if key in cover and cover[key] > 0:
+            ach = cover[key] * B * pp / (k["ms"] * 1e-3) / 1e12
+            d.update(achieved=ach, frac=ach / p64, algorithmic_flops_per_trajectory_step=cover[key])
+            if key == "far_fft" and "far_executed" in fl:
                 # the far field replaces the taps it covers by an FFT convolution: judge the kernel on the
                 # flops it executes, and keep the direct-product equivalent beside it
-                ex = fl["far_executed"] * B * PIECE / (k["ms"] * 1e-3) / 1e12
-                per_kernel[key].update(achieved=ex, frac=ex / p64, direct_product_equivalent_tflops=ach,
-                                       note="achieved = executed FFT + per-frequency product flops; the same "
-                                            "taps as a direct product would be direct_product_equivalent_tflops")
+                ex = fl["far_executed"] * B * pp / (k["ms"] * 1e-3) / 1e12
+                d.update(achieved=ex, frac=ex / p64, direct_product_equivalent_tflops=ach,
+                         note="achieved = executed FFT + per-frequency product flops; the same taps as a direct "
+                              "product would be direct_product_equivalent_tflops")
+        per_kernel[key] = d
+    roof = None
     if per_kernel:
         dom = max(per_kernel, key=lambda n: per_kernel[n]["share_of_step"])
-        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-        if os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+        if os.path.exists(tpath) and c["name"] == "cfg2":
             traffic = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_launch")
-        roof = dict(bound="tensor", kernel=dom, achieved=per_kernel[dom]["achieved"], peak=p64, unit="TFLOP/s",
-                    frac=per_kernel[dom]["frac"], traffic=traffic,
+        whole = (value / world) * fl["total"] / (p64 * 1e12)
+        whole_hbm = (value / world) * fl["bytes"] / (hbm * 1e9)
+        roof = dict(bound="tensor", kernel=dom, achieved=per_kernel[dom].get("achieved"), peak=p64, unit="TFLOP/s",
+                    frac=per_kernel[dom].get("frac"), traffic=traffic,
                     peak_source="FP64 DMMA.8x8x4 peak measured on this pool (profiles/r01_fp64_peaks.json); "
                                 "MEASURED_PEAKS.json has no FP64 entry (cuBLAS DGEMM 8192^3: 35.45 TFLOP/s)",
-                    kernels=per_kernel,
-                    whole_step_frac=(value / world) * fl["total"] / (p64 * 1e12),
+                    kernels=per_kernel, whole_step_frac=whole, whole_step_frac_of_hbm=whole_hbm,
                     flops_per_trajectory_step=fl)
     del m
     torch.cuda.empty_cache()
 
-    # `value` runs with trajectory saving off: ps/qs for 4096 trajectories x 2^15 steps (128 GB) do not fit
-    # beside the 90 GB of noise.  The same loop WITH the ps/qs stores of md.vv (md.py:330-333), on a shorter
-    # noise period so that the buffers fit, shows what saving costs; e2e below always saves.
-    value_savepq = None
-    if not a.no_e2e:
-        nmd_s = min(nmd, 4096)
-        ms_ = build(B, nmd_s, rank * B, True, a.seed, a.mode)
-        ms_.initialise()
-        ms_.ResetHis()
-        for b in ms_.baths:
-            b.gnoi()
-        ms_.ResetSavepq(True)
-        for _ in range(a.warmup):
-            ms_.steps(PIECE)
-        torch.cuda.synchronize()
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(min(a.steps, 16)):
-            ms_.steps(PIECE)
-        s1.record()
-        torch.cuda.synchronize()
-        barrier()
-        t_s = max_over_ranks(s0.elapsed_time(s1))
-        value_savepq = dict(value=B * world * PIECE * min(a.steps, 16) / (t_s * 1e-3), nmd=nmd_s,
-                            note="same loop with savepq=True (960 B stored per trajectory-step)")
-        del ms_
-        torch.cuda.empty_cache()
+    # ------------------------------------------------------------ N-GPU invariance
+    shard = None
+    if not a.no_shard_check and c["nd"] <= 100:
+        shard = shard_check(c, a, rank, world, dev)
 
     # ------------------------------------------------------------ end to end through the class API
     e2e = None
+    value_savepq = None
     if not a.no_e2e:
+        nmd_e = c["nmd"]
         Be = min(a.e2e_batch, B)
-        nsub = B // Be
-        me = build(Be, nmd, rank * B, True, a.seed + 1, a.mode)
+        while B % Be:
+            Be //= 2
+        # sub-ensemble size: noise + saved trajectories (+ scratch) must fit; the second noise set of the overlapped
+        # pipeline only when it fits as well (run_pipelined checks)
+        per_traj = 8 * nmd_e * (sum(_bath_ncs(c)) + 2 * c["nd"])
+        free, _ = torch.cuda.mem_get_info(dev)
+        while Be > 32 and per_traj * Be + (20 << 30) > free and B % (Be // 2) == 0:
+            Be //= 2
+        me = build(c, Be, rank * B, True, a.seed + 1, a.mode)
         for b in me.baths:
             b.spectral_factors()                       # host setup (eigh per frequency), as the reference does once
         h2d = sum(b.spectral_factors().L.nbytes for b in me.baths)
@@ -360,75 +493,90 @@ def run_ours(a):
         for b in me.baths:
             b.gnoi()
         me.ResetSavepq(True)
-        me.steps(PIECE)
+        me.steps(min(256, nmd_e))
         me.GetPower()
         torch.cuda.synchronize()
         barrier()
         t0 = time.perf_counter()
-        psum = np.zeros(nmd); p2sum = np.zeros(nmd); cur = np.zeros(len(me.baths)); ek = 0.0
-        for sub in range(nsub):
-            me.traj0 = rank * B + sub * Be
-            for b in me.baths:
-                b._traj0 = me.traj0
-                b.spectral_factors().drop_device_copy()    # this segment's inputs cross the bus again
-            me.initialise()
-            me.ResetHis()
-            for b in me.baths:
-                b.gnoi()
-            me.ResetSavepq(True)
-            me.steps(nmd)
-            me.GetPower()
-            psum += me.power_sum; p2sum += me.power2_sum
-            cur += np.array([float(b._cur_dev[:, :Be].mean().item()) * Be for b in me.baths])
-            ek += float(me._etot[:, :Be].mean().item()) * Be
-        res = ensemble.allreduce_sums([psum, p2sum, cur, np.array([ek])])
+        try:
+            r = ensemble.run_pipelined(me, B, traj0=rank * B, segment=0, overlap=a.overlap, reupload_factors=True)
+        except torch.cuda.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            r = ensemble.run_pipelined(me, B, traj0=rank * B, segment=0, overlap=False, reupload_factors=True)
+        res = ensemble.allreduce_sums([r["power_sum"], r["power2_sum"], r["cur_sum"], np.array([r["ekin_sum"]])])
         torch.cuda.synchronize()
         barrier()
         sec = max_over_ranks(time.perf_counter() - t0)
-        d2h = 2 * nmd * 8 + (len(me.baths) + 1) * 8
-        e2e = dict(value=B * world * nmd / sec, unit="trajectory-steps/s", h2d_bytes_per_step=int(h2d),
-                   d2h_bytes_per_step=int(d2h), seconds=sec, sub_ensembles=nsub, sub_batch=Be,
-                   step="one sub-ensemble Run segment: factors H2D + noise generation + %d md steps with savepq + "
-                        "power spectra + D2H" % nmd,
+        d2h = 2 * nmd_e * 8 + (2 * len(me.baths) + 1) * 8
+        br = r["seconds"]
+        # HBM roofline of the noise / spectra legs: bytes one pass over the data moves (algorithmic: white noise in,
+        # noise rows out; saved trajectories in) against the measured copy bandwidth
+        nb_noise = 8 * (nmd_e // 2 + 1 + nmd_e) * sum(_bath_ncs(c)) * B
+        nb_spec = 8 * nmd_e * 2 * c["nd"] * B
+        e2e = dict(value=B * world * nmd_e / sec, unit="trajectory-steps/s", h2d_bytes_per_step=int(h2d * (B // Be)),
+                   d2h_bytes_per_step=int(d2h), seconds=sec, sub_ensembles=B // Be, sub_batch=Be,
+                   step="one Run segment of the whole ensemble in sub-ensembles: factors H2D + noise generation + %d md "
+                        "steps with savepq + power spectra + D2H" % nmd_e,
+                   breakdown=dict(h2d="inside noise_gen (async copy of %.2f GB per sub-ensemble from pinned memory)" % (h2d / 1e9),
+                                  noise_gen=br["noise_gen"], steps=br["steps"], spectra=br["spectra"],
+                                  reductions=br["reductions"], d2h=br["d2h"], total=br["total"], overlapped=br["overlap"],
+                                  note="device seconds per leg summed over sub-ensembles; with overlap noise_gen of "
+                                       "sub-ensemble s+1 runs on a side stream beside the steps of s"),
+                   hbm_frac=dict(noise_gen=nb_noise / max(br["noise_gen"], 1e-9) / 1e9 / hbm,
+                                 spectra=nb_spec / max(br["spectra"], 1e-9) / 1e9 / hbm,
+                                 note="algorithmic bytes (white noise in + noise rows out; saved p, q in) / leg time / "
+                                      "%.0f GB/s" % hbm),
+                   steps_rate=B * nmd_e / max(br["steps"], 1e-9),
                    mean_current_nW=[float(x) * 243414. / (B * world) for x in res[2]],
                    finite=bool(np.isfinite(res[0]).all() and np.isfinite(res[1]).all()))
+        value_savepq = dict(value=e2e["steps_rate"] * world, note="stepping legs of the e2e run alone (savepq=True, "
+                            "%d-trajectory sub-ensembles)" % Be)
         del me
         torch.cuda.empty_cache()
 
     # ------------------------------------------------------------ CPU baseline (rank 0, N == 1)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
-        r = cpu_throughput(a.cpu_steps, 8)
+        heavy = c["nd"] > 100 or c["ml"] > 200
+        r = cpu_throughput(c, 2 if heavy else 64, 1 if heavy else 8, budget=a.cpu_seconds)
         cpu = dict(value=r["value"], unit="trajectory-steps/s", cores=r["cores"], kind=r["kind"],
                    per_core=r["per_core"],
-                   sample="%d md.vv steps of one trajectory per core (one process per core), cfg2 shape, "
-                          "noise table nmd=256" % a.cpu_steps)
+                   sample="%d md.vv steps of one trajectory per core (one process per core), %s"
+                          % (r["steps_per_core"], CPU_ARM))
 
     if rank == 0:
         out = dict(metric="trajectory_steps_per_s", value=value, unit="trajectory-steps/s", n_gpus=world,
-                   steps=a.steps, warmup=a.warmup, ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak",
-                   vs_baseline=None, dtype="f64", data="synthetic", config=workload_config(a), clocks=clocks,
+                   steps=a.steps, warmup=a.warmup, ms_per_step=ms / a.steps, higher_is_better=True, scaling=c["scaling"],
+                   vs_baseline=None, dtype="f64", data="synthetic", config=workload_config(a, c, piece), clocks=clocks,
                    gpu_launches=int(launches), e2e=e2e, roofline=roof, cpu_baseline=cpu, value_with_savepq=value_savepq,
-                   setup_s=t_setup, finite=finite, step_mode=a.mode)
+                   shard_check=shard, setup_s=t_setup, finite=finite, step_mode=a.mode, timed_seconds=ms * 1e-3)
         _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
+def _bath_ncs(c):
+    return ([c["nce"]] if c["nce"] else []) + ([c["ncl"], c["ncr"]] if c["leads"] else [])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="trajectories per GPU")
-    ap.add_argument("--nmd", type=int, default=2 ** 15)
-    ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 per-step pipeline, 2 fused")
+    ap.add_argument("--config", default="cfg2", help="cfg2 (default) | cfg3 | cfg4 | cfg4s | sweep:<nd>,<ml>,<B>[,<nc>]")
+    ap.add_argument("--batch", type=int, default=0, help="trajectories per GPU (default: the configuration's)")
+    ap.add_argument("--nmd", type=int, default=0)
+    ap.add_argument("--piece", type=int, default=0, help="md steps per bench step (default: sized to ~0.15 s)")
+    ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 per-step pipeline, 2 on-chip step kernels")
     ap.add_argument("--seed", type=int, default=20240)
     ap.add_argument("--e2e-batch", type=int, default=2048)
-    ap.add_argument("--cpu-steps", type=int, default=1024)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--overlap", action="store_true", help="e2e: generate the next sub-ensemble's noise on a side stream while the current one steps (needs a second set of noise buffers)")
+    ap.add_argument("--no-shard-check", action="store_true")
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3

@@ -117,6 +117,12 @@ int pymd_noise_generate(const double* lre_dev, const double* lim_dev, const doub
                         int nmd, int nc, int ldb, int n0, int n1, double dt, double* out_dev,
                         void* work_dev, void* stream);
 
+/* The same for white noise held per trajectory chunk: xi_chunk dev [nf][nc][cw] belongs to the trajectories
+ * n0 <= n < n0 + cw of out (dev [nmd][nc][ldb]); cw a multiple of 8.  With pymd_philox_normal called per chunk
+ * (traj0 + n0) the white noise of a large ensemble never exists as a whole (noise.py:282 draws it value by value). */
+int pymd_noise_generate_chunk(const double* lre_dev, const double* lim_dev, const double* xi_chunk_dev, int cw,
+                              int nmd, int nc, int ldb, int n0, double dt, double* out_dev, void* work_dev, void* stream);
+
 /* N.random.normal replacement (noise.py:282): counter-based Philox4x32-10 + Box-Muller using both
  * outputs (rows 2r and 2r+1 share the counter r).  Element (row r, trajectory n) depends only on
  * (seed, stream_id, r, traj0+n): results do not depend on how the ensemble is sharded over GPUs.

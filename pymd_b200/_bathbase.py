@@ -77,31 +77,49 @@ class BathBase(object):
             self._factors_key = key
         return self._factors
 
-    def _gnoi(self, xi=None, segment=None):
+    def _gnoi(self, xi=None, segment=None, out=None, traj0=None):
         """``segment``: index of the md.Run segment the noise is for; selects the Philox stream, so that the
         realisation depends only on (seed, bath, segment, trajectory) and a resumed run repeats the uninterrupted
-        one.  Hand-driven loops (segment=None) count the calls instead."""
+        one.  Hand-driven loops (segment=None) count the calls instead.  ``out`` / ``traj0``: generate into that
+        device buffer for the sub-ensemble starting at that global trajectory index WITHOUT making it the current
+        noise (ensemble.run_pipelined prepares the next sub-ensemble on a side stream this way)."""
         import torch
         if self.dt is None or self.nmd is None:
             raise ValueError("%s.gnoi: the md information dt and nmd are not set!" % type(self).__name__)
         fac = self.spectral_factors()
         nf = int(self.nmd / 2) + 1
         dev = self._dev()
+        detached = out is not None
+        if out is None:
+            out = self._noise_target()
         if xi is None:
             if self._seed is None:
                 self._seed = int(N.random.randint(0, 2 ** 31 - 1))
             sid = self._ngnoi if segment is None else int(segment)
-            x = _noise.white_noise(nf, self.nc, self.ldb, self._seed,
-                                   ((self._index + 1) << 16) ^ (sid & 0xFFFF), self._traj0, dev)
-            if self.batch < self.ldb:
-                x[:, :, self.batch:] = 0.0          # padding trajectories stay at rest
+            _noise.generate_philox(fac, self.dt, self.nmd, self.ldb, self.batch, self._seed,
+                                   ((self._index + 1) << 16) ^ (sid & 0xFFFF),
+                                   self._traj0 if traj0 is None else int(traj0), out)
         else:
             x = _noise._as_device_xi(xi, nf, self.nc, self.batch, self.ldb, dev)
+            _noise.generate(fac, x, self.dt, self.nmd, out=out)
+        if detached:
+            return
         self._ngnoi = self._ngnoi + 1 if segment is None else int(segment) + 1
-        if self._noise_dev is None or tuple(self._noise_dev.shape) != (self.nmd, self.nc, self.ldb):
-            self._noise_dev = torch.empty((self.nmd, self.nc, self.ldb), dtype=torch.float64, device=dev)
-        _noise.generate(fac, x, self.dt, self.nmd, out=self._noise_dev)
+        self._noise_dev = out
         self._noise_version = getattr(self, "_noise_version", 0) + 1
+
+    def _noise_target(self):
+        """The device buffer the next gnoi() writes: the current one, or the spare one of a double-buffered run
+        (ensemble.run_pipelined generates the next sub-ensemble's noise while the current one is stepping)."""
+        import torch
+        shape = (self.nmd, self.nc, self.ldb)
+        spare = getattr(self, "_noise_spare", None)
+        if spare is not None and tuple(spare.shape) == shape:
+            self._noise_spare = self._noise_dev if (self._noise_dev is not None and tuple(self._noise_dev.shape) == shape) else None
+            return spare
+        if self._noise_dev is None or tuple(self._noise_dev.shape) != shape:
+            return torch.empty(shape, dtype=torch.float64, device=self._dev())
+        return self._noise_dev
 
     @property
     def noise(self):

@@ -39,6 +39,8 @@ PROTOTYPES = {
     "pymd_noise_work_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "pymd_noise_generate": (C.c_int, [c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                       c_dp, c_dp, c_dp]),
+    "pymd_noise_generate_chunk": (C.c_int, [c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                            c_dp, c_dp, c_dp]),
     "pymd_profile_enable": (C.c_int, [c_ctx, C.c_int]),
     "pymd_profile_read": (C.c_int, [c_ctx, c_dp, c_dp]),
     "pymd_philox_normal": (C.c_int, [c_dp, C.c_longlong, C.c_int, C.c_uint64, C.c_uint32, C.c_longlong, c_dp]),

@@ -297,6 +297,7 @@ int finalize(pymd_ctx* c) {
     int rc;
     if ((rc = upload(&c->d_dyn, dynp))) return rc;
     if ((rc = upload(&c->d_mp, mp))) return rc;
+    c->mp_host = mp;
     if (c->ncon > 0 && (rc = upload(&c->d_con, c->con))) return rc;
 
     c->ws_bytes = ws_doubles * sizeof(double) + (size_t)ldb * sizeof(int);

@@ -74,7 +74,7 @@ struct pymd_ctx {
     double dt = 0;
     int ldn = 0;                       // padded row length of nd x nd operands
     pymd::BathHost bath[PYMD_MAX_BATHS];
-    std::vector<double> dyn, con;
+    std::vector<double> dyn, con, mp_host;     // mp_host: [nd][ldn] host copy of d_mp (constraint operands)
     double* d_dyn = nullptr;           // [nd][ldn]
     double* d_mp = nullptr;            // [nd][ldn]  sum_b scatter(alpha_b kernel_b[0])
     double* d_con = nullptr;           // [ncon][nd]

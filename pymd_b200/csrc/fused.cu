@@ -30,96 +30,17 @@
 #include <type_traits>
 #include <vector>
 
-#include "engine.cuh"
+#include "fused.cuh"
 
 namespace pymd {
 
 int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st, long long wmax = -1,
                 int accumulate = 0);
+// fused3.cu: two-unit variant of the warp-specialised kernel
+size_t plan3(const pymd_ctx* c, FusedParams& fp, bool hasq, int NJ);
+int launch_f3(const FusedParams& fp, size_t smem, int NJ, bool hasq, bool hascon, cudaStream_t st);
 
 namespace {
-
-constexpr int FW = 8;        // warps per CTA
-constexpr int NDP = 64;      // padded rows (8 per warp)
-constexpr int FT = 8;        // steps per block
-constexpr int MAXKS = 16;    // k-steps of the nd x nd operators (nd <= 64)
-constexpr int FB_MAX = 4;    // baths supported by the fused path
-constexpr int MAXIT = 4;     // work items of each kind per warp
-
-struct FusedBath {
-    int nc, ncp, ml, nonlocal, R, slot0, ntap, ldk, direct;       // direct: local remainder bath, noise read straight from HBM
-    int off_hd, off_kin, off_hist, off_nb, off_cids, off_inrem;   // smem offsets (doubles)
-    int lda;
-    const double* noise;
-    const double* P;          // [FT][nc][ldb] pre-block tail
-    double* tail_cur;         // [nc][ldb] tail(t) carried between launches
-    double* ring;
-    double* cur;
-    const double* head_g;     // [nc][lda]
-    const double* kin_g;      // [kBlockT][nc][nc]
-    const int* cids_g;
-    const int* inv_g;
-    // in-kernel mid field (mid == 1): A fragments of dt K[k], k = 2..2+kMidK-1, and the far field
-    const double* kmid;       // [kMidK][ncp/8][ncp/4][32]
-    const double* F;          // [kFarS][nc][ldb] rows of the current super-block
-    const double* kinf;       // fused2: dt K[1..8] as A fragments [8][ncp/8][ncp/4][32]
-    const double* hdf;        // fused2: alpha K[0] as A fragments [ncp/8][ncp/4][32]
-};
-
-struct FusedParams {
-    int nd, ks, ldb, ldn, nbath, nmd, ncon, nsteps, rem, aq, carry_valid;
-    int nosplit;              // testing knob (PYMD_FUSED_SPLIT=0): never split work items into n-tile halves
-    int mid;                  // 1: several blocks per launch, pre-block tails computed in the kernel
-    int r0;                   // steps since the start of the super-block at launch
-    long long hc0;            // history rows appended before p(t0)
-    long long t0;
-    double dt;
-    double *p, *q, *ps, *qs, *etot, *fpotn;
-    int* samef;
-    const double *dyn, *mp, *aqT, *con3;      // con3: [3][ncon][nd] = c, D c, AqT c
-    int off_xp0, off_xp1, off_xq, off_curp, off_conp, off_zero, off_conv;
-    int off_opD, off_opQ;     // fused2: dyn / AqT as fragment-ordered shared-memory operands
-    int pair_b[4], pair_mt[4];    // fused2: (bath, m8 tile) owned by each bath warp, -1 = none
-    double cmax;              // max_i |c_i| of the (single) constraint vector
-    int smem_doubles;
-#ifdef PYMD_FUSED_TIMING
-    long long* timing;        // [32] accumulated clock64 deltas per phase (tools/build_timing.sh builds only)
-#endif
-    FusedBath b[FB_MAX];
-};
-
-__device__ __forceinline__ double colsum8(double v) {     // sum over the 8 lanes sharing lane%4
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    v += __shfl_xor_sync(0xffffffffu, v, 8);
-    v += __shfl_xor_sync(0xffffffffu, v, 16);
-    return v;
-}
-// Reduce-scatter over the 8 lanes sharing lane%4 (lr = lane>>2): lane lr returns sum_lanes v[lr].
-// 7 shuffles for 8 column sums instead of 24.
-__device__ __forceinline__ double rs8(const double (&v)[8], int lr) {
-    const bool h4 = lr & 4, h2 = lr & 2, h1 = lr & 1;
-    double k[4], m[2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const double keep = h4 ? v[i + 4] : v[i], send = h4 ? v[i] : v[i + 4];
-        k[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const double keep = h2 ? k[i + 2] : k[i], send = h2 ? k[i] : k[i + 2];
-        m[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    const double keep = h1 ? m[1] : m[0], send = h1 ? m[0] : m[1];
-    return keep + __shfl_xor_sync(0xffffffffu, send, 4);
-}
-__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
-__device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
-
-template <int NT>
-__device__ __forceinline__ void zero_acc(double (&a)[NT][2]) {
-#pragma unroll
-    for (int j = 0; j < NT; ++j) a[j][0] = a[j][1] = 0.0;
-}
 
 // acc[j] += A(rows of this warp) . X[:, 8j..8j+7]   (A fragments in registers, X in smem)
 // FULLK: all MAXKS k-steps without the per-step branch (operator columns >= nd are zero, the padding
@@ -874,6 +795,17 @@ __global__ void __launch_bounds__(FW * 32, 1) fused_kernel(const FusedParams P) 
 //     256 row threads only.
 // Used when every non-direct bath has ncp <= 16 and there are at most 4 (bath, m8 tile) pairs.
 constexpr int RW2 = 8, TW2 = 12, NTH2 = TW2 * 32;
+// register re-balancing between the two row-warp groups and the bath group (setmaxnreg works on groups of four
+// warps): 2 x F2_ROW_REGS + F2_BATH_REGS <= 3 x 168
+#ifndef F2_SETMAXNREG
+#define F2_SETMAXNREG 0
+#endif
+#ifndef F2_ROW_REGS
+#define F2_ROW_REGS 192
+#endif
+#ifndef F2_BATH_REGS
+#define F2_BATH_REGS 120
+#endif
 
 __device__ __forceinline__ void row_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, 384;" ::: "memory"); }
@@ -942,6 +874,9 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
 
     if (roww) {
     // ================================================================== ROW WARPS
+#if F2_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F2_ROW_REGS));      // the bath warp group hands registers over
+#endif
     // ---- row-warp state
     double aM[MAXKS];
 #pragma unroll
@@ -1243,6 +1178,9 @@ __global__ void __launch_bounds__(NTH2, 1) fused2_kernel(const FusedParams P) {
 
     } else {
     // ================================================================== BATH WARPS
+#if F2_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F2_BATH_REGS));
+#endif
     // ---- bath-warp state: the pair (bath pb, m8 tile pmt) and its tap / head fragments
     const int pb = roww ? -1 : P.pair_b[w - RW2], pmt = roww ? 0 : P.pair_mt[w - RW2];
     double kf[FT][4], hf[4];
@@ -1575,13 +1513,20 @@ int prepare_scattered_operands(pymd_ctx* c, int aq_bath) {
     }
     if (c->ncon > 0 && !c->d_con3) {
         const int nd = c->nd, nc3 = c->ncon;
-        std::vector<double> c3((size_t)3 * nc3 * nd, 0.0);
+        std::vector<double> c3((size_t)4 * nc3 * nd, 0.0);      // c, D c, AqT c, Mp^T c
         for (int k = 0; k < nc3; ++k)
             for (int i = 0; i < nd; ++i) {
                 c3[(size_t)k * nd + i] = c->con[(size_t)k * nd + i];
                 double sd = 0.0;
                 for (int j = 0; j < nd; ++j) sd += c->dyn[(size_t)i * nd + j] * c->con[(size_t)k * nd + j];
                 c3[(size_t)(nc3 + k) * nd + i] = sd;
+            }
+        // Mp^T c (fused3: c.Mp x = (Mp^T c).x lets the constraint dots be taken one round early)
+        for (int k = 0; k < nc3; ++k)
+            for (int j = 0; j < nd; ++j) {
+                double sw = 0.0;
+                for (int i = 0; i < nd; ++i) sw += c->mp_host[(size_t)i * c->ldn + j] * c->con[(size_t)k * nd + i];
+                c3[(size_t)(3 * nc3 + k) * nd + j] = sw;
             }
         if (hasq) {
             const BathHost& H = c->bath[aq_bath];
@@ -1649,6 +1594,17 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
         if (smem2 > 227 * 1024) use2 = false;
         else fp = t2;
     }
+    // two-unit variant (fused3.cu) where it applies: the default for 16- and 32-trajectory tiles
+    // (PYMD_FUSED3 = 0 / 1 / unset: never / wherever it applies / per-tile default)
+    const char* e3 = getenv("PYMD_FUSED3");
+    bool use3 = use2 && (e3 ? atoi(e3) != 0 : NT == 4);
+    size_t smem3 = 0;
+    if (use3) {
+        FusedParams t3 = fp;
+        smem3 = plan3(c, t3, hasq, NT / 2);
+        if (smem3 > 227 * 1024) use3 = false;
+        else fp = t3;
+    }
     int rc;
     if (!c->tail_valid) {
         for (int b = 0; b < c->nbath; ++b)
@@ -1715,7 +1671,8 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
         fp.nsteps = ns;
         fp.carry_valid = c->fpot_valid ? 1 : 0;
         prof_begin(c, 1, st);
-        if (use2) {
+        if (use3) rc = launch_f3(fp, smem3, NT / 2, hasq, c->ncon > 0, st);
+        else if (use2) {
             const bool con = c->ncon > 0;
             if (NT == 4)
                 rc = hasq ? (con ? launch_f2<4, true, true>(fp, smem2, grid, st) : launch_f2<4, true, false>(fp, smem2, grid, st))
@@ -1742,6 +1699,18 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
     {
         long long h[32];
         cudaMemcpy(h, fp.timing, sizeof(h), cudaMemcpyDeviceToHost);
+        if (use3) {
+            const double nr = (double)grid * 8 * nsteps, nbw = (double)grid * 4 * nsteps;
+            const char* rn[8] = {"A.matvec", "A.elem", "reduce+B.matvec", "B.elem/C.elem", "C.matvec", "barrier-wait", "mid", "pre-mid"};
+            const char* bn[8] = {"job", "prefetch", "-", "-", "-", "H-wait", "-", "-"};
+            double tr = 0, tb = 0;
+            fprintf(stderr, "[fused3 timing] row warps, cycles per warp-step:");
+            for (int i = 0; i < 8; ++i) { fprintf(stderr, " %s=%.0f", rn[i], h[i] / nr); tr += h[i] / nr; }
+            fprintf(stderr, " total=%.0f\n[fused3 timing] bath warps:", tr);
+            for (int i = 0; i < 8; ++i) if (bn[i][0] != '-') { fprintf(stderr, " %s=%.0f", bn[i], h[16 + i] / nbw); tb += h[16 + i] / nbw; }
+            fprintf(stderr, " total=%.0f\n", tb);
+            return PYMD_OK;
+        }
         if (use2) {
             // only the LAST launch of this call (the counters are cleared per call, accumulated over its launches)
             const double nr = (double)grid * RW2 * nsteps, nbw = (double)grid * (TW2 - RW2) * nsteps;

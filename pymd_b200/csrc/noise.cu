@@ -265,15 +265,17 @@ size_t pymd_noise_work_bytes(int nmd, int nc, int ncols) {
     return 2 * (size_t)(nmd / 2) * nc * ncols * sizeof(double2);
 }
 
-int pymd_noise_generate(const double* lre, const double* lim, const double* xi, int nmd, int nc, int ldb,
-                        int n0, int n1, double dt, double* out, void* work, void* stream) {
+// xi: [nf][nc][xi_ld] white noise whose column 0 is trajectory n0 of the output; out: [nmd][nc][ldb]
+static int noise_generate_impl(const double* lre, const double* lim, const double* xi, int xi_ld, int xi_n0, int nmd, int nc,
+                               int ldb, int n0, int n1, double dt, double* out, void* work, void* stream) {
     PYMD_REQUIRE(lre && xi && out && work, "noise_generate: null argument");
     PYMD_REQUIRE(nmd >= 4 && (nmd & (nmd - 1)) == 0, "noise_generate: nmd=%d must be a power of two >= 4", nmd);
-    PYMD_REQUIRE(nc > 0 && ldb > 0 && ldb % 32 == 0, "noise_generate: nc=%d ldb=%d", nc, ldb);
+    PYMD_REQUIRE(nc > 0 && ldb > 0 && ldb % 32 == 0 && xi_ld % 8 == 0, "noise_generate: nc=%d ldb=%d xi_ld=%d", nc, ldb, xi_ld);
     PYMD_REQUIRE(0 <= n0 && n0 < n1 && n1 <= ldb && n0 % 8 == 0 && (n1 - n0) % 8 == 0,
                  "noise_generate: trajectory range [%d, %d) of %d (multiples of 8)", n0, n1, ldb);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int half = nmd / 2, cw = n1 - n0;
+    PYMD_REQUIRE(xi_n0 >= 0 && xi_n0 + cw <= xi_ld, "noise_generate: white-noise columns [%d, %d) of %d", xi_n0, xi_n0 + cw, xi_ld);
     const double2* twN = twiddle_table(nmd);
     PYMD_REQUIRE(twN, "noise_generate: twiddle table allocation failed");
     // Z goes to W0; the passes ping-pong W1, W0, W1, ...; the last one writes the real rows of `out`
@@ -282,15 +284,15 @@ int pymd_noise_generate(const double* lre, const double* lim, const double* xi, 
     int rc;
     if (nc <= 64) {
         // tensor-pipe shaping: all operand planes of a frequency pair fit in shared memory
-        if (nc <= 16) rc = lim ? launch_shape<4, true>(lre, lim, xi, nmd, nc, ldb, n0, cw, twN, W0, st)
-                               : launch_shape<4, false>(lre, lim, xi, nmd, nc, ldb, n0, cw, twN, W0, st);
-        else rc = lim ? launch_shape<16, true>(lre, lim, xi, nmd, nc, ldb, n0, cw, twN, W0, st)
-                      : launch_shape<16, false>(lre, lim, xi, nmd, nc, ldb, n0, cw, twN, W0, st);
+        if (nc <= 16) rc = lim ? launch_shape<4, true>(lre, lim, xi, nmd, nc, xi_ld, xi_n0, cw, twN, W0, st)
+                               : launch_shape<4, false>(lre, lim, xi, nmd, nc, xi_ld, xi_n0, cw, twN, W0, st);
+        else rc = lim ? launch_shape<16, true>(lre, lim, xi, nmd, nc, xi_ld, xi_n0, cw, twN, W0, st)
+                      : launch_shape<16, false>(lre, lim, xi, nmd, nc, xi_ld, xi_n0, cw, twN, W0, st);
         if (rc) return rc;
     } else {
         PYMD_REQUIRE(cw % SX == 0, "noise_generate: trajectory chunks must be multiples of %d for nc > 64", SX);
         dim3 grid(half / 2 + 1, cw / SX), blk(SX, SY);
-        shape_kernel<<<grid, blk, 0, st>>>(lre, lim, xi, nmd, nc, ldb, n0, cw, twN, W0);
+        shape_kernel<<<grid, blk, 0, st>>>(lre, lim, xi, nmd, nc, xi_ld, xi_n0, cw, twN, W0);
         PYMD_CUDA_CHECK(cudaGetLastError());
     }
     FftPlan p{};
@@ -300,6 +302,16 @@ int pymd_noise_generate(const double* lre, const double* lim, const double* xi, 
     p.dst_cw = cw; p.dst_cs = ldb;
     p.scale = 1.0 / ((double)nmd * dt);
     return fft_columns(W0, out + n0, W1, W0, p, st, nullptr);
+}
+
+int pymd_noise_generate(const double* lre, const double* lim, const double* xi, int nmd, int nc, int ldb,
+                        int n0, int n1, double dt, double* out, void* work, void* stream) {
+    return noise_generate_impl(lre, lim, xi, ldb, n0, nmd, nc, ldb, n0, n1, dt, out, work, stream);
+}
+
+int pymd_noise_generate_chunk(const double* lre, const double* lim, const double* xi_chunk, int cw, int nmd, int nc, int ldb,
+                              int n0, double dt, double* out, void* work, void* stream) {
+    return noise_generate_impl(lre, lim, xi_chunk, cw, 0, nmd, nc, ldb, n0, n0 + cw, dt, out, work, stream);
 }
 
 int pymd_philox_normal(double* out, long long rows, int ldb, uint64_t seed, uint32_t stream_id,

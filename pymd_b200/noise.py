@@ -111,6 +111,15 @@ class SpectralFactors:
         """Forget the device copies: the next gnoi() uploads the factors again."""
         self._dev = {}
 
+    def upload_copy(self, dev):
+        """A fresh device copy of L (asynchronous, from pinned memory, on the current stream) that is NOT yet the
+        one gnoi() uses: ensemble.run_pipelined uploads the next sub-ensemble's inputs on a copy stream."""
+        re, im = self._pinned()
+        return (re.to(dev, non_blocking=True), im.to(dev, non_blocking=True) if im is not None else None)
+
+    def adopt_device_copy(self, dev, pair):
+        self._dev[str(dev)] = pair
+
     def as_oracle(self):
         return self.lam, self.U
 
@@ -192,6 +201,12 @@ class DeviceSpectralFactors:
     def drop_device_copy(self):
         """The factors live on the device; there is no host copy to upload again."""
 
+    def upload_copy(self, dev):
+        return self.device_factors(dev)
+
+    def adopt_device_copy(self, dev, pair):
+        pass
+
     def as_oracle(self):
         return self.lam, self.U
 
@@ -262,7 +277,7 @@ def electron_factors(efric, exim, exip, bias, T, ecut, dt, nmd, classical=False,
 
 
 # ------------------------------------------------------------------ device pipeline
-MAX_WORK_BYTES = 12 << 30    # FFT scratch bound for noise generation
+MAX_WORK_BYTES = 8 << 30     # scratch bound (FFT ping-pong + white-noise chunk) for noise generation
 
 _SCRATCH = {}
 
@@ -307,6 +322,31 @@ def generate(factors, xi, dt, nmd, out=None):
     for n0 in range(0, ldb, cw):
         n1 = min(ldb, n0 + cw)
         _lib.call("pymd_noise_generate", lre.data_ptr(), _lib.ptr(lim), xi.data_ptr(), nmd, nc, ldb, n0, n1,
+                  float(dt), out.data_ptr(), work.data_ptr(), _lib.stream_ptr())
+    return out
+
+
+def generate_philox(factors, dt, nmd, ldb, batch, seed, stream_id, traj0, out):
+    """noise[t][i][traj] from spectral factors and the library's Philox normals, one trajectory chunk at a time:
+    the white noise (nf x nc x ldb doubles, 16 GB for the 60-dof bath of 2048 trajectories) never exists as a
+    whole.  Element (f, i, traj0 + n) of the white noise is the same whatever the chunking or the sharding."""
+    import torch
+    nf, nc, _ = factors.shape
+    dev = out.device
+    lre, lim = factors.device_factors(dev)
+    per_col = _lib.load().pymd_noise_work_bytes(nmd, nc, 1) + 8 * nf * nc
+    cw = max(32, min(ldb, (MAX_WORK_BYTES // per_col) // 32 * 32))
+    work = _scratch(per_col * cw, dev)
+    wbytes = _lib.load().pymd_noise_work_bytes(nmd, nc, cw)
+    xi = work[wbytes:wbytes + 8 * nf * nc * cw].view(torch.float64)
+    for n0 in range(0, ldb, cw):
+        w = min(cw, ldb - n0)
+        x = xi[:nf * nc * w].view(nf, nc, w)
+        _lib.call("pymd_philox_normal", x.data_ptr(), nf * nc, w, int(seed) & (2 ** 64 - 1),
+                  int(stream_id) & 0xFFFFFFFF, int(traj0) + n0, _lib.stream_ptr())
+        if n0 + w > batch:
+            x[:, :, max(batch - n0, 0):] = 0.0          # padding trajectories stay at rest
+        _lib.call("pymd_noise_generate_chunk", lre.data_ptr(), _lib.ptr(lim), x.data_ptr(), w, nmd, nc, ldb, n0,
                   float(dt), out.data_ptr(), work.data_ptr(), _lib.stream_ptr())
     return out
 

@@ -7,9 +7,10 @@ from . import _lib
 MAX_CHUNK_BYTES = 8 << 30
 
 
-def ensemble_powerspec(traj_dev, dt, nmd, nvalid, wsq):
+def ensemble_powerspec(traj_dev, dt, nmd, nvalid, wsq, host=True):
     """sum over dofs and over the first ``nvalid`` trajectories of |Fourier1D(x)|^2/(dt nmd)
-    (times w_i^2 when wsq) for a device array [nmd][nd][ldb]; returns a host vector (nmd,)."""
+    (times w_i^2 when wsq) for a device array [nmd][nd][ldb]; returns a host vector (nmd,)
+    (``host=False``: the device tensor, no synchronisation)."""
     import torch
     lib = _lib.load()
     n, nd, ldb = traj_dev.shape
@@ -22,7 +23,7 @@ def ensemble_powerspec(traj_dev, dt, nmd, nvalid, wsq):
                        device=traj_dev.device)
     _lib.call("pymd_powerspec", traj_dev.data_ptr(), nmd, nd, ldb, int(nvalid), float(dt), 1 if wsq else 0,
               out.data_ptr(), work.data_ptr(), chunk, _lib.stream_ptr())
-    return out.cpu().numpy()
+    return out.cpu().numpy() if host else out
 
 
 def _single(xs, dt, nmd, wsq):

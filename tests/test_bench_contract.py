@@ -28,7 +28,16 @@ def test_algorithmic_flop_accounting_matches_the_survey():
     and the per-kernel split adds up to it."""
     sys.path.insert(0, ROOT)
     import bench
-    fl = bench.algorithmic_flops()
-    assert fl["total"] == 142200
+    c = bench.workload("cfg2", 1)
+    fl = bench.algorithmic(c)
+    assert fl["total"] == 142200 and fl["bytes"] == 8 * (90 + 3 + 1)
     assert abs(fl["fused"] + fl["tail"] - fl["total"]) < 1e-9
     assert fl["far_executed"] < 0.2 * fl["tail"]
+    assert bench.default_piece(c) == 8192
+    # config 4 stretch: 2 nd^2 + 2 x 2 (ml + 2) nc^2 without the electron bath
+    s = bench.algorithmic(bench.workload("cfg4s", 1))
+    assert s["total"] == 2 * 510 ** 2 + 2 * 2 * 2002 * 81 ** 2
+    # config 3 is the strong-scaling layout: 8192 trajectories over the GPUs of the box
+    assert bench.workload("cfg3", 8)["batch"] == 1024 and bench.workload("cfg3", 8)["scaling"] == "strong"
+    w = bench.workload("sweep:256,1000,4096", 1)
+    assert (w["nd"], w["ml"], w["batch"], w["ncl"]) == (255, 1000, 4096, 63)

@@ -164,13 +164,15 @@ def test_switching_between_step_modes(cuda, case):
         assert T.relerr(m.p[..., n], om.p) < TOL and T.relerr(m.q[..., n], om.q) < TOL
 
 
-@pytest.mark.parametrize("nt", ["1", "2", "4"])
-@pytest.mark.parametrize("case", ["aubz", "chain39", "ragged"])
-def test_fused_tile_sizes(cuda, case, nt, monkeypatch):
+@pytest.mark.parametrize("nt,f3", [("1", "1"), ("2", "1"), ("4", "1"), ("2", "0"), ("4", "0")])
+@pytest.mark.parametrize("case", ["aubz", "chain39", "ragged", "cfg4"])
+def test_fused_tile_sizes(cuda, case, nt, f3, monkeypatch):
     """Every trajectory-tile size of the fused kernel (8, 16, 32 trajectories per CTA), forced
     through the PYMD_FUSED_NT testing knob, against the oracle; 40 trajectories so that tiles are
-    partially padded and several CTAs run."""
+    partially padded and several CTAs run.  16- and 32-trajectory tiles take the two-unit kernel
+    (fused3.cu) by default and the single-unit warp-specialised one (fused2) with PYMD_FUSED3=0."""
     monkeypatch.setenv("PYMD_FUSED_NT", nt)
+    monkeypatch.setenv("PYMD_FUSED3", f3)
     c = T.CASES[case]
     B = 40
     m, j = T.device_md(c, B, step_mode=2)
@@ -273,34 +275,39 @@ def test_run_matches_oracle_run(cuda):
     assert np.abs(cm - ocm).max() < 1e-9 * np.abs(ocm).max()
 
 
-def test_size_independent_properties_at_scale(cuda):
+def test_size_independent_properties_at_scale(cuda, monkeypatch):
     """Properties checked at an ensemble size the oracle cannot follow (B = 4096, AuBZ shape):
-    (1) trajectory n is independent of the ensemble it runs in (bit-identical in B=4096 and B=32);
+    (1) trajectory n is independent of the ensemble it runs in: bit-identical in an ensemble of 4091 and in one
+        of 32 placed at the same global indices when both use the same trajectory tile (the kernels differ in
+        their summation order, so across tile sizes the agreement is to rounding: 1e-12);
     (2) the dynamics are linear: doubling noise and initial state doubles the trajectory;
     (3) padded trajectories stay exactly at rest; (4) all finite."""
     c = dict(T.CASES["aubz"]); c["nmd"] = 64
-    big, _ = T.device_md(c, 4096 - 5, savepq=False, seed=9)
-    big.initialise(); big.ResetHis()
-    for b in big.baths:
-        b.gnoi()
-    big.steps(48)
+
+    def run(B, traj0=0, scale=1.0):
+        m, _ = T.device_md(c, B, savepq=False, seed=9, traj0=traj0)
+        m.initialise(); m.ResetHis()
+        if scale != 1.0:
+            m.p, m.q = scale * np.asarray(m.p), scale * np.asarray(m.q)
+        for b in m.baths:
+            b.gnoi()
+            if scale != 1.0:
+                b._noise_dev.mul_(scale)
+        m.steps(48)
+        return m
+
+    monkeypatch.setenv("PYMD_FUSED_NT", "4")
+    big = run(4096 - 5)
     pb, qb = big.p, big.q
     assert np.isfinite(pb).all() and np.isfinite(qb).all()
     assert float(big._p[:, big.batch:].abs().max()) == 0.0
-    small, _ = T.device_md(c, 32, savepq=False, seed=9, traj0=64)
-    small.initialise(); small.ResetHis()
-    for b in small.baths:
-        b.gnoi()
-    small.steps(48)
+    small = run(32, traj0=64)
     assert np.array_equal(small.p, pb[:, 64:96]) and np.array_equal(small.q, qb[:, 64:96])
-    dbl, _ = T.device_md(c, 32, savepq=False, seed=9, traj0=64)
-    dbl.initialise(); dbl.ResetHis()
-    dbl.p, dbl.q = 2.0 * np.asarray(dbl.p), 2.0 * np.asarray(dbl.q)
-    for b in dbl.baths:
-        b.gnoi()
-        b._noise_dev.mul_(2.0)
-    dbl.steps(48)
+    dbl = run(32, traj0=64, scale=2.0)
     assert T.relerr(dbl.p, 2.0 * small.p) < 1e-12
+    monkeypatch.delenv("PYMD_FUSED_NT")
+    auto = run(32, traj0=64)                    # the tile size the library picks for 32 trajectories
+    assert T.relerr(auto.p, pb[:, 64:96]) < 1e-12 and T.relerr(auto.q, qb[:, 64:96]) < 1e-12
 
 
 def test_external_driver_is_refused(cuda):
