@@ -148,6 +148,12 @@ size_t pymd_powerspec_work_bytes(int nmd, int nd, int ldb, long long chunk_cols)
 int pymd_powerspec(const double* traj_dev, int nmd, int nd, int ldb, int nvalid, double dt, int wsq,
                    double* out_dev, void* work_dev, long long chunk_cols, void* stream);
 
+/* Time means of per-trajectory records (the kappa.*.dat numbers of md.Run, md.py:619: mean over the nmd rows of
+ * bath.cur; likewise md.etot): out[n] = scale * sum_r a[r][n] for a dev [rows][ldb], deterministic (fixed chunking).
+ * work: dev scratch of pymd_column_sums_work_bytes(ldb). */
+size_t pymd_column_sums_work_bytes(int ldb);
+int pymd_column_sums(const double* a_dev, long long rows, int ldb, double scale, double* out_dev, void* work_dev, void* stream);
+
 /* Batched complex FFT along the slowest axis: data dev [n][cols] complex128 in place,
  * sign = -1 (numpy fft) or +1 (numpy ifft, unscaled). */
 int pymd_fft_columns(double* data_dev, int n, long long cols, int sign, void* work_dev, void* stream);

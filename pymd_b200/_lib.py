@@ -49,6 +49,8 @@ PROTOTYPES = {
     "pymd_powerspec_work_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_longlong]),
     "pymd_powerspec": (C.c_int, [c_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, c_dp, c_dp,
                                  C.c_longlong, c_dp]),
+    "pymd_column_sums_work_bytes": (C.c_size_t, [C.c_int]),
+    "pymd_column_sums": (C.c_int, [c_dp, C.c_longlong, C.c_int, C.c_double, c_dp, c_dp, c_dp]),
     "pymd_fft_columns": (C.c_int, [c_dp, C.c_int, C.c_longlong, C.c_int, c_dp, c_dp]),
     "pymd_fft_work_bytes": (C.c_size_t, [C.c_int, C.c_longlong]),
     "pymd_fft_num_passes": (C.c_int, [C.c_int]),

@@ -41,7 +41,7 @@ struct Slots {
 
 // ------------------------------------------------------------------ stage kernels
 // block = (32 trajectories, 8 row lanes); a thread walks rows y, y+8, ... of one trajectory.
-constexpr int TX = 32, TY = 8;
+constexpr int TX = 8, TY = 32;     // 8 trajectories x 32 row lanes per CTA: ldb / 8 CTAs (a 1024-trajectory ensemble fills 128 SMs)
 
 __device__ __forceinline__ double block_rows_sum(double v, double (*red)[TX]) {
     red[threadIdx.y][threadIdx.x] = v;
@@ -234,6 +234,8 @@ int finalize(pymd_ctx* c) {
         PYMD_REQUIRE(c->sd.b[b].noise, "pymd_step: bath %d has no noise bound (call gnoi)", b);
         PYMD_REQUIRE(c->sd.b[b].cur, "pymd_step: bath %d has no current buffer bound", b);
         PYMD_REQUIRE(H.ml == 1 || c->sd.b[b].ring, "pymd_step: bath %d (ml=%d) has no history bound", b, H.ml);
+        fdl_free(H);                              // rebuilt on the first per-step-pipeline call that wants it
+        H.fdl_tried = false;
         const int nc = H.nc;
         H.lda = round_up(nc, 32);
         const double alpha = H.dt_scaled ? c->dt : 1.0;
@@ -427,8 +429,28 @@ static int generic_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) 
     // rows per bath (the velocity history is read once per GT steps instead of every step); the rows that
     // enter during the block are added per step by a small product over the s+1 newest ring rows.
     constexpr int GT = 8;
-    for (int s0 = 0; s0 < nsteps; s0 += GT) {
-        const int T = std::min(GT, nsteps - s0);
+    for (int b = 0; b < c->nbath; ++b) {
+        BathHost& H = c->bath[b];
+        if (H.ml > 1 && !H.fdl_tried) {
+            H.fdl_tried = true;
+            if (fdl_wanted(c, H) && (rc = fdl_build(c, b))) return rc;
+        }
+    }
+    for (int s0 = 0, T = 0; s0 < nsteps; s0 += T) {
+        T = std::min(GT, nsteps - s0);
+        // long memories: rows older than the current super-block of L steps come from the frequency-domain delay
+        // line (fdl.cu); a block of GT steps never straddles two super-blocks
+        long long r0[PYMD_MAX_BATHS] = {};
+        for (int b = 0; b < c->nbath; ++b) {
+            BathHost& H = c->bath[b];
+            if (H.ml <= 1 || !H.fdl_L) continue;
+            r0[b] = H.hcount - H.fdl_base;
+            if (!H.fdl_valid || r0[b] < 0 || r0[b] >= H.fdl_L) {
+                if ((rc = fdl_advance(c, b, st))) return rc;
+                r0[b] = 0;
+            }
+            T = std::min<long long>(T, H.fdl_L - r0[b]);
+        }
         double* Pblk[PYMD_MAX_BATHS] = {};
         for (int b = 0; b < c->nbath; ++b) {
             BathHost& H = c->bath[b];
@@ -436,7 +458,11 @@ static int generic_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) 
             // the buffer that does not hold tail(t) of the step about to start
             const bool inA = d.b[b].tail_cur >= H.d_tailA && d.b[b].tail_cur < H.d_tailA + (size_t)kBlockT * H.nc * c->ldb;
             Pblk[b] = inA ? H.d_tailB : H.d_tailA;
-            if ((rc = launch_tail(c, b, T, 2, Pblk[b], st))) return rc;
+            if (H.fdl_L) {
+                PYMD_CUDA_CHECK(cudaMemcpyAsync(Pblk[b], H.d_fdlF + (size_t)r0[b] * H.nc * c->ldb,
+                                                (size_t)T * H.nc * c->ldb * sizeof(double), cudaMemcpyDeviceToDevice, st));
+                if ((rc = launch_tail(c, b, T, 2, Pblk[b], st, r0[b], 1))) return rc;
+            } else if ((rc = launch_tail(c, b, T, 2, Pblk[b], st))) return rc;
         }
         for (int s = s0; s < s0 + T; ++s) {
             const long long t = t0 + s;
@@ -536,6 +562,7 @@ int pymd_ctx_destroy(pymd_ctx* c) {
     if (!c) return PYMD_OK;
     for (auto& H : c->bath) {
         cudaFree(H.d_cids); cudaFree(H.d_inv); cudaFree(H.d_head); cudaFree(H.d_aq);
+        fdl_free(H);
         cudaFree(H.d_krev); cudaFree(H.d_kintra); cudaFree(H.d_ghat); cudaFree(H.d_far); cudaFree(H.d_kmid); cudaFree(H.d_kinf); cudaFree(H.d_hdf);
     }
     cudaFree(c->d_dyn); cudaFree(c->d_mp); cudaFree(c->d_con); cudaFree(c->d_aqT); cudaFree(c->d_con3); cudaFree(c->ws);
@@ -603,6 +630,7 @@ int pymd_bind_history(pymd_ctx* c, int b, double* ring, int ring_len) {
     c->sd.b[b].ring = ring;
     c->bath[b].R = ring_len;
     c->bath[b].hcount = 0;
+    c->bath[b].fdl_valid = false;
     c->finalized = false;
     return PYMD_OK;
 }
@@ -634,6 +662,7 @@ int pymd_reset_history(pymd_ctx* c, void* stream) {
             PYMD_CUDA_CHECK(cudaMemsetAsync(c->sd.b[b].ring, 0, (size_t)H.R * H.ncp * c->ldb * sizeof(double), st));
         H.hcount = 0;
         H.far_valid = false;
+        H.fdl_valid = false;
     }
     c->tail_valid = false;
     return PYMD_OK;
@@ -655,6 +684,7 @@ static int history_copy(pymd_ctx* c, int b, double* dense, int nrows, int to_rin
                                         static_cast<cudaStream_t>(stream)));
         H.hcount = nrows;
         H.far_valid = false;
+        H.fdl_valid = false;
         c->tail_valid = false;
     }
     history_copy_kernel<<<592, 256, 0, static_cast<cudaStream_t>(stream)>>>(

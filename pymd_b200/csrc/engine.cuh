@@ -60,6 +60,15 @@ struct BathHost {
     double* d_kmid = nullptr;     // [kMidK][ncp/8][ncp/4][32] A fragments of dt K[k], k = 2.. (fused mid field)
     bool far_valid = false;
     long long far_base = 0;       // hcount at the start of the super-block d_far belongs to
+    // fdl.cu: frequency-domain delay line of the per-step pipeline (long memories, any nc)
+    int fdl_L = 0, fdl_P = 0, fdl_head = 0;   // partition length, partitions, ring slot of the newest block spectrum
+    bool fdl_valid = false, fdl_tried = false;
+    long long fdl_base = 0;       // hcount at the start of the super-block d_fdlF belongs to
+    double* d_fdlA = nullptr;     // [L+1][2 nc][P * 2 ncp]  real block form of Ghat_p(f), partitions in reversed order
+    double* d_fdlS = nullptr;     // [L+1][P][2][ncp][ldb]   spectra of the last P history blocks
+    double* d_fdlY = nullptr;     // [L+1][2][nc][ldb]
+    double* d_fdlF = nullptr;     // [L][nc][ldb]            far field of the current super-block
+    double* d_fdlZ = nullptr;     // 3 x [2L][ncp * ldb] complex work (FFT source and ping-pong buffers)
     long long Lk = 0;
     int padf = 0;
     int lda = 0;
@@ -92,6 +101,10 @@ struct pymd_ctx {
 };
 
 namespace pymd {
+bool fdl_wanted(const pymd_ctx* c, const BathHost& H);
+int fdl_build(pymd_ctx* c, int b);
+int fdl_advance(pymd_ctx* c, int b, cudaStream_t st);
+void fdl_free(BathHost& H);
 bool far_supported(const BathHost& H);
 int far_build(pymd_ctx* c, int b);
 int far_launch(pymd_ctx* c, unsigned mask, cudaStream_t st);

@@ -21,7 +21,10 @@ struct __align__(16) Smem {
 };
 
 template <int BM, int BN, int STAGES, int WM, int WN, int NPROD>
-__global__ void __launch_bounds__((WM * WN + NPROD) * 32) gemm_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__((WM * WN + NPROD) * 32) gemm_kernel(GemmArgs g) {
+    g.a_base += (long long)blockIdx.z * g.a_bs;
+    g.x_base += (long long)blockIdx.z * g.x_bs;
+    g.y_base += (long long)blockIdx.z * g.y_bs;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<BM, BN, STAGES>& s = *reinterpret_cast<Smem<BM, BN, STAGES>*>(smem_raw);
     constexpr int LDB = BN + 4;
@@ -151,7 +154,7 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM);
+    dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.nbatch > 1 ? a.nbatch : 1);
     gemm_kernel<BM, BN, STAGES, WM, WN, NPROD><<<grid, (WM * WN + NPROD) * 32, smem, stream>>>(a);
     PYMD_CUDA_CHECK(cudaGetLastError());
     return PYMD_OK;
@@ -172,8 +175,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
         const long long per_sm = (ctas + 147) / 148;
         return (double)ctas / (double)(per_sm * 148);
     };
-    const long long c64 = (long long)((a.N + 63) / 64) * ((a.M + 63) / 64);
-    const long long c32 = (long long)((a.N + 31) / 32) * ((a.M + 31) / 32);
+    const long long nbz = a.nbatch > 1 ? a.nbatch : 1;
+    PYMD_REQUIRE(nbz <= 65535 && (a.a_bs % 2) == 0 && (a.x_bs % 2) == 0 && (a.y_bs % 2) == 0, "gemm: bad batch nbatch=%d", a.nbatch);
+    const long long c64 = nbz * ((a.N + 63) / 64) * ((a.M + 63) / 64);
+    const long long c32 = nbz * ((a.N + 31) / 32) * ((a.M + 31) / 32);
     const double pad64 = (double)a.M / (double)(((a.M + 63) / 64) * 64);
     const double pad32 = (double)a.M / (double)(((a.M + 31) / 32) * 32);
     const double e64 = fill(c64) * 0.9 * pad64, e32 = fill(c32) * 0.45 * pad32;

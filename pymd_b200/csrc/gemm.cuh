@@ -31,6 +31,9 @@ struct GemmArgs {
     long long seg_aoff[2];
     double alpha;
     int accumulate;
+    // batch of independent products (grid.z): operand bases advance by these strides (doubles) per batch index
+    int nbatch = 1;
+    long long a_bs = 0, x_bs = 0, y_bs = 0;
 };
 
 // Launch on `stream`; returns a PYMD_* status.

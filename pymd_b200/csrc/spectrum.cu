@@ -76,6 +76,32 @@ __global__ void power_final_kernel(const double* __restrict__ partial, int ncb_t
 
 using namespace pymd;
 
+// column sums of a [rows][ldb] array in two deterministic stages: CS_CHUNKS row chunks, then their fixed-order sum
+namespace pymd {
+namespace {
+constexpr int CS_CHUNKS = 64;
+__global__ void colsum_partial_kernel(const double* a, long long rows, int ldb, double* partial) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= ldb) return;
+    const long long per = (rows + CS_CHUNKS - 1) / CS_CHUNKS, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    long long r = r0;
+    for (; r + 3 < r1; r += 4) {
+        s0 += a[r * ldb + n]; s1 += a[(r + 1) * ldb + n]; s2 += a[(r + 2) * ldb + n]; s3 += a[(r + 3) * ldb + n];
+    }
+    for (; r < r1; ++r) s0 += a[r * ldb + n];
+    partial[(size_t)blockIdx.y * ldb + n] = (s0 + s1) + (s2 + s3);
+}
+__global__ void colsum_final_kernel(const double* partial, int ldb, double scale, double* out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= ldb) return;
+    double s = 0.0;
+    for (int c = 0; c < CS_CHUNKS; ++c) s += partial[(size_t)c * ldb + n];
+    out[n] = scale * s;
+}
+}  // namespace
+}  // namespace pymd
+
 extern "C" {
 
 static long long ps_chunk(long long total, long long chunk) {
@@ -128,6 +154,17 @@ int pymd_powerspec(const double* traj, int nmd, int nd, int ldb, int nvalid, dou
     PYMD_CUDA_CHECK(cudaGetLastError());
     return PYMD_OK;
 }
+
+int pymd_column_sums(const double* a_dev, long long rows, int ldb, double scale, double* out_dev, void* work_dev, void* stream) {
+    PYMD_REQUIRE(a_dev && out_dev && work_dev && rows > 0 && ldb > 0, "column_sums: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* partial = static_cast<double*>(work_dev);
+    colsum_partial_kernel<<<dim3((ldb + 127) / 128, CS_CHUNKS), 128, 0, st>>>(a_dev, rows, ldb, partial);
+    colsum_final_kernel<<<(ldb + 127) / 128, 128, 0, st>>>(partial, ldb, scale, out_dev);
+    PYMD_CUDA_CHECK(cudaGetLastError());
+    return PYMD_OK;
+}
+size_t pymd_column_sums_work_bytes(int ldb) { return (size_t)CS_CHUNKS * ldb * sizeof(double); }
 
 size_t pymd_fft_work_bytes(int n, long long cols) { return 2 * (size_t)n * cols * sizeof(double2); }
 

@@ -48,10 +48,11 @@ def ensemble_average(mdrun, batch_total):
     mean currents (nW) and their standard errors, and the mean kinetic energy."""
     from . import units as U
     nb = len(mdrun.baths)
-    cur_t = [b._cur_dev[:, :mdrun.batch].mean(0) for b in mdrun.baths]          # time mean per trajectory
+    from .spectrum import time_means
+    cur_t = [time_means(b._cur_dev)[:mdrun.batch] for b in mdrun.baths]         # time mean per trajectory
     cur_sum = N.array([float(c.sum().item()) for c in cur_t])
     cur_sq = N.array([float((c * c).sum().item()) for c in cur_t])
-    ek = float(mdrun._etot[:, :mdrun.batch].mean(0).sum().item())
+    ek = float(time_means(mdrun._etot)[:mdrun.batch].sum().item())
     p1 = getattr(mdrun, "power_sum", N.zeros(mdrun.nmd))
     p2 = getattr(mdrun, "power2_sum", N.zeros(mdrun.nmd))
     p1, p2, cur_sum, cur_sq, ekv = allreduce_sums([p1, p2, cur_sum, cur_sq, N.array([ek])])
@@ -81,7 +82,7 @@ def run_pipelined(mdrun, batch_total, traj0=0, segment=0, overlap=False, reuploa
     local trajectories, ready for ensemble.allreduce_sums; one device->host copy at the end."""
     import time
     import torch
-    from .spectrum import ensemble_powerspec
+    from .spectrum import ensemble_powerspec, time_means
     Be = mdrun.batch
     if batch_total % Be:
         raise ValueError("run_pipelined: batch_total must be a multiple of md.batch")
@@ -165,11 +166,12 @@ def run_pipelined(mdrun, batch_total, traj0=0, segment=0, overlap=False, reuploa
                 generate(s + 1)
             acc_p += s1
             acc_p2 += s2
+            # time means per trajectory: one pass over each [nmd][ldb] record
             for i, b in enumerate(baths):
-                ct = b._cur_dev[:, :Be].mean(0)
+                ct = time_means(b._cur_dev)[:Be]
                 acc_c[0, i] += ct.sum()
                 acc_c[1, i] += (ct * ct).sum()
-            acc_e += mdrun._etot[:, :Be].mean(0).sum()
+            acc_e += time_means(mdrun._etot)[:Be].sum()
             tev[s][3].record(main)
     main.synchronize()
     side.synchronize()

@@ -575,8 +575,9 @@ class md(object):
                 self.power = (power * j + self.power) / float(j + 1)       # md.py:604-607
                 self.power2 = (power2 * j + self.power2) / float(j + 1)
             self.dump(self.npie - 1, j)
+            from .spectrum import time_means
             for ii, b in enumerate(self.baths):
-                self.curmean[j, ii] = float(b._cur_dev[:, :self.batch].mean().item()) * U.curcof
+                self.curmean[j, ii] = float(time_means(b._cur_dev)[:self.batch].mean().item()) * U.curcof
             if self.write_files:
                 self._write_outputs(j)
 

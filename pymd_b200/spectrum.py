@@ -26,6 +26,19 @@ def ensemble_powerspec(traj_dev, dt, nmd, nvalid, wsq, host=True):
     return out.cpu().numpy() if host else out
 
 
+def time_means(rec_dev, out=None):
+    """Per-trajectory time mean of a device record [rows][ldb] (bath.cur, md.etot): device vector [ldb]."""
+    import torch
+    lib = _lib.load()
+    rows, ldb = rec_dev.shape
+    if out is None:
+        out = torch.empty(ldb, dtype=torch.float64, device=rec_dev.device)
+    work = torch.empty(lib.pymd_column_sums_work_bytes(ldb), dtype=torch.uint8, device=rec_dev.device)
+    _lib.call("pymd_column_sums", rec_dev.data_ptr(), rows, ldb, 1.0 / rows, out.data_ptr(), work.data_ptr(),
+              _lib.stream_ptr())
+    return out
+
+
 def _single(xs, dt, nmd, wsq):
     import torch
     a = N.asarray(xs, dtype=N.float64)

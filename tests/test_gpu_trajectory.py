@@ -640,3 +640,43 @@ def test_several_constraint_vectors(cuda, case, batch, mode):
     pipeline explicitly; also through md.initialise (constraints applied after every mode, md.py:284-285)."""
     m = _parity_run(case, batch, mode, seed=47, chunks=[2, 7, 13], trajs=sorted({0, batch - 1}))
     assert np.asarray(m.constraint).shape[0] == T.CASES[case]["nconstr"]
+
+
+@pytest.mark.parametrize("case,nmd,ml,batch", [("chain39", 512, 250, 5), ("ragged", 256, 130, 33), ("chain39", 256, 64, 2)])
+def test_delay_line_far_field_of_the_per_step_pipeline(cuda, case, nmd, ml, batch, monkeypatch):
+    """csrc/fdl.cu: the frequency-domain delay line (partitioned fast convolution, partitions of 32 / 64 steps) that
+    the per-step pipeline uses for memories of 64 steps and more, against the direct block-Toeplitz product
+    (PYMD_FDL=0) and against the oracle, over several super-blocks, with ragged steps() calls (super-blocks start at
+    arbitrary times), a switch to the fused kernel and back in the middle (the delay line is rebuilt from the
+    velocity ring), and a history restore."""
+    c = dict(T.CASES[case]); c["nmd"] = nmd; c["ml"] = ml
+    runs = {}
+    for fdl in ("1", "0"):
+        monkeypatch.setenv("PYMD_FDL", fdl)
+        m, j = T.device_md(c, batch, step_mode=1)
+        xi, r = T.draw(c, m, batch, seed=19)
+        m.initialise(r=r)
+        m.ResetHis()
+        for b, bath in enumerate(m.baths):
+            bath.gnoi(xi=xi[0][b])
+        m.ResetSavepq()
+        done = 0
+        for i, n in enumerate([5, 40, 1, 70, 33, 64, 9]):
+            n = min(n, nmd - done)
+            if not n:
+                break
+            m.step_mode = 2 if i == 3 else 1            # one stretch on the on-chip kernels
+            m.steps(n)
+            done += n
+            if i == 4:
+                m.set_history(m.phis)                   # history restore: the delay line starts again from the ring
+        m.step_mode = 1
+        m.steps(nmd - done)
+        runs[fdl] = (m, [np.array(b.cur) for b in m.baths], np.array(m.ps), np.array(m.qs))
+    (m1, cur1, ps1, qs1), (m0, cur0, ps0, qs0) = runs["1"], runs["0"]
+    assert T.relerr(ps1, ps0) < 1e-12 and T.relerr(qs1, qs0) < 1e-12
+    for a, b in zip(cur1, cur0):
+        assert np.abs(a - b).max() < 1e-11 * max(np.abs(b).max(), 1e-300)
+    n = batch - 1
+    om, recs = T.run_oracle(c, j, m1, xi, r, n, nmd)
+    compare(m1, recs[0], n, tol=3e-11)

@@ -4,7 +4,7 @@ set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 OUT=/tmp/pymd_timing_build
 mkdir -p $OUT
-for f in engine gemm fused fused3 local far fft noise spectrum init setup; do
+for f in engine gemm fused fused3 local far fdl fft noise spectrum init setup; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -DPYMD_FUSED_TIMING \
        -c $ROOT/pymd_b200/csrc/$f.cu -o $OUT/$f.o &
 done
