@@ -194,8 +194,10 @@ __device__ __forceinline__ void zmid_phase(const FusedParams& P, double* sm, int
     zbar_sync(bar_R(u), ZRW * 32);                      // staging buffer (a head buffer) free again
 }
 
-// NJ: n8 tiles per unit; KS: k-steps of the nd x nd operators (15 when nd <= 60, else 16)
-template <int NJ, bool HASQ, bool HASCON, int KS>
+// NJ: n8 tiles per unit; KS: k-steps of the nd x nd operators (15 when nd <= 60, else 16); SPEC = 1: the usual bath
+// layout (a direct remainder bath first, then exactly two shared-memory baths: AuBZ, Au6_3x3) with the per-row bath
+// loop unrolled without conditions
+template <int NJ, bool HASQ, bool HASCON, int KS, int SPEC>
 __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
     constexpr int N = ZU * 8 * NJ, LD = N + 4, NU = 8 * NJ;
     extern __shared__ __align__(16) double sm[];
@@ -370,24 +372,46 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
                     }
                 }
         };
-        // base + sum over the baths, in bath order (the order fused2 and the 8-warp kernel add them in), of
-        // noise-minus-tail in buffer `buf` for entry (m, j): shared-memory rows of the small baths, `nz` for the
-        // direct remainder bath.  The remainder bath's own share (when it is a shared-memory bath) is returned too.
-        auto nb_sum = [&](int buf, int m, int j, double2 f, double nz0, double nz1, double2& rem_part) {
-            rem_part = make_double2(0.0, 0.0);
+        // noise-minus-tail rows of the shared-memory baths in buffer `buf` for entry (m, j): loads only (all entries
+        // of a round are loaded before any of them is used or stored, so that the loads overlap)
+        constexpr int NSL = SPEC ? 2 : FB_MAX;
+        auto nb_load = [&](int buf, int m, int j, double2 (&v)[NSL]) {
             const double* base = sm + P.off_nb3 + buf * P.nbstride + cu + 8 * j + 2 * lc;
+#pragma unroll
+            for (int i = 0; i < NSL; ++i) {
+                v[i] = make_double2(0.0, 0.0);
+                if (SPEC || i < P.nsm) v[i] = ld2(base + ((nbpk[m] >> (8 * i)) & 255u) * LD);
+            }
+        };
+        // f + sum over the baths, in bath order (the order fused2 and the 8-warp kernel add them in): `nz` for the
+        // direct remainder bath at its position; the remainder bath's own share (a shared-memory bath) is returned too
+        auto nb_add = [&](double2 f, const double2 (&v)[NSL], double nz0, double nz1, double2& rem_part) {
+            rem_part = make_double2(0.0, 0.0);
+            if (SPEC) {
+                f.x += nz0; f.y += nz1;
+                f.x += v[0].x; f.y += v[0].y;
+                f.x += v[1].x; f.y += v[1].y;
+                return f;
+            }
 #pragma unroll
             for (int i = 0; i <= FB_MAX; ++i) {
                 if (i == P.dpos) { f.x += nz0; f.y += nz1; }
                 if (i < FB_MAX && i < P.nsm) {
-                    const double2 v = ld2(base + ((nbpk[m] >> (8 * i)) & 255u) * LD);
-                    f.x += v.x; f.y += v.y;
-                    if (i == P.remi) rem_part = v;
+                    f.x += v[i < NSL ? i : 0].x; f.y += v[i < NSL ? i : 0].y;
+                    if (i == P.remi) rem_part = v[i < NSL ? i : 0];
                 }
             }
             return f;
         };
 
+        // ring slot that receives p_c(t+1) of the current step, per shared-memory bath (counted, not divided)
+        int rslot[NSL], rmod[NSL];
+#pragma unroll
+        for (int i = 0; i < NSL; ++i) {
+            const FusedBath& B = P.b[SPEC ? i + 1 : P.smb[i < P.nsm ? i : 0]];
+            rmod[i] = B.R;
+            rslot[i] = (B.slot0 + 1) % B.R;
+        }
         double fpot[2][NJ][2], uq[2][NJ][2], fb[2][NJ][2];
         zero3(fpot); zero3(uq); zero3(fb);
         int nbuf = 0;
@@ -438,33 +462,51 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
                     double v[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = 0.0;
+                    // stage 1: every shared-memory load; stage 2: arithmetic; stage 3: the stores (a store between
+                    // two entries would order the loads of the second behind it)
+                    double2 pvv[2][NJ], qvv[2][NJ], nbv[2][NJ][NSL];
+#pragma unroll
+                    for (int m = 0; m < 2; ++m)
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            pvv[m][j] = live[m] ? ld2(&sm[xpc + own[m] + 8 * j]) : make_double2(0.0, 0.0);
+                            qvv[m][j] = ld2(&sm[xq + own[m] + 8 * j]);
+                            nb_load(nbuf, m, j, nbv[m][j]);
+                        }
+                    double2 phv[2][NJ], qnv[2][NJ];
 #pragma unroll
                     for (int m = 0; m < 2; ++m) {
 #pragma unroll
                         for (int j = 0; j < NJ; ++j) {
-                            const int n = cu + 8 * j + 2 * lc;
-                            const double2 pv = live[m] ? ld2(&sm[xpc + own[m] + 8 * j]) : make_double2(0.0, 0.0);
-                            const double2 qv = ld2(&sm[xq + own[m] + 8 * j]);
+                            const double2 pv = pvv[m][j], qv = qvv[m][j];
                             double2 cr;
-                            const double2 fs = nb_sum(nbuf, m, j, make_double2(fpot[m][j][0] + uq[m][j][0] - hA[m][j][0],
-                                                                               fpot[m][j][1] + uq[m][j][1] - hA[m][j][1]),
-                                                      nzr[m][j][0], nzr[m][j][1], cr);
+                            const double2 fs = nb_add(make_double2(fpot[m][j][0] + uq[m][j][0] - hA[m][j][0],
+                                                                   fpot[m][j][1] + uq[m][j][1] - hA[m][j][1]),
+                                                      nbv[m][j], nzr[m][j][0], nzr[m][j][1], cr);
                             const double f0 = fs.x, f1 = fs.y;
                             // force of the remainder bath on this row: its noise (minus tail), minus ALL heads (the
                             // heads of the small baths on shared dofs are added back by the bath warps), plus AqT q
                             double c0 = cr.x + nzr[m][j][0] - mrem[m] * hA[m][j][0];
                             double c1 = cr.y + nzr[m][j][1] - mrem[m] * hA[m][j][1];
                             if (HASQ) { c0 += mrem[m] * uq[m][j][0]; c1 += mrem[m] * uq[m][j][1]; }
-                            if (live[m]) {
-                                st2(&sm[xpn + own[m] + 8 * j], pv.x + f0 * dt / 2.0, pv.y + f1 * dt / 2.0);
-                                st2(&sm[xq + own[m] + 8 * j], qv.x + pv.x * dt + f0 * dt2 / 2.0, qv.y + pv.y * dt + f1 * dt2 / 2.0);
-                                if (P.ps) st2(&P.ps[((size_t)tn_cur * nd + row[m]) * ldb + col0 + n], pv.x, pv.y);
-                                if (P.qs) st2(&P.qs[((size_t)tn_cur * nd + row[m]) * ldb + col0 + n], qv.x, qv.y);
-                            }
+                            phv[m][j] = make_double2(pv.x + f0 * dt / 2.0, pv.y + f1 * dt / 2.0);
+                            qnv[m][j] = make_double2(qv.x + pv.x * dt + f0 * dt2 / 2.0, qv.y + pv.y * dt + f1 * dt2 / 2.0);
                             v[4 * j + 0] += pv.x * pv.x;
                             v[4 * j + 1] += pv.y * pv.y;
                             v[4 * j + 2] += pv.x * c0;
                             v[4 * j + 3] += pv.y * c1;
+                        }
+                    }
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        if (!live[m]) continue;
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            const int n = cu + 8 * j + 2 * lc;
+                            st2(&sm[xpn + own[m] + 8 * j], phv[m][j].x, phv[m][j].y);
+                            st2(&sm[xq + own[m] + 8 * j], qnv[m][j].x, qnv[m][j].y);
+                            if (P.ps) st2(&P.ps[((size_t)tn_cur * nd + row[m]) * ldb + col0 + n], pvv[m][j].x, pvv[m][j].y);
+                            if (P.qs) st2(&P.qs[((size_t)tn_cur * nd + row[m]) * ldb + col0 + n], qvv[m][j].x, qvv[m][j].y);
                         }
                     }
                     // column sums over this warp's 16 rows: lane lr ends with value lr = (n-tile lr>>2, kind lr&3)
@@ -478,15 +520,6 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
                 TICK3(1)
                 zbar_sync(bar_NBR(u), (ZRW + ZBW) * 32);                        // ---- S2: unit's row warps + bath warps' arrival
                 TICK3(5)
-                // currents and kinetic energy of time t: fixed-order sum of the per-warp slots
-                for (int e = wr * 32 + lane; e < (nb + 1) * NU; e += ZRW * 32) {
-                    const int b = e / NU, n = cu + e % NU;
-                    double sum = 0.0;
-#pragma unroll
-                    for (int ww = 0; ww < ZSL; ++ww) sum += sm[P.off_curp + (b * ZSL + ww) * N + n];
-                    if (b < nb) P.b[b].cur[(size_t)tn_cur * ldb + col0 + n] = sum;
-                    else P.etot[(size_t)tn_cur * ldb + col0 + n] = 0.5 * sum;
-                }
                 nbuf ^= 1;
                 { const int tmp = xpc; xpc = xpn; xpn = tmp; }      // xpc: p(t+1/2)
                 {
@@ -495,6 +528,19 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
                     load_direct(tn1, nzr);
                     zero3(aDq); zero3(uq);
                     dq_matvec(sm + xq, aDq, uq);
+                    // currents and kinetic energy of time t: fixed-order sum of the per-warp slots (placed behind the
+                    // first operator product of the round so that its loads and adds run while the DMMAs drain)
+                    for (int e = wr * 32 + lane; e < (nb + 1) * NU; e += ZRW * 32) {
+                        const int b = e / NU, n = cu + e % NU;
+                        double sl[ZSL];
+#pragma unroll
+                        for (int ww = 0; ww < ZSL; ++ww) sl[ww] = sm[P.off_curp + (b * ZSL + ww) * N + n];
+                        double sum = 0.0;
+#pragma unroll
+                        for (int ww = 0; ww < ZSL; ++ww) sum += sl[ww];
+                        if (b < nb) P.b[b].cur[(size_t)tn_cur * ldb + col0 + n] = sum;
+                        else P.etot[(size_t)tn_cur * ldb + col0 + n] = 0.5 * sum;
+                    }
 #pragma unroll
                     for (int m = 0; m < 2; ++m)
 #pragma unroll
@@ -513,30 +559,45 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
                             wv[m] = sm[P.off_conv + 3 * NDP + row[m]];
                         }
                     }
+                    double2 phB[2][NJ], q1B[2][NJ], nbB[2][NJ][NSL], p1B[2][NJ];
+#pragma unroll
+                    for (int m = 0; m < 2; ++m)
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            phB[m][j] = ld2(&sm[xpc + own[m] + 8 * j]);
+                            q1B[m][j] = HASCON ? ld2(&sm[xq + own[m] + 8 * j]) : make_double2(0.0, 0.0);
+                            nb_load(nbuf, m, j, nbB[m][j]);
+                        }
 #pragma unroll
                     for (int m = 0; m < 2; ++m) {
 #pragma unroll
                         for (int j = 0; j < NJ; ++j) {
                             double2 cr;
-                            const double2 fs = nb_sum(nbuf, m, j, make_double2(fpot[m][j][0] + uq[m][j][0], fpot[m][j][1] + uq[m][j][1]),
-                                                      nzr[m][j][0], nzr[m][j][1], cr);
+                            const double2 fs = nb_add(make_double2(fpot[m][j][0] + uq[m][j][0], fpot[m][j][1] + uq[m][j][1]),
+                                                      nbB[m][j], nzr[m][j][0], nzr[m][j][1], cr);
                             const double f0 = fs.x, f1 = fs.y;
                             fb[m][j][0] = f0;
                             fb[m][j][1] = f1;
-                            const double2 ph = ld2(&sm[xpc + own[m] + 8 * j]);
+                            const double2 ph = phB[m][j];
                             const double p1x = ph.x + dt * (f0 - hB[m][j][0]) / 2.0, p1y = ph.y + dt * (f1 - hB[m][j][1]) / 2.0;
-                            if (live[m]) st2(&sm[xpn + own[m] + 8 * j], p1x, p1y);
+                            p1B[m][j] = make_double2(p1x, p1y);
                             if (HASCON && live[m]) {
                                 // md.ApplyConstraint (md.py:739-762), one vector: c.p(t+1) before projection is
                                 // c.(p1/2 + dt/2 f) - dt/2 (Mp^T c).p1 by linearity, and c.q' is known since round A:
                                 // both dots are reduced here, so round C needs no barrier of its own
-                                const double2 q1 = ld2(&sm[xq + own[m] + 8 * j]);
+                                const double2 q1 = q1B[m][j];
                                 vB[4 * j + 0] += cv[m] * (ph.x + dt * f0 / 2.0) - dt * (wv[m] * p1x) / 2.0;
                                 vB[4 * j + 1] += cv[m] * (ph.y + dt * f1 / 2.0) - dt * (wv[m] * p1y) / 2.0;
                                 vB[4 * j + 2] += cv[m] * q1.x;
                                 vB[4 * j + 3] += cv[m] * q1.y;
                             }
                         }
+                    }
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        if (!live[m]) continue;
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) st2(&sm[xpn + own[m] + 8 * j], p1B[m][j].x, p1B[m][j].y);
                     }
                     if (HASCON) {
                         const double part = rs8(vB, lr);      // lane lr: value lr = (n-tile lr>>2, kind lr&3: d0, d1, g0, g1)
@@ -552,6 +613,16 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
                 { const int tmp = xpc; xpc = xpn; xpn = tmp; }      // xpc: p1, xpn: p(t+1/2)
                 {
                     // ============ round C: third evaluation, head p1 -> p(t+1), constraint ============
+                    // history rows of this thread's two operator rows in the shared-memory baths (-1: not a bath dof),
+                    // extracted before the product so that nothing is fetched between it and the last barrier
+                    int hrow[2][NSL];
+#pragma unroll
+                    for (int m = 0; m < 2; ++m)
+#pragma unroll
+                        for (int i = 0; i < NSL; ++i) {
+                            const int r = (int)((nbpk[m] >> (8 * i)) & 255u);
+                            hrow[m][i] = ((SPEC || i < P.nsm) && r != P.nbzero) ? r - P.b[SPEC ? i + 1 : P.smb[i]].nbrow0 : -1;
+                        }
                     double hC[2][NJ][2];
                     zero3(hC);
                     mp_matvec(sm + xpc, hC);
@@ -610,19 +681,16 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
                         }
                         // p_c(t+1) enters the block history / the HBM ring
 #pragma unroll
-                        for (int i = 0; i < FB_MAX; ++i) {
-                            if (i >= P.nsm) continue;
-                            const int r = (int)((nbpk[m] >> (8 * i)) & 255u);
-                            if (r == P.nbzero) continue;
-                            const FusedBath& B = P.b[P.smb[i]];
-                            const int ip = r - B.nbrow0;
+                        for (int i = 0; i < NSL; ++i) {
+                            const int ip = hrow[m][i];
+                            if (ip < 0) continue;
+                            const FusedBath& B = P.b[SPEC ? i + 1 : P.smb[i]];
                             if (!B.nonlocal) {
 #pragma unroll
                                 for (int j = 0; j < NJ; ++j) st2(&sm[B.off_hist + ip * LD + cu + 8 * j + 2 * lc], pn[m][j][0], pn[m][j][1]);
                             } else if (g + 1 < P.nsteps) {
                                 const int hb = B.off_hist + (((s + 1) & (FT - 1)) * B.ncp + ip) * LD + cu + 2 * lc;
-                                const int slot = (B.slot0 + g + 1) % B.R;
-                                double* rp = &B.ring[((size_t)slot * B.ncp + ip) * ldb + col0 + cu + 2 * lc];
+                                double* rp = &B.ring[((size_t)rslot[i] * B.ncp + ip) * ldb + col0 + cu + 2 * lc];
 #pragma unroll
                                 for (int j = 0; j < NJ; ++j) {
                                     st2(&sm[hb + 8 * j], pn[m][j][0], pn[m][j][1]);
@@ -631,6 +699,9 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
                             }
                         }
                     }
+#pragma unroll
+                    for (int i = 0; i < NSL; ++i)
+                        if (++rslot[i] >= rmod[i]) rslot[i] = 0;
                 }
                 if (g + 1 < gend) zbar_arrive(bar_H(u), (ZRW + ZBW) * 32);      // history row of the next step is in place
                 TICK3(3)
@@ -718,15 +789,22 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
                     xi[j] = make_double2(0.0, 0.0);
                     if (valid) xi[j] = ld2(&B.noise[((size_t)tn1 * B.nc + rr) * ldb + col0 + cu + 8 * j + 2 * lc]);
                 }
+                // ... and so are the pre-block tails P[s] except at a block start, where the unit's mid phase writes
+                // them just before it signals H
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    pt[j] = make_double2(0.0, 0.0);
+                    if (valid && B.nonlocal && s > 0) pt[j] = __ldcg(reinterpret_cast<const double2*>(&B.P[((size_t)s * B.nc + rr) * ldb + col0 + cu + 8 * j + 2 * lc]));
+                }
                 TICK3(1)
                 zbar_sync(bar_H(u), (ZRW + ZBW) * 32);  // p_c(t) of the unit is in the block history, P[s] is written
                 TICK3(5)
                 if (pb >= 0) {
                     const int KQ = B.ncp / 4;
+                    if (s == 0) {
 #pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        pt[j] = make_double2(0.0, 0.0);
-                        if (valid && B.nonlocal) pt[j] = __ldcg(reinterpret_cast<const double2*>(&B.P[((size_t)s * B.nc + rr) * ldb + col0 + cu + 8 * j + 2 * lc]));
+                        for (int j = 0; j < NJ; ++j)
+                            if (valid && B.nonlocal) pt[j] = __ldcg(reinterpret_cast<const double2*>(&B.P[((size_t)s * B.nc + rr) * ldb + col0 + cu + 8 * j + 2 * lc]));
                     }
                     const int hs = B.nonlocal ? s : 0;
                     if (pb != P.rem) {
@@ -867,29 +945,35 @@ size_t plan3(const pymd_ctx* c, FusedParams& fp, bool hasq, int NJ) {
 }
 
 namespace {
-template <int NJ, bool Q, bool C, int KS>
+template <int NJ, bool Q, bool C, int KS, int SPEC>
 int launch_f3_t(const FusedParams& fp, size_t smem, int grid, cudaStream_t st) {
     static bool cfg = false;
     if (!cfg) {
-        PYMD_CUDA_CHECK(cudaFuncSetAttribute(fused3_kernel<NJ, Q, C, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        PYMD_CUDA_CHECK(cudaFuncSetAttribute(fused3_kernel<NJ, Q, C, KS, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         cfg = true;
     }
-    fused3_kernel<NJ, Q, C, KS><<<grid, ZTH, smem, st>>>(fp);
+    fused3_kernel<NJ, Q, C, KS, SPEC><<<grid, ZTH, smem, st>>>(fp);
     PYMD_CUDA_CHECK(cudaGetLastError());
     return PYMD_OK;
 }
-template <int NJ, int KS>
+template <int NJ, int KS, int SPEC>
 int launch_f3_k(const FusedParams& fp, size_t smem, int grid, bool hasq, bool hascon, cudaStream_t st) {
-    if (hasq) return hascon ? launch_f3_t<NJ, true, true, KS>(fp, smem, grid, st) : launch_f3_t<NJ, true, false, KS>(fp, smem, grid, st);
-    return hascon ? launch_f3_t<NJ, false, true, KS>(fp, smem, grid, st) : launch_f3_t<NJ, false, false, KS>(fp, smem, grid, st);
+    if (hasq) return hascon ? launch_f3_t<NJ, true, true, KS, SPEC>(fp, smem, grid, st) : launch_f3_t<NJ, true, false, KS, SPEC>(fp, smem, grid, st);
+    return hascon ? launch_f3_t<NJ, false, true, KS, SPEC>(fp, smem, grid, st) : launch_f3_t<NJ, false, false, KS, SPEC>(fp, smem, grid, st);
 }
 }  // namespace
 
 int launch_f3(const FusedParams& fp, size_t smem, int NJ, bool hasq, bool hascon, cudaStream_t st) {
     const int grid = fp.ldb / (ZU * 8 * NJ);
     const bool k15 = fp.nd <= 60;
-    if (NJ == 2) return k15 ? launch_f3_k<2, 15>(fp, smem, grid, hasq, hascon, st) : launch_f3_k<2, 16>(fp, smem, grid, hasq, hascon, st);
-    return k15 ? launch_f3_k<1, 15>(fp, smem, grid, hasq, hascon, st) : launch_f3_k<1, 16>(fp, smem, grid, hasq, hascon, st);
+    // the usual layout: a direct remainder bath first, then exactly two shared-memory baths (electron bath + two leads)
+    const bool spec = k15 && fp.nsm == 2 && fp.dpos == 0 && fp.remi < 0;
+    if (NJ == 2) {
+        if (spec) return launch_f3_k<2, 15, 1>(fp, smem, grid, hasq, hascon, st);
+        return k15 ? launch_f3_k<2, 15, 0>(fp, smem, grid, hasq, hascon, st) : launch_f3_k<2, 16, 0>(fp, smem, grid, hasq, hascon, st);
+    }
+    if (spec) return launch_f3_k<1, 15, 1>(fp, smem, grid, hasq, hascon, st);
+    return k15 ? launch_f3_k<1, 15, 0>(fp, smem, grid, hasq, hascon, st) : launch_f3_k<1, 16, 0>(fp, smem, grid, hasq, hascon, st);
 }
 
 }  // namespace pymd
