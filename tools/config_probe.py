@@ -1,6 +1,8 @@
 """Throughput probe of the other BASELINE configs (mode auto): cfg3 Alkane-like (ebath only, nd=96,
-bias), cfg4 Au6-like stretch (nd=510, leads nc=81, ml=2000), and a sweep point.  Parity of these
-paths is covered by tests (per-step pipeline); this only reports traj-steps/s."""
+bias), cfg4 Au6-like stretch (nd=510, leads nc=81, ml=2000), and a sweep point; this only reports traj-steps/s
+(bench.py --config ... is the driver-visible way).  Parity of these shapes: tests/test_gpu_trajectory.py
+test_baseline_config_shapes (nd = 96, nd = 42), test_large_junctions_with_memory_baths (nd = 129 / 150 with memory
+baths), test_delay_line_far_field_of_the_per_step_pipeline."""
 import argparse, json, os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np, torch
