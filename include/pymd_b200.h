@@ -88,9 +88,11 @@ int pymd_history_get(pymd_ctx* ctx, int b, double* out_dev, int nrows, void* str
 int pymd_history_set(pymd_ctx* ctx, int b, const double* in_dev, int nrows, void* stream);
 
 /* nsteps calls of md.vv (md.py:315-358) starting at md.t = t0, for the whole ensemble.
- * mode: 0 = auto, 1 = per-step GEMM pipeline (any configuration), 2 = on-chip step kernels (fused.cu for
- * nd <= 64 with the FFT far field of far.cu when every memory bath has ml >= 24 and nc <= 16; local.cu for
- * 64 < nd <= 96 with one memory-less bath); mode 2 fails if the configuration fits neither. */
+ * mode: 0 = auto, 1 = per-step GEMM pipeline (any configuration; memories of 64 steps and more through the
+ * frequency-domain delay line of fdl.cu), 2 = on-chip step kernels (fused3.cu / fused.cu for nd <= 64 with the FFT
+ * far field of far.cu when every memory bath has ml >= 24 and nc <= 16; local.cu for 64 < nd <= 96 with one
+ * memory-less bath); mode 2 fails if the configuration fits neither.  Auto prefers mode 2 where it applies, except
+ * for memories of 2000 steps and more. */
 int pymd_step(pymd_ctx* ctx, long long t0, int nsteps, int mode, void* stream);
 /* number of kernel launches issued by this ctx so far */
 long long pymd_launch_count(const pymd_ctx* ctx);

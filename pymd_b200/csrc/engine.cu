@@ -708,7 +708,15 @@ int pymd_step(pymd_ctx* c, long long t0, int nsteps, int mode, void* stream) {
     if (rc) return rc;
     if (nsteps == 0) return PYMD_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (mode == 0) mode = (fused_supported(c) || local_supported(c)) ? 2 : 1;
+    if (mode == 0) {
+        mode = (fused_supported(c) || local_supported(c)) ? 2 : 1;
+        // very long memories: the far field of the on-chip path re-transforms one 97-row window per 97 taps and launch,
+        // the delay line of the per-step pipeline keeps the block spectra; measured at nd = 63, 4096 trajectories:
+        // ml = 1000: 58 M (on-chip) vs 37 M traj-steps/s, ml = 4000: 17 M vs 30 M -- the lines cross near ml = 1800
+        if (mode == 2 && fused_supported(c))
+            for (int b = 0; b < c->nbath; ++b)
+                if (c->bath[b].ml >= 2000 && fdl_wanted(c, c->bath[b])) mode = 1;
+    }
     if (mode == 2) {
         // on-chip step kernels: fused.cu (nd <= 64), local.cu (64 < nd <= 96, one bath without memory)
         if (fused_supported(c)) return fused_step(c, t0, nsteps, st);
