@@ -38,11 +38,13 @@ namespace {
 #ifndef Z_SETMAXNREG
 #define Z_SETMAXNREG 1
 #endif
+// Measured (us per 32-step launch, 32- / 16-trajectory tiles): 200/104: 428 / 253, 208/88: 423 / 258, 216/72: 420 / 263,
+// 224/56: 429 / 273, 232/40: 476 / 287 -- 216/72 for the 32-trajectory tiles, 200/104 for the 16-trajectory ones.
 #ifndef Z_ROW_REGS
-#define Z_ROW_REGS 200
+#define Z_ROW_REGS (NJ == 2 ? 216 : 200)
 #endif
 #ifndef Z_BATH_REGS
-#define Z_BATH_REGS 104
+#define Z_BATH_REGS (NJ == 2 ? 72 : 104)
 #endif
 // Unit 1 starts half a step behind unit 0, so that the element-wise part of one unit's round meets the operator
 // products of the other (units that start together stay in lockstep and leave the DMMA pipe idle together).

@@ -66,7 +66,7 @@ def ensemble_average(mdrun, batch_total):
                 ekin=float(ekv[0]) / B, nbath=nb)
 
 
-def run_pipelined(mdrun, batch_total, traj0=0, segment=0, overlap=False, reupload_factors=False):
+def run_pipelined(mdrun, batch_total, traj0=0, segment=0, overlap=False, reupload_factors=False, state=None):
     """One md.Run segment (initialise, ResetHis, fresh noise, nmd steps with saved trajectories, GetPower) for
     an ensemble of ``batch_total`` trajectories that is larger than what fits beside its own saved trajectories:
     it is processed in sub-ensembles of ``mdrun.batch`` trajectories (global indices traj0 + s batch ...).  The
@@ -78,11 +78,15 @@ def run_pipelined(mdrun, batch_total, traj0=0, segment=0, overlap=False, reuploa
     4 %, not worth the second 45 GB; it is off by default and needs the memory to be there.  Every per-trajectory
     result is identical either way: noise and initial phases are functions of (seed, segment, global index).
 
-    Returns dict(power_sum, power2_sum [nmd], cur_sum, cur_sq [nbath], ekin_sum, seconds=dict(...)): sums over the
-    local trajectories, ready for ensemble.allreduce_sums; one device->host copy at the end."""
+    ``state``: streams, the second noise set and the accumulators of a previous call (returned as out["state"]); a
+    run of several segments passes it on, so that only the first segment allocates.
+
+    Returns dict(power_sum, power2_sum [nmd], cur_sum, cur_sq [nbath], ekin_sum, seconds=dict(...), state): sums over
+    the local trajectories, ready for ensemble.allreduce_sums; one device->host copy at the end."""
     import time
     import torch
     from .spectrum import ensemble_powerspec, time_means
+    t_enter = time.perf_counter()
     Be = mdrun.batch
     if batch_total % Be:
         raise ValueError("run_pipelined: batch_total must be a multiple of md.batch")
@@ -93,24 +97,30 @@ def run_pipelined(mdrun, batch_total, traj0=0, segment=0, overlap=False, reuploa
     nmd, ldb = mdrun.nmd, mdrun.ldb
     if mdrun._ps is None:
         mdrun.ResetSavepq(True)
-    free, _ = torch.cuda.mem_get_info(dev)
-    need = sum(8 * nmd * b.nc * ldb for b in baths)
-    overlap = bool(overlap and nsub > 1 and free > need + (30 << 30))      # second noise set + scratch must fit
-    main = torch.cuda.Stream(dev, priority=-1)
-    side = torch.cuda.Stream(dev, priority=0) if overlap else main
-    copy = torch.cuda.Stream(dev, priority=0)             # factor uploads of the next sub-ensemble (copy engine)
+    if state is not None and state.get("key") == (id(mdrun), Be, nmd, ldb, bool(overlap)):
+        overlap, main, side, copy, bufs, acc_p, acc_p2, acc_c, acc_e = state["objs"]
+        acc_p.zero_(); acc_p2.zero_(); acc_c.zero_(); acc_e.zero_()
+    else:
+        want = bool(overlap)
+        free, _ = torch.cuda.mem_get_info(dev)
+        need = sum(8 * nmd * b.nc * ldb for b in baths)
+        overlap = bool(overlap and nsub > 1 and free > need + (30 << 30))      # second noise set + scratch must fit
+        main = torch.cuda.Stream(dev, priority=-1)
+        side = torch.cuda.Stream(dev, priority=0) if overlap else main
+        copy = torch.cuda.Stream(dev, priority=0)             # factor uploads of the next sub-ensemble (copy engine)
+        bufs = [[None, None] for _ in baths]
+        for i, b in enumerate(baths):
+            shape = (nmd, b.nc, ldb)
+            cur = b._noise_dev if (b._noise_dev is not None and tuple(b._noise_dev.shape) == shape) else \
+                torch.empty(shape, dtype=torch.float64, device=dev)
+            bufs[i][0] = cur
+            bufs[i][1] = torch.empty(shape, dtype=torch.float64, device=dev) if overlap else cur
+        acc_p = torch.zeros(nmd, dtype=torch.float64, device=dev)
+        acc_p2 = torch.zeros(nmd, dtype=torch.float64, device=dev)
+        acc_c = torch.zeros((2, len(baths)), dtype=torch.float64, device=dev)
+        acc_e = torch.zeros(1, dtype=torch.float64, device=dev)
+        state = dict(key=(id(mdrun), Be, nmd, ldb, want), objs=(overlap, main, side, copy, bufs, acc_p, acc_p2, acc_c, acc_e))
     staged = {}
-    bufs = [[None, None] for _ in baths]
-    for i, b in enumerate(baths):
-        shape = (nmd, b.nc, ldb)
-        cur = b._noise_dev if (b._noise_dev is not None and tuple(b._noise_dev.shape) == shape) else \
-            torch.empty(shape, dtype=torch.float64, device=dev)
-        bufs[i][0] = cur
-        bufs[i][1] = torch.empty(shape, dtype=torch.float64, device=dev) if overlap else cur
-    acc_p = torch.zeros(nmd, dtype=torch.float64, device=dev)
-    acc_p2 = torch.zeros(nmd, dtype=torch.float64, device=dev)
-    acc_c = torch.zeros((2, len(baths)), dtype=torch.float64, device=dev)
-    acc_e = torch.zeros(1, dtype=torch.float64, device=dev)
     torch.cuda.synchronize(dev)
     ready = [torch.cuda.Event() for _ in range(nsub)]
     done = [torch.cuda.Event() for _ in range(nsub)]
@@ -180,7 +190,7 @@ def run_pipelined(mdrun, batch_total, traj0=0, segment=0, overlap=False, reuploa
     out = dict(power_sum=acc_p.cpu().numpy(), power2_sum=acc_p2.cpu().numpy(), cur_sum=acc_c[0].cpu().numpy(),
                cur_sq=acc_c[1].cpu().numpy(), ekin_sum=float(acc_e.item()))
     t2 = time.perf_counter()
-    out["seconds"] = dict(total=t2 - t0, d2h=t2 - t1, overlap=overlap, sub_ensembles=nsub,
+    out["seconds"] = dict(total=t2 - t0, d2h=t2 - t1, setup=t0 - t_enter, overlap=overlap, sub_ensembles=nsub,
                           steps=sum(e[0].elapsed_time(e[1]) for e in tev) * 1e-3,
                           spectra=sum(e[1].elapsed_time(e[2]) for e in tev) * 1e-3,
                           reductions=sum(e[2].elapsed_time(e[3]) for e in tev) * 1e-3,
@@ -190,4 +200,5 @@ def run_pipelined(mdrun, batch_total, traj0=0, segment=0, overlap=False, reuploa
     mdrun.power_sum, mdrun.power2_sum = out["power_sum"], out["power2_sum"]
     mdrun.power = N.stack((dw * N.arange(nmd), out["power_sum"] / batch_total), axis=1)
     mdrun.power2 = N.stack((dw * N.arange(nmd), out["power2_sum"] / batch_total), axis=1)
+    out["state"] = state
     return out

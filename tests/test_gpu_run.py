@@ -138,3 +138,35 @@ def test_operands_changed_after_the_first_step_reach_the_device(cuda):
             om.vv()
         assert T.relerr(m.p[..., n], om.p) < 1e-11 and T.relerr(m.q[..., n], om.q) < 1e-11
         assert T.relerr(m.ps[10:22, :, n], om.ps[10:22]) < 1e-11
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_pipelined_sub_ensembles_equal_one_run_per_sub_ensemble(cuda, overlap):
+    """ensemble.run_pipelined (what bench.py's e2e leg calls): an ensemble of 96 trajectories in three sub-ensembles
+    of 32 -- with and without the next sub-ensemble's noise generated on a side stream -- gives exactly the sums of
+    three separate runs (initialise, gnoi, steps, GetPower) of the same global trajectory indices."""
+    from pymd_b200 import ensemble
+    c = dict(T.CASES["eph"], nmd=64, ml=30)
+    Be, nsub, seed = 32, 3, 21
+    m, _ = T.device_md(c, Be, seed=seed, traj0=5)
+    for b in m.baths:
+        b.spectral_factors()
+    r = ensemble.run_pipelined(m, Be * nsub, traj0=5, segment=0, overlap=overlap, reupload_factors=True)
+    assert r["seconds"]["overlap"] == overlap and r["seconds"]["sub_ensembles"] == nsub
+    p1 = np.zeros(c["nmd"]); p2 = np.zeros(c["nmd"]); cs = np.zeros(len(m.baths)); cq = np.zeros(len(m.baths)); ek = 0.0
+    for s in range(nsub):
+        a, _ = T.device_md(c, Be, seed=seed, traj0=5 + s * Be)
+        a.initialise(stream=0); a.ResetHis()
+        for b in a.baths:
+            b._gnoi(segment=0)
+        a.ResetSavepq(True)
+        a.steps(c["nmd"])
+        a.GetPower()
+        p1 += a.power_sum; p2 += a.power2_sum
+        for i, b in enumerate(a.baths):
+            ct = b.cur.mean(0)
+            cs[i] += ct.sum(); cq[i] += (ct * ct).sum()
+        ek += a.etot.mean(0).sum()
+    assert np.array_equal(r["power_sum"], p1) and np.array_equal(r["power2_sum"], p2)
+    assert T.relerr(r["cur_sum"], cs) < 1e-12 and T.relerr(r["cur_sq"], cq) < 1e-12 and abs(r["ekin_sum"] / ek - 1) < 1e-12
+    assert T.relerr(m.power2[:, 1], p2 / (Be * nsub)) < 1e-15
