@@ -346,8 +346,8 @@ int finalize(pymd_ctx* c) {
 }
 
 // Y[M][ldb] = alpha * A[M][lda] X(rows gathered by idx)        (plain operands)
-static int gemm_plain(pymd_ctx* c, const double* A, int lda, int M, int K, const double* X,
-                      const int* xidx, double* Y, double alpha, int accumulate, cudaStream_t st) {
+static GemmArgs plain_args(pymd_ctx* c, const double* A, int lda, int M, int K, const double* X, const int* xidx, double* Y,
+                           double alpha, int accumulate) {
     GemmArgs g{};
     g.a_base = A; g.a_ld = lda; g.a_ls = 0; g.a_mod = M;
     g.x_base = X; g.x_idx = xidx; g.x_ld = c->ldb;
@@ -355,30 +355,42 @@ static int gemm_plain(pymd_ctx* c, const double* A, int lda, int M, int K, const
     g.M = M; g.N = c->ldb;
     g.nseg = 1; g.seg_lo[0] = 0; g.seg_hi[0] = K; g.seg_aoff[0] = 0;
     g.alpha = alpha; g.accumulate = accumulate;
+    return g;
+}
+static int gemm_plain(pymd_ctx* c, const double* A, int lda, int M, int K, const double* X,
+                      const int* xidx, double* Y, double alpha, int accumulate, cudaStream_t st) {
+    const GemmArgs g = plain_args(c, A, lda, M, K, X, xidx, Y, alpha, accumulate);
     c->launches++;
     prof_begin(c, 2, st);
     const int rc = launch_gemm(g, st);
     prof_end(c, st);
     return rc;
 }
+// the products collected in m as ONE launch (profile class cls)
+static int flush_multi(pymd_ctx* c, GemmMulti& m, int cls, cudaStream_t st) {
+    if (m.n == 0) return PYMD_OK;
+    c->launches++;
+    prof_begin(c, cls, st);
+    const int rc = launch_gemm_multi(m, st);
+    prof_end(c, st);
+    m.n = 0;
+    return rc;
+}
 
 // out[s][i][n] = dt * sum_{lag>=0} K[s + koff + lag][i][:] . ring(newest - lag)[:][n],  s < T
 // wmax >= 0: only the newest wmax ring rows; accumulate: out += product.
-int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st, long long wmax, int accumulate) {
+// operands of that product; false when no history row contributes (nothing to launch)
+static bool tail_args(pymd_ctx* c, int b, int T, int koff, double* out, long long wmax, int accumulate, GemmArgs& g) {
     BathHost& H = c->bath[b];
     const int R = H.R, ncp = H.ncp;
     long long W = H.ml - koff;                 // lags 0 .. ml-1-koff contribute
     if (wmax >= 0 && W > wmax) W = wmax;
     if (W > H.hcount) W = H.hcount;
     if (W > R) W = R;
-    if (W <= 0) {
-        if (!accumulate)
-            PYMD_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)T * H.nc * c->ldb * sizeof(double), st));
-        return PYMD_OK;
-    }
+    if (W <= 0) return false;
     const int h = (int)((H.hcount - 1) % R);
     const int lo = h - (int)(W - 1);
-    GemmArgs g{};
+    g = GemmArgs{};
     g.a_base = H.d_krev; g.a_ld = H.Lk; g.a_ls = -ncp; g.a_mod = H.nc;
     g.x_base = c->sd.b[b].ring; g.x_idx = nullptr; g.x_ld = c->ldb;
     g.y_base = out; g.y_idx = nullptr; g.y_ld = c->ldb;
@@ -393,6 +405,16 @@ int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t s
         g.seg_lo[1] = (lo + R) * ncp; g.seg_hi[1] = R * ncp; g.seg_aoff[1] = base - (long long)R * ncp;
     }
     g.alpha = c->dt; g.accumulate = accumulate;
+    return true;
+}
+
+int launch_tail(pymd_ctx* c, int b, int T, int koff, double* out, cudaStream_t st, long long wmax, int accumulate) {
+    GemmArgs g{};
+    if (!tail_args(c, b, T, koff, out, wmax, accumulate, g)) {
+        if (!accumulate)
+            PYMD_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)T * c->bath[b].nc * c->ldb * sizeof(double), st));
+        return PYMD_OK;
+    }
     c->launches++;
     prof_begin(c, 0, st);
     const int rc = launch_gemm(g, st);
@@ -468,14 +490,21 @@ static int generic_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) 
             const long long t = t0 + s;
             const int tn = (int)(t % c->nmd), tn1 = (int)((t + 1) % c->nmd);
             Slots slots{};
-            // heads of the first force evaluation: g_b = alpha K_b[0] p_c - Aq q_c
+            // heads of the first force evaluation: g_b = alpha K_b[0] p_c - Aq q_c.  The small products of a step
+            // that do not depend on each other share a launch (gemm_multi_kernel).
+            GemmMulti mm{};
             for (int b = 0; b < c->nbath; ++b) {
                 BathHost& H = c->bath[b];
-                if ((rc = gemm_plain(c, H.d_head, H.lda, H.nc, H.nc, d.p, H.d_cids, d.b[b].g, 1.0, 0, st))) return rc;
+                if (mm.n == GemmMulti::kMax && (rc = flush_multi(c, mm, 2, st))) return rc;
+                mm.a[mm.n++] = plain_args(c, H.d_head, H.lda, H.nc, H.nc, d.p, H.d_cids, d.b[b].g, 1.0, 0);
+                slots.s[b] = H.ml > 1 ? (int)(H.hcount % H.R) : 0;
+            }
+            if ((rc = flush_multi(c, mm, 2, st))) return rc;
+            for (int b = 0; b < c->nbath; ++b) {
+                BathHost& H = c->bath[b];
                 if (H.has_aq &&
                     (rc = gemm_plain(c, H.d_aq, H.lda, H.nc, H.nc, d.q, H.d_cids, d.b[b].g, -1.0, 1, st)))
                     return rc;
-                slots.s[b] = H.ml > 1 ? (int)(H.hcount % H.R) : 0;
             }
             prof_begin(c, 3, st);
             stage_a_kernel<<<grd, blk, 0, st>>>(d, tn, slots);
@@ -488,18 +517,22 @@ static int generic_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) 
             for (int b = 0; b < c->nbath; ++b) {
                 if (c->bath[b].ml <= 1) continue;
                 double* row = Pblk[b] + (size_t)(s - s0) * c->bath[b].nc * c->ldb;
-                if ((rc = launch_tail(c, b, 1, 1, row, st, s - s0 + 1, 1))) return rc;
+                if (mm.n == GemmMulti::kMax && (rc = flush_multi(c, mm, 0, st))) return rc;
+                if (tail_args(c, b, 1, 1, row, s - s0 + 1, 1, mm.a[mm.n])) ++mm.n;
                 d.b[b].tail_next = row;
             }
-            // potential force at q' (the only dyn product of the step when unconstrained)
-            if ((rc = gemm_plain(c, c->d_dyn, c->ldn, c->nd, c->nd, d.qn, nullptr, d.fpotn, -1.0, 0, st))) return rc;
+            if ((rc = flush_multi(c, mm, 0, st))) return rc;
+            // potential force at q' (the only dyn product of the step when unconstrained), the q-coupled operators
+            // at q' and the summed heads of the second evaluation
+            mm.a[mm.n++] = plain_args(c, c->d_dyn, c->ldn, c->nd, c->nd, d.qn, nullptr, d.fpotn, -1.0, 0);
+            mm.a[mm.n++] = plain_args(c, c->d_mp, c->ldn, c->nd, c->nd, d.ph, nullptr, d.h, 1.0, 0);
             for (int b = 0; b < c->nbath; ++b) {
                 BathHost& H = c->bath[b];
-                if (H.has_aq &&
-                    (rc = gemm_plain(c, H.d_aq, H.lda, H.nc, H.nc, d.qn, H.d_cids, d.b[b].uq, 1.0, 0, st)))
-                    return rc;
+                if (!H.has_aq) continue;
+                if (mm.n == GemmMulti::kMax && (rc = flush_multi(c, mm, 2, st))) return rc;
+                mm.a[mm.n++] = plain_args(c, H.d_aq, H.lda, H.nc, H.nc, d.qn, H.d_cids, d.b[b].uq, 1.0, 0);
             }
-            if ((rc = gemm_plain(c, c->d_mp, c->ldn, c->nd, c->nd, d.ph, nullptr, d.h, 1.0, 0, st))) return rc;
+            if ((rc = flush_multi(c, mm, 2, st))) return rc;
             prof_begin(c, 3, st);
             stage_b_kernel<<<grd, blk, 0, st>>>(d, tn1);
             prof_end(c, st);

@@ -21,11 +21,29 @@ struct __align__(16) Smem {
 };
 
 template <int BM, int BN, int STAGES, int WM, int WN, int NPROD>
+__device__ __forceinline__ void gemm_body(const GemmArgs& g, unsigned char* smem_raw);
+
+template <int BM, int BN, int STAGES, int WM, int WN, int NPROD>
 __global__ void __launch_bounds__((WM * WN + NPROD) * 32) gemm_kernel(GemmArgs g) {
     g.a_base += (long long)blockIdx.z * g.a_bs;
     g.x_base += (long long)blockIdx.z * g.x_bs;
     g.y_base += (long long)blockIdx.z * g.y_bs;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    gemm_body<BM, BN, STAGES, WM, WN, NPROD>(g, smem_raw);
+}
+
+// several independent products of similar shape in ONE launch (blockIdx.z selects the problem): the small per-step
+// products of the per-step pipeline fill the SMs together instead of one after the other
+template <int BM, int BN, int STAGES, int WM, int WN, int NPROD>
+__global__ void __launch_bounds__((WM * WN + NPROD) * 32) gemm_multi_kernel(const GemmMulti m) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const GemmArgs& g = m.a[blockIdx.z];
+    if ((int)blockIdx.y * BM >= g.M || (int)blockIdx.x * BN >= g.N) return;     // this problem has fewer tiles
+    gemm_body<BM, BN, STAGES, WM, WN, NPROD>(g, smem_raw);
+}
+
+template <int BM, int BN, int STAGES, int WM, int WN, int NPROD>
+__device__ __forceinline__ void gemm_body(const GemmArgs& g, unsigned char* smem_raw) {
     Smem<BM, BN, STAGES>& s = *reinterpret_cast<Smem<BM, BN, STAGES>*>(smem_raw);
     constexpr int LDB = BN + 4;
     constexpr int NCOMPUTE = WM * WN;
@@ -146,6 +164,25 @@ __global__ void __launch_bounds__((WM * WN + NPROD) * 32) gemm_kernel(GemmArgs g
 }
 
 template <int BM, int BN, int STAGES, int WM, int WN, int NPROD>
+int launch_multi_t(const GemmMulti& m, cudaStream_t stream) {
+    static bool configured = false;
+    const int smem = static_cast<int>(sizeof(Smem<BM, BN, STAGES>));
+    if (!configured) {
+        PYMD_CUDA_CHECK(cudaFuncSetAttribute(gemm_multi_kernel<BM, BN, STAGES, WM, WN, NPROD>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    int gx = 0, gy = 0;
+    for (int i = 0; i < m.n; ++i) {
+        gx = max(gx, (m.a[i].N + BN - 1) / BN);
+        gy = max(gy, (m.a[i].M + BM - 1) / BM);
+    }
+    gemm_multi_kernel<BM, BN, STAGES, WM, WN, NPROD><<<dim3(gx, gy, m.n), (WM * WN + NPROD) * 32, smem, stream>>>(m);
+    PYMD_CUDA_CHECK(cudaGetLastError());
+    return PYMD_OK;
+}
+
+template <int BM, int BN, int STAGES, int WM, int WN, int NPROD>
 int launch_t(const GemmArgs& a, cudaStream_t stream) {
     static bool configured = false;
     const int smem = static_cast<int>(sizeof(Smem<BM, BN, STAGES>));
@@ -162,29 +199,61 @@ int launch_t(const GemmArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
-int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+static int gemm_validate(const GemmArgs& a) {
     PYMD_REQUIRE(a.M > 0 && a.N > 0 && (a.N % 2) == 0, "gemm: bad shape M=%d N=%d", a.M, a.N);
     PYMD_REQUIRE(a.nseg >= 0 && a.nseg <= 2, "gemm: nseg=%d", a.nseg);
     for (int sg = 0; sg < a.nseg; ++sg)
         PYMD_REQUIRE(((a.seg_aoff[sg] + a.seg_lo[sg]) % 2) == 0 && (a.a_ld % 2) == 0 && (a.a_ls % 2) == 0,
                      "gemm: A rows must be 16-byte aligned");
     PYMD_REQUIRE((a.x_ld % 2) == 0 && (a.y_ld % 2) == 0, "gemm: X/Y leading dims must be even");
-    // Tile choice by estimated efficiency = SM fill x per-tile DMMA efficiency (measured: a 64x64 CTA
-    // tile with 32x32 warp tiles needs 1 LDS per 2 DMMA and sustains ~0.9 of the pipe; 32x32 ~0.45).
+    return PYMD_OK;
+}
+
+// Tile choice by estimated efficiency = SM fill x per-tile DMMA efficiency (measured: a 64x64 CTA
+// tile with 32x32 warp tiles needs 1 LDS per 2 DMMA and sustains ~0.9 of the pipe; 32x32 ~0.45).
+// Returns 64, 32 or 16 (the BM of the configuration); `nprob` products of this shape share the launch.
+static int gemm_tile(const GemmArgs& a, long long nprob) {
     auto fill = [](long long ctas) {          // CTAs on one SM share its DMMA pipe
         const long long per_sm = (ctas + 147) / 148;
         return (double)ctas / (double)(per_sm * 148);
     };
-    const long long nbz = a.nbatch > 1 ? a.nbatch : 1;
-    PYMD_REQUIRE(nbz <= 65535 && (a.a_bs % 2) == 0 && (a.x_bs % 2) == 0 && (a.y_bs % 2) == 0, "gemm: bad batch nbatch=%d", a.nbatch);
-    const long long c64 = nbz * ((a.N + 63) / 64) * ((a.M + 63) / 64);
-    const long long c32 = nbz * ((a.N + 31) / 32) * ((a.M + 31) / 32);
+    const long long c64 = nprob * ((a.N + 63) / 64) * ((a.M + 63) / 64);
+    const long long c32 = nprob * ((a.N + 31) / 32) * ((a.M + 31) / 32);
     const double pad64 = (double)a.M / (double)(((a.M + 63) / 64) * 64);
     const double pad32 = (double)a.M / (double)(((a.M + 31) / 32) * 32);
     const double e64 = fill(c64) * 0.9 * pad64, e32 = fill(c32) * 0.45 * pad32;
-    if (a.M > 16 && e64 >= e32) return launch_t<64, 64, 5, 2, 4, 4>(a, stream);   // one CTA per SM: 8 DMMA warps + 4 producer warps
-    if (a.M > 16) return launch_t<32, 32, 3, 2, 2, 1>(a, stream);
-    return launch_t<16, 32, 3, 2, 2, 1>(a, stream);
+    if (a.M > 16 && e64 >= e32) return 64;
+    if (a.M > 16) return 32;
+    return 16;
+}
+
+int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+    int rc = gemm_validate(a);
+    if (rc) return rc;
+    const long long nbz = a.nbatch > 1 ? a.nbatch : 1;
+    PYMD_REQUIRE(nbz <= 65535 && (a.a_bs % 2) == 0 && (a.x_bs % 2) == 0 && (a.y_bs % 2) == 0, "gemm: bad batch nbatch=%d", a.nbatch);
+    switch (gemm_tile(a, nbz)) {
+        case 64: return launch_t<64, 64, 5, 2, 4, 4>(a, stream);   // one CTA per SM: 8 DMMA warps + 4 producer warps
+        case 32: return launch_t<32, 32, 3, 2, 2, 1>(a, stream);
+        default: return launch_t<16, 32, 3, 2, 2, 1>(a, stream);
+    }
+}
+
+int launch_gemm_multi(const GemmMulti& m, cudaStream_t stream) {
+    PYMD_REQUIRE(m.n >= 1 && m.n <= GemmMulti::kMax, "gemm_multi: n=%d", m.n);
+    if (m.n == 1) return launch_gemm(m.a[0], stream);
+    int big = 0;
+    for (int i = 0; i < m.n; ++i) {
+        int rc = gemm_validate(m.a[i]);
+        if (rc) return rc;
+        PYMD_REQUIRE(m.a[i].nbatch <= 1, "gemm_multi: batched problems are launched alone");
+        if ((long long)m.a[i].M * m.a[i].N > (long long)m.a[big].M * m.a[big].N) big = i;
+    }
+    switch (gemm_tile(m.a[big], m.n)) {
+        case 64: return launch_multi_t<64, 64, 5, 2, 4, 4>(m, stream);
+        case 32: return launch_multi_t<32, 32, 3, 2, 2, 1>(m, stream);
+        default: return launch_multi_t<16, 32, 3, 2, 2, 1>(m, stream);
+    }
 }
 
 }  // namespace pymd

@@ -36,7 +36,15 @@ struct GemmArgs {
     long long a_bs = 0, x_bs = 0, y_bs = 0;
 };
 
+// several independent products in one launch
+struct GemmMulti {
+    static constexpr int kMax = 4;
+    int n = 0;
+    GemmArgs a[kMax];
+};
+
 // Launch on `stream`; returns a PYMD_* status.
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
+int launch_gemm_multi(const GemmMulti& m, cudaStream_t stream);
 
 }  // namespace pymd
