@@ -196,9 +196,10 @@ __device__ __forceinline__ void zmid_phase(const FusedParams& P, double* sm, int
     zbar_sync(bar_R(u), ZRW * 32);                      // staging buffer (a head buffer) free again
 }
 
-// NJ: n8 tiles per unit; KS: k-steps of the nd x nd operators (15 when nd <= 60, else 16); SPEC = 1: the usual bath
-// layout (a direct remainder bath first, then exactly two shared-memory baths: AuBZ, Au6_3x3) with the per-row bath
-// loop unrolled without conditions
+// NJ: n8 tiles per unit; KS: k-steps of the nd x nd operators (15 when nd <= 60, else 16); SPEC: the per-row bath loop
+// unrolled without conditions for the two usual bath layouts -- 1: a direct remainder bath first, then exactly two
+// shared-memory baths (electron bath + two leads: AuBZ, Au6_3x3); 2: exactly two shared-memory baths and nothing else,
+// the first one being the remainder bath (two leads: tests/test.py); 0: anything else (run-time loop)
 template <int NJ, bool HASQ, bool HASCON, int KS, int SPEC>
 __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
     constexpr int N = ZU * 8 * NJ, LD = N + 4, NU = 8 * NJ;
@@ -377,6 +378,7 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
         // noise-minus-tail rows of the shared-memory baths in buffer `buf` for entry (m, j): loads only (all entries
         // of a round are loaded before any of them is used or stored, so that the loads overlap)
         constexpr int NSL = SPEC ? 2 : FB_MAX;
+        constexpr int BOFF = SPEC == 1 ? 1 : 0;      // bath index of the first shared-memory bath in the specialised layouts
         auto nb_load = [&](int buf, int m, int j, double2 (&v)[NSL]) {
             const double* base = sm + P.off_nb3 + buf * P.nbstride + cu + 8 * j + 2 * lc;
 #pragma unroll
@@ -389,8 +391,14 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
         // direct remainder bath at its position; the remainder bath's own share (a shared-memory bath) is returned too
         auto nb_add = [&](double2 f, const double2 (&v)[NSL], double nz0, double nz1, double2& rem_part) {
             rem_part = make_double2(0.0, 0.0);
-            if (SPEC) {
+            if (SPEC == 1) {
                 f.x += nz0; f.y += nz1;
+                f.x += v[0].x; f.y += v[0].y;
+                f.x += v[1].x; f.y += v[1].y;
+                return f;
+            }
+            if (SPEC == 2) {
+                rem_part = v[0];
                 f.x += v[0].x; f.y += v[0].y;
                 f.x += v[1].x; f.y += v[1].y;
                 return f;
@@ -410,7 +418,7 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
         int rslot[NSL], rmod[NSL];
 #pragma unroll
         for (int i = 0; i < NSL; ++i) {
-            const FusedBath& B = P.b[SPEC ? i + 1 : P.smb[i < P.nsm ? i : 0]];
+            const FusedBath& B = P.b[SPEC ? i + BOFF : P.smb[i < P.nsm ? i : 0]];
             rmod[i] = B.R;
             rslot[i] = (B.slot0 + 1) % B.R;
         }
@@ -623,7 +631,7 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
 #pragma unroll
                         for (int i = 0; i < NSL; ++i) {
                             const int r = (int)((nbpk[m] >> (8 * i)) & 255u);
-                            hrow[m][i] = ((SPEC || i < P.nsm) && r != P.nbzero) ? r - P.b[SPEC ? i + 1 : P.smb[i]].nbrow0 : -1;
+                            hrow[m][i] = ((SPEC || i < P.nsm) && r != P.nbzero) ? r - P.b[SPEC ? i + BOFF : P.smb[i]].nbrow0 : -1;
                         }
                     double hC[2][NJ][2];
                     zero3(hC);
@@ -686,7 +694,7 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
                         for (int i = 0; i < NSL; ++i) {
                             const int ip = hrow[m][i];
                             if (ip < 0) continue;
-                            const FusedBath& B = P.b[SPEC ? i + 1 : P.smb[i]];
+                            const FusedBath& B = P.b[SPEC ? i + BOFF : P.smb[i]];
                             if (!B.nonlocal) {
 #pragma unroll
                                 for (int j = 0; j < NJ; ++j) st2(&sm[B.off_hist + ip * LD + cu + 8 * j + 2 * lc], pn[m][j][0], pn[m][j][1]);
@@ -968,14 +976,24 @@ int launch_f3_k(const FusedParams& fp, size_t smem, int grid, bool hasq, bool ha
 int launch_f3(const FusedParams& fp, size_t smem, int NJ, bool hasq, bool hascon, cudaStream_t st) {
     const int grid = fp.ldb / (ZU * 8 * NJ);
     const bool k15 = fp.nd <= 60;
-    // the usual layout: a direct remainder bath first, then exactly two shared-memory baths (electron bath + two leads)
-    const bool spec = k15 && fp.nsm == 2 && fp.dpos == 0 && fp.remi < 0;
-    if (NJ == 2) {
-        if (spec) return launch_f3_k<2, 15, 1>(fp, smem, grid, hasq, hascon, st);
-        return k15 ? launch_f3_k<2, 15, 0>(fp, smem, grid, hasq, hascon, st) : launch_f3_k<2, 16, 0>(fp, smem, grid, hasq, hascon, st);
+    // the usual layouts (see the kernel's SPEC parameter)
+    int spec = 0;
+    if (fp.nbath == 3 && fp.nsm == 2 && fp.dpos == 0 && fp.remi < 0) spec = 1;
+    else if (fp.nbath == 2 && fp.nsm == 2 && fp.dpos < 0 && fp.remi == 0 && !hasq) spec = 2;
+#define PYMD_F3_CASE(NJV, KSV)                                                                                         \
+    {                                                                                                                  \
+        if (spec == 1) return launch_f3_k<NJV, KSV, 1>(fp, smem, grid, hasq, hascon, st);                              \
+        if (spec == 2) return hascon ? launch_f3_t<NJV, false, true, KSV, 2>(fp, smem, grid, st)                       \
+                                     : launch_f3_t<NJV, false, false, KSV, 2>(fp, smem, grid, st);                     \
+        return launch_f3_k<NJV, KSV, 0>(fp, smem, grid, hasq, hascon, st);                                             \
     }
-    if (spec) return launch_f3_k<1, 15, 1>(fp, smem, grid, hasq, hascon, st);
-    return k15 ? launch_f3_k<1, 15, 0>(fp, smem, grid, hasq, hascon, st) : launch_f3_k<1, 16, 0>(fp, smem, grid, hasq, hascon, st);
+    if (NJ == 2) {
+        if (k15) PYMD_F3_CASE(2, 15)
+        PYMD_F3_CASE(2, 16)
+    }
+    if (k15) PYMD_F3_CASE(1, 15)
+    PYMD_F3_CASE(1, 16)
+#undef PYMD_F3_CASE
 }
 
 }  // namespace pymd
