@@ -503,7 +503,22 @@ def run_ours(a):
         free, _ = torch.cuda.mem_get_info(dev)
         while Be > 32 and per_traj * Be + (20 << 30) > free and B % (Be // 2) == 0:
             Be //= 2
-        me = build(c, Be, rank * B, True, a.seed + 1, a.mode)
+        # records overlaid on the consumed noise rows (md.enable_record_overlay): the whole ensemble steps as ONE
+        # sub-ensemble with savepq when [ps | qs] + slack fits (129 GB for cfg2) and the two-unit kernel applies
+        overlay = False
+        me = None
+        if not a.no_record_overlay and c["nd"] <= 64 and 2 * c["nd"] >= sum(_bath_ncs(c)) and B % 32 == 0 \
+                and 8 * (nmd_e + 36) * 2 * c["nd"] * B + (24 << 30) < free:
+            try:
+                me = build(c, B, rank * B, True, a.seed + 1, a.mode)
+                me.enable_record_overlay()
+                overlay, Be = True, B
+            except Exception as ex:                     # not applicable (bath layout): sub-ensembles instead
+                print("record overlay not used: %s" % ex, file=sys.stderr)
+                me = None
+                torch.cuda.empty_cache()
+        if me is None:
+            me = build(c, Be, rank * B, True, a.seed + 1, a.mode)
         for b in me.baths:
             b.spectral_factors()                       # host setup (eigh per frequency), as the reference does once
         h2d = sum(b.spectral_factors().L.nbytes for b in me.baths)
@@ -534,7 +549,7 @@ def run_ours(a):
         nb_noise = 8 * (nmd_e // 2 + 1 + nmd_e) * sum(_bath_ncs(c)) * B
         nb_spec = 8 * nmd_e * 2 * c["nd"] * B
         e2e = dict(value=B * world * nmd_e / sec, unit="trajectory-steps/s", h2d_bytes_per_step=int(h2d * (B // Be)),
-                   d2h_bytes_per_step=int(d2h), seconds=sec, sub_ensembles=B // Be, sub_batch=Be,
+                   d2h_bytes_per_step=int(d2h), seconds=sec, sub_ensembles=B // Be, sub_batch=Be, record_overlay=overlay,
                    step="one Run segment of the whole ensemble in sub-ensembles: factors H2D + noise generation + %d md "
                         "steps with savepq + power spectra + D2H" % nmd_e,
                    breakdown=dict(h2d="inside noise_gen (async copy of %.2f GB per sub-ensemble from pinned memory)" % (h2d / 1e9),
@@ -596,6 +611,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-record-overlay", action="store_true", help="e2e: keep saved trajectories and noise in separate arrays (sub-ensembles of --e2e-batch)")
     ap.add_argument("--overlap", action="store_true", help="e2e: generate the next sub-ensemble's noise on a side stream while the current one steps (needs a second set of noise buffers)")
     ap.add_argument("--no-shard-check", action="store_true")
     a = ap.parse_args()

@@ -72,6 +72,18 @@ int pymd_bind_noise(pymd_ctx* ctx, int b, const double* noise_dev);
  * md.etot (md.py:119,328): dev [nmd][nd][ldb], [nmd][nd][ldb], [nmd][ldb]. */
 int pymd_bind_outputs(pymd_ctx* ctx, double* ps_dev, double* qs_dev, double* etot_dev);
 
+/* Overlaid records (optional): saved trajectories and noise of a large ensemble in ONE buffer.  Row t of ps / qs is
+ * written exactly when noise row t has been consumed, so the rows of [ps | qs] (2 nd ldb doubles each) may overlay the
+ * END-aligned noise rows (sum_b nc_b ldb doubles each, <= 2 nd ldb) of the same buffer: 129 GB instead of 218 GB for
+ * 4096 trajectories of config 2, which lets them step as one ensemble with savepq.  The rows are then strided:
+ * row_stride = doubles between consecutive time rows (ps and qs share it; every bath's noise shares the noise row).
+ * The noise is no longer periodic in place: row `nmd` (a copy of row 0, pymd_set_noise_wrap_row(ctx, nmd)) is what the
+ * last step of a segment reads (phbath.py:196), and a pymd_step call must not run past the end of the noise table.
+ * Only the two-unit on-chip step kernel (fused3.cu) supports strided records; pymd_step fails otherwise. */
+int pymd_bind_outputs_strided(pymd_ctx* ctx, double* ps_dev, double* qs_dev, double* etot_dev, long long row_stride);
+int pymd_bind_noise_strided(pymd_ctx* ctx, int b, const double* noise_dev, long long row_stride);
+int pymd_set_noise_wrap_row(pymd_ctx* ctx, int row);
+
 /* bath.cur (md.py:342): dev [nmd][ldb];  md.fhis[b] restricted to the bath's dofs
  * (md.py:343; NULL = not recorded): dev [nmd][nc][ldb]. */
 int pymd_bind_bath_outputs(pymd_ctx* ctx, int b, double* cur_dev, double* fhis_dev);
@@ -125,6 +137,11 @@ int pymd_noise_generate(const double* lre_dev, const double* lim_dev, const doub
 int pymd_noise_generate_chunk(const double* lre_dev, const double* lim_dev, const double* xi_chunk_dev, int cw,
                               int nmd, int nc, int ldb, int n0, double dt, double* out_dev, void* work_dev, void* stream);
 
+/* ... with the rows of out `out_row_stride` doubles apart (overlaid records, see pymd_bind_noise_strided) */
+int pymd_noise_generate_chunk_ld(const double* lre_dev, const double* lim_dev, const double* xi_chunk_dev, int cw,
+                                 int nmd, int nc, int ldb, int n0, double dt, double* out_dev, long long out_row_stride,
+                                 void* work_dev, void* stream);
+
 /* N.random.normal replacement (noise.py:282): counter-based Philox4x32-10 + Box-Muller using both
  * outputs (rows 2r and 2r+1 share the counter r).  Element (row r, trajectory n) depends only on
  * (seed, stream_id, r, traj0+n): results do not depend on how the ensemble is sharded over GPUs.
@@ -149,6 +166,10 @@ int pymd_init_state(pymd_ctx* ctx, const double* U_host, const double* hw_host,
 size_t pymd_powerspec_work_bytes(int nmd, int nd, int ldb, long long chunk_cols);
 int pymd_powerspec(const double* traj_dev, int nmd, int nd, int ldb, int nvalid, double dt, int wsq,
                    double* out_dev, void* work_dev, long long chunk_cols, void* stream);
+
+/* pymd_powerspec for rows `row_stride` doubles apart (overlaid records) */
+int pymd_powerspec_ld(const double* traj_dev, long long row_stride, int nmd, int nd, int ldb, int nvalid, double dt, int wsq,
+                      double* out_dev, void* work_dev, long long chunk_cols, void* stream);
 
 /* Time means of per-trajectory records (the kappa.*.dat numbers of md.Run, md.py:619: mean over the nmd rows of
  * bath.cur; likewise md.etot): out[n] = scale * sum_r a[r][n] for a dev [rows][ldb], deterministic (fixed chunking).

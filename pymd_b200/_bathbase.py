@@ -102,6 +102,9 @@ class BathBase(object):
         else:
             x = _noise._as_device_xi(xi, nf, self.nc, self.batch, self.ldb, dev)
             _noise.generate(fac, x, self.dt, self.nmd, out=out)
+        wrap = getattr(self, "_noise_wrap", None)
+        if wrap is not None and out.data_ptr() == self._noise_dev.data_ptr():
+            wrap.copy_(out[0])              # overlaid records: "row nmd" of the noise is a copy of row 0 (phbath.py:196)
         if detached:
             return
         self._ngnoi = self._ngnoi + 1 if segment is None else int(segment) + 1
@@ -113,6 +116,8 @@ class BathBase(object):
         (ensemble.run_pipelined generates the next sub-ensemble's noise while the current one is stepping)."""
         import torch
         shape = (self.nmd, self.nc, self.ldb)
+        if getattr(self, "_noise_wrap", None) is not None:
+            return self._noise_dev          # a view into md's overlaid record buffer
         spare = getattr(self, "_noise_spare", None)
         if spare is not None and tuple(spare.shape) == shape:
             self._noise_spare = self._noise_dev if (self._noise_dev is not None and tuple(self._noise_dev.shape) == shape) else None

@@ -29,6 +29,9 @@ PROTOTYPES = {
     "pymd_bind_history": (C.c_int, [c_ctx, C.c_int, c_dp, C.c_int]),
     "pymd_bind_noise": (C.c_int, [c_ctx, C.c_int, c_dp]),
     "pymd_bind_outputs": (C.c_int, [c_ctx, c_dp, c_dp, c_dp]),
+    "pymd_bind_outputs_strided": (C.c_int, [c_ctx, c_dp, c_dp, c_dp, C.c_longlong]),
+    "pymd_bind_noise_strided": (C.c_int, [c_ctx, C.c_int, c_dp, C.c_longlong]),
+    "pymd_set_noise_wrap_row": (C.c_int, [c_ctx, C.c_int]),
     "pymd_bind_bath_outputs": (C.c_int, [c_ctx, C.c_int, c_dp, c_dp]),
     "pymd_reset_history": (C.c_int, [c_ctx, c_dp]),
     "pymd_invalidate_cache": (C.c_int, [c_ctx]),
@@ -41,6 +44,10 @@ PROTOTYPES = {
                                       c_dp, c_dp, c_dp]),
     "pymd_noise_generate_chunk": (C.c_int, [c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                             c_dp, c_dp, c_dp]),
+    "pymd_noise_generate_chunk_ld": (C.c_int, [c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                               c_dp, C.c_longlong, c_dp, c_dp]),
+    "pymd_powerspec_ld": (C.c_int, [c_dp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, c_dp, c_dp,
+                                    C.c_longlong, c_dp]),
     "pymd_profile_enable": (C.c_int, [c_ctx, C.c_int]),
     "pymd_profile_read": (C.c_int, [c_ctx, c_dp, c_dp]),
     "pymd_philox_normal": (C.c_int, [c_dp, C.c_longlong, C.c_int, C.c_uint64, C.c_uint32, C.c_longlong, c_dp]),

@@ -671,12 +671,36 @@ int pymd_bind_history(pymd_ctx* c, int b, double* ring, int ring_len) {
 int pymd_bind_noise(pymd_ctx* c, int b, const double* noise) {
     PYMD_REQUIRE(c && noise && b >= 0 && b < c->nbath, "bind_noise: bad argument");
     c->sd.b[b].noise = noise;
+    c->sd.b[b].noise_ld = 0;
+    return PYMD_OK;
+}
+
+int pymd_bind_noise_strided(pymd_ctx* c, int b, const double* noise, long long row_stride) {
+    PYMD_REQUIRE(c && noise && b >= 0 && b < c->nbath, "bind_noise_strided: bad argument");
+    PYMD_REQUIRE(row_stride >= (long long)c->bath[b].nc * c->ldb && row_stride % 2 == 0, "bind_noise_strided: row stride %lld", row_stride);
+    c->sd.b[b].noise = noise;
+    c->sd.b[b].noise_ld = row_stride == (long long)c->bath[b].nc * c->ldb ? 0 : row_stride;
+    return PYMD_OK;
+}
+
+int pymd_set_noise_wrap_row(pymd_ctx* c, int row) {
+    PYMD_REQUIRE(c && (row == 0 || row == c->nmd), "set_noise_wrap_row: row %d (0 or nmd)", row);
+    c->sd.noise_wrap = row;
     return PYMD_OK;
 }
 
 int pymd_bind_outputs(pymd_ctx* c, double* ps, double* qs, double* etot) {
     PYMD_REQUIRE(c && etot, "bind_outputs: etot is required");
     c->sd.ps = ps; c->sd.qs = qs; c->sd.etot = etot;
+    c->sd.rec_ld = 0;
+    return PYMD_OK;
+}
+
+int pymd_bind_outputs_strided(pymd_ctx* c, double* ps, double* qs, double* etot, long long row_stride) {
+    PYMD_REQUIRE(c && etot && ps && qs, "bind_outputs_strided: null argument");
+    PYMD_REQUIRE(row_stride >= (long long)c->nd * c->ldb && row_stride % 2 == 0, "bind_outputs_strided: row stride %lld", row_stride);
+    c->sd.ps = ps; c->sd.qs = qs; c->sd.etot = etot;
+    c->sd.rec_ld = row_stride == (long long)c->nd * c->ldb ? 0 : row_stride;
     return PYMD_OK;
 }
 
@@ -741,6 +765,16 @@ int pymd_step(pymd_ctx* c, long long t0, int nsteps, int mode, void* stream) {
     if (rc) return rc;
     if (nsteps == 0) return PYMD_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    bool strided = c->sd.rec_ld != 0 || c->sd.noise_wrap != 0;
+    for (int b = 0; b < c->nbath; ++b) strided = strided || c->sd.b[b].noise_ld != 0;
+    if (strided) {
+        // overlaid records (ps / qs rows written over consumed noise rows): only the two-unit on-chip kernel reads
+        // and writes them, and a call must not run past the end of the noise table
+        PYMD_REQUIRE(mode != 1 && fused_supported(c), "step: strided record / noise layouts need the on-chip step kernel");
+        PYMD_REQUIRE(c->sd.noise_wrap == 0 || (t0 % c->nmd) + nsteps <= c->nmd,
+                     "step: with overlaid records a call must end at the end of the noise table (t0=%lld nsteps=%d nmd=%d)", t0, nsteps, c->nmd);
+        return fused_step(c, t0, nsteps, st);
+    }
     if (mode == 0) {
         mode = (fused_supported(c) || local_supported(c)) ? 2 : 1;
         // very long memories: the far field of the on-chip path re-transforms one 97-row window per 97 taps and launch,

@@ -19,6 +19,7 @@ struct BathDev {
     const int* inv;        // [nd] -> local index or -1
     const int* cids;       // [nc]
     const double* noise;   // [nmd][nc][ldb]
+    long long noise_ld;    // doubles between noise rows; 0 = nc * ldb (contiguous)
     double* cur;           // [nmd][ldb]
     double* fhis;          // [nmd][nc][ldb] or null
     double* ring;          // [R][ncp][ldb]
@@ -30,6 +31,8 @@ struct BathDev {
 
 struct StepDev {
     int nd, ldb, nbath, nmd, ncon;
+    long long rec_ld;      // doubles between rows of ps / qs; 0 = nd * ldb (contiguous)
+    int noise_wrap;        // noise row that stands for row nmd (0: row 0, the noise is periodic in place)
     double dt;
     double *p, *q, *ps, *qs, *etot;
     double *ph, *qn, *p1, *fpotn, *fpotc, *fbase, *h;

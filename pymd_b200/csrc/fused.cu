@@ -1584,7 +1584,10 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
         B.tail_cur = d.b[b].tail_cur; B.P = d.b[b].tail_next;
         B.head_g = H.d_head; B.lda = H.lda; B.kin_g = H.d_kintra; B.cids_g = H.d_cids; B.inv_g = H.d_inv;
         B.kinf = H.d_kinf; B.hdf = H.d_hdf;
+        B.nld = d.b[b].noise_ld ? d.b[b].noise_ld : (long long)H.nc * c->ldb;
     }
+    fp.rec_ld = d.rec_ld ? d.rec_ld : (long long)c->nd * c->ldb;
+    fp.wrap_row = d.noise_wrap;
     // warp-specialised variant (12 warps) when the trajectory tile is 32 and the baths qualify
     bool use2 = NT >= 2 && !(getenv("PYMD_FUSED2") && atoi(getenv("PYMD_FUSED2")) == 0);
     size_t smem2 = 0;
@@ -1597,13 +1600,19 @@ int fused_step(pymd_ctx* c, long long t0, int nsteps, cudaStream_t st) {
     // two-unit variant (fused3.cu) where it applies: the default for 16- and 32-trajectory tiles
     // (PYMD_FUSED3 = 0 / 1 / unset: never / wherever it applies / per-tile default)
     const char* e3 = getenv("PYMD_FUSED3");
-    bool use3 = use2 && (e3 ? atoi(e3) != 0 : NT == 4);
+    bool use3 = use2 && (e3 ? atoi(e3) != 0 : (NT == 4 || d.rec_ld != 0 || d.noise_wrap != 0));
     size_t smem3 = 0;
     if (use3) {
         FusedParams t3 = fp;
         smem3 = plan3(c, t3, hasq, NT / 2);
         if (smem3 > 227 * 1024) use3 = false;
         else fp = t3;
+    }
+    {
+        bool strided = d.rec_ld != 0 || d.noise_wrap != 0;
+        for (int b = 0; b < c->nbath; ++b) strided = strided || d.b[b].noise_ld != 0;
+        PYMD_REQUIRE(!strided || use3, "fused: strided record / noise layouts need the two-unit kernel (16- or 32-trajectory tiles, "
+                                       "small baths of at most 16 dofs)");
     }
     int rc;
     if (!c->tail_valid) {

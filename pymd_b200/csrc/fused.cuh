@@ -17,6 +17,7 @@ struct FusedBath {
     int off_hd, off_kin, off_hist, off_nb, off_cids, off_inrem;   // smem offsets (doubles)
     int lda;
     int nbrow0;               // fused3: first row of this bath in the combined noise-minus-tail buffer
+    long long nld;            // fused3: doubles between consecutive noise rows (nc * ldb unless the records are overlaid)
     const double* noise;
     const double* P;          // [FT][nc][ldb] pre-block tail
     double* tail_cur;         // [nc][ldb] tail(t) carried between launches
@@ -47,6 +48,8 @@ struct FusedParams {
     int off_xp0, off_xp1, off_xq, off_curp, off_conp, off_zero, off_conv;
     int off_opD, off_opQ;     // fused2: dyn / AqT as fragment-ordered shared-memory operands
     int off_nb3, nbstride, nbzero;   // fused3: combined noise-minus-tail buffer [2][nbzero + 1][LD], last row zero
+    long long rec_ld;         // fused3: doubles between consecutive rows of ps / qs (nd * ldb unless overlaid)
+    int wrap_row;             // fused3: noise row read as "row nmd" (0: the noise is periodic in place, phbath.py:196)
     int dpos;                 // fused3: how many shared-memory baths precede the direct remainder bath (-1: none is direct)
     int nsm, smb[4], remi;    // fused3: the shared-memory (non-direct) baths, and the remainder bath's position among them (-1: direct)
     int pair_b[4], pair_mt[4];    // fused2: (bath, m8 tile) owned by each bath warp, -1 = none

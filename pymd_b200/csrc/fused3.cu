@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
         double* NB = sm + P.off_nb3 + B.nbrow0 * LD;
         for (int e = tid; e < B.nc * N; e += ZTH) {
             const int r = e / N, n = e % N;
-            double v = B.noise[((size_t)tn0 * B.nc + r) * ldb + col0 + n];
+            double v = B.noise[(size_t)tn0 * B.nld + (size_t)r * ldb + col0 + n];
             if (B.nonlocal) v -= B.tail_cur[(size_t)r * ldb + col0 + n];
             NB[r * LD + n] = v;
         }
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
                     mrem[m] = 1.0;
                     if (P.b[P.rem].direct) {
                         dnz[m] = P.b[P.rem].noise + (size_t)ip * ldb + col0 + cu + 2 * lc;
-                        dnz_stride = (size_t)P.b[P.rem].nc * ldb;
+                        dnz_stride = (size_t)P.b[P.rem].nld;
                     }
                 }
             }
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
             for (int g = g0; g < gend; ++g) {
                 const int s = g - g0;
                 const int tn_cur = tn;
-                const int tn1 = tn + 1 == P.nmd ? 0 : tn + 1;
+                const int tn1 = tn + 1 == P.nmd ? P.wrap_row : tn + 1;
                 {
                     // ============ round A: first force evaluation at time t, head p(t) ============
                     double hA[2][NJ][2], nzr[2][NJ][2];
@@ -515,8 +515,8 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
                             const int n = cu + 8 * j + 2 * lc;
                             st2(&sm[xpn + own[m] + 8 * j], phv[m][j].x, phv[m][j].y);
                             st2(&sm[xq + own[m] + 8 * j], qnv[m][j].x, qnv[m][j].y);
-                            if (P.ps) st2(&P.ps[((size_t)tn_cur * nd + row[m]) * ldb + col0 + n], pvv[m][j].x, pvv[m][j].y);
-                            if (P.qs) st2(&P.qs[((size_t)tn_cur * nd + row[m]) * ldb + col0 + n], qvv[m][j].x, qvv[m][j].y);
+                            if (P.ps) st2(&P.ps[(size_t)tn_cur * P.rec_ld + (size_t)row[m] * ldb + col0 + n], pvv[m][j].x, pvv[m][j].y);
+                            if (P.qs) st2(&P.qs[(size_t)tn_cur * P.rec_ld + (size_t)row[m] * ldb + col0 + n], qvv[m][j].x, qvv[m][j].y);
                         }
                     }
                     // column sums over this warp's 16 rows: lane lr ends with value lr = (n-tile lr>>2, kind lr&3)
@@ -773,16 +773,16 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
         for (int g = 0; g < P.nsteps; ++g) {
             const int s = g & (FT - 1);
             const int nbuf = g & 1;
-            const int tn1 = tn + 1 == P.nmd ? 0 : tn + 1;
+            const int tn1 = tn + 1 == P.nmd ? P.wrap_row : tn + 1;
             {
                 // L2 prefetch of the noise rows two steps ahead: the 128 bath threads cover the 128-byte lines of all rows
-                const int tn2 = tn1 + 1 == P.nmd ? 0 : tn1 + 1;
+                const int tn2 = tn1 + 1 >= P.nmd ? P.wrap_row : tn1 + 1;
                 int e = tid - ZU * ZRW * 32;
                 for (int b = 0; b < nb; ++b) {
                     constexpr int LPR = (N * 8 + 127) / 128;       // 128-byte lines per row tile
                     const int cnt = P.b[b].nc * LPR;
                     for (; e < cnt; e += ZBW * 32)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.b[b].noise + ((size_t)tn2 * P.b[b].nc + e / LPR) * ldb + col0 + (e % LPR) * 16));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.b[b].noise + (size_t)tn2 * P.b[b].nld + (size_t)(e / LPR) * ldb + col0 + (e % LPR) * 16));
                     e -= cnt;
                 }
             }
@@ -797,7 +797,7 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     xi[j] = make_double2(0.0, 0.0);
-                    if (valid) xi[j] = ld2(&B.noise[((size_t)tn1 * B.nc + rr) * ldb + col0 + cu + 8 * j + 2 * lc]);
+                    if (valid) xi[j] = ld2(&B.noise[(size_t)tn1 * B.nld + (size_t)rr * ldb + col0 + cu + 8 * j + 2 * lc]);
                 }
                 // ... and so are the pre-block tails P[s] except at a block start, where the unit's mid phase writes
                 // them just before it signals H

@@ -267,7 +267,7 @@ size_t pymd_noise_work_bytes(int nmd, int nc, int ncols) {
 
 // xi: [nf][nc][xi_ld] white noise whose column 0 is trajectory n0 of the output; out: [nmd][nc][ldb]
 static int noise_generate_impl(const double* lre, const double* lim, const double* xi, int xi_ld, int xi_n0, int nmd, int nc,
-                               int ldb, int n0, int n1, double dt, double* out, void* work, void* stream) {
+                               int ldb, int n0, int n1, double dt, double* out, void* work, void* stream, long long out_ld = 0) {
     PYMD_REQUIRE(lre && xi && out && work, "noise_generate: null argument");
     PYMD_REQUIRE(nmd >= 4 && (nmd & (nmd - 1)) == 0, "noise_generate: nmd=%d must be a power of two >= 4", nmd);
     PYMD_REQUIRE(nc > 0 && ldb > 0 && ldb % 32 == 0 && xi_ld % 8 == 0, "noise_generate: nc=%d ldb=%d xi_ld=%d", nc, ldb, xi_ld);
@@ -298,7 +298,7 @@ static int noise_generate_impl(const double* lre, const double* lim, const doubl
     FftPlan p{};
     p.n = half; p.cols = (long long)nc * cw; p.sign = -1;
     p.load = LOAD_C; p.store = STORE_REAL_ROWS;
-    p.src_ld = p.cols; p.dst_ld = (long long)nc * ldb;
+    p.src_ld = p.cols; p.dst_ld = out_ld ? out_ld : (long long)nc * ldb;
     p.dst_cw = cw; p.dst_cs = ldb;
     p.scale = 1.0 / ((double)nmd * dt);
     return fft_columns(W0, out + n0, W1, W0, p, st, nullptr);
@@ -312,6 +312,12 @@ int pymd_noise_generate(const double* lre, const double* lim, const double* xi, 
 int pymd_noise_generate_chunk(const double* lre, const double* lim, const double* xi_chunk, int cw, int nmd, int nc, int ldb,
                               int n0, double dt, double* out, void* work, void* stream) {
     return noise_generate_impl(lre, lim, xi_chunk, cw, 0, nmd, nc, ldb, n0, n0 + cw, dt, out, work, stream);
+}
+
+int pymd_noise_generate_chunk_ld(const double* lre, const double* lim, const double* xi_chunk, int cw, int nmd, int nc, int ldb,
+                                 int n0, double dt, double* out, long long out_row_stride, void* work, void* stream) {
+    PYMD_REQUIRE(out_row_stride >= (long long)nc * ldb && out_row_stride % 2 == 0, "noise_generate: output row stride %lld", out_row_stride);
+    return noise_generate_impl(lre, lim, xi_chunk, cw, 0, nmd, nc, ldb, n0, n0 + cw, dt, out, work, stream, out_row_stride);
 }
 
 int pymd_philox_normal(double* out, long long rows, int ldb, uint64_t seed, uint32_t stream_id,

@@ -115,8 +115,22 @@ size_t pymd_powerspec_work_bytes(int nmd, int nd, int ldb, long long chunk_cols)
     return (size_t)(nmd / 2 + 1) * ncb_total * sizeof(double) + 2 * (size_t)(nmd / 2) * chunk * sizeof(double2) + 256;
 }
 
+static int powerspec_impl(const double* traj, int nmd, int nd, int ldb, int nvalid, double dt, int wsq, double* out,
+                          void* work, long long chunk_cols, void* stream, long long row_ld);
+
 int pymd_powerspec(const double* traj, int nmd, int nd, int ldb, int nvalid, double dt, int wsq, double* out,
                    void* work, long long chunk_cols, void* stream) {
+    return powerspec_impl(traj, nmd, nd, ldb, nvalid, dt, wsq, out, work, chunk_cols, stream, 0);
+}
+
+int pymd_powerspec_ld(const double* traj, long long row_stride, int nmd, int nd, int ldb, int nvalid, double dt, int wsq,
+                      double* out, void* work, long long chunk_cols, void* stream) {
+    PYMD_REQUIRE(row_stride >= (long long)nd * ldb && row_stride % 2 == 0, "powerspec: row stride %lld", row_stride);
+    return powerspec_impl(traj, nmd, nd, ldb, nvalid, dt, wsq, out, work, chunk_cols, stream, row_stride);
+}
+
+static int powerspec_impl(const double* traj, int nmd, int nd, int ldb, int nvalid, double dt, int wsq, double* out,
+                          void* work, long long chunk_cols, void* stream, long long row_ld) {
     PYMD_REQUIRE(traj && out && work, "powerspec: null argument");
     PYMD_REQUIRE(nmd >= 4 && (nmd & (nmd - 1)) == 0, "powerspec: nmd=%d must be a power of two >= 4", nmd);
     PYMD_REQUIRE(nvalid > 0 && nvalid <= ldb, "powerspec: nvalid=%d ldb=%d", nvalid, ldb);
@@ -139,7 +153,7 @@ int pymd_powerspec(const double* traj, int nmd, int nd, int ldb, int nvalid, dou
         FftPlan p{};
         p.n = half; p.cols = cols; p.sign = -1;
         p.load = LOAD_REAL_PAIRS; p.store = STORE_C;
-        p.src_ld = total; p.dst_ld = cols; p.scale = 1.0;
+        p.src_ld = row_ld ? row_ld : total; p.dst_ld = cols; p.scale = 1.0;
         // passes write bufA, bufB, bufA, ...; the last one reads buf[(np-2)&1] and must write the other
         double2* dst = (np % 2) ? bufA : bufB;
         double2* a = bufA;

@@ -270,6 +270,8 @@ class md(object):
         return out
 
     def _savepq_alloc(self):
+        if getattr(self, "_overlay", False):
+            return
         if self._savepq and self.nph is not None:
             shape = (self.nmd, self.nph, self.ldb)
             if self._ps is None or tuple(self._ps.shape) != shape:
@@ -277,9 +279,58 @@ class md(object):
         else:
             self._ps = self._qs = None
 
+    # ------------------------------------------------------------------ overlaid records (large ensembles)
+    RECORD_SLACK_ROWS = 36        # a launch covers <= 32 steps and its CTAs advance independently
+
+    def enable_record_overlay(self):
+        """Keep the saved trajectories AND the noise of every bath in ONE device buffer: row t of [ps | qs] is written
+        exactly when noise row t has been consumed, so the 2 nph ldb doubles of a record row may overlay the
+        end-aligned noise rows (sum_b nc_b ldb <= 2 nph ldb doubles each).  4096 trajectories of config 2 then need
+        129 GB instead of 218 GB and step as ONE ensemble with savepq=True (the reference keeps both arrays for its
+        single trajectory, md.py:146-147, phbath.py:157).  Consequences: bath.noise is only valid until the next
+        steps() call; a steps() call must end at the end of the noise table (md.Run's pieces do); ResetSavepq does
+        not zero; white noise cannot be injected (gnoi(xi=...)); the two-unit step kernel must apply (nph <= 64, small
+        baths of <= 16 dofs).  Call after the last AddBath and before gnoi()."""
+        import torch
+        if not self._savepq:
+            raise ValueError("md.enable_record_overlay: needs savepq=True")
+        self._ps = self._qs = None
+        self._overlay = True                # from here on _savepq_alloc leaves the records alone
+        self._ensure()
+        nd, ldb, nmd = self.nph, self.ldb, self.nmd
+        W = 2 * nd * ldb                                   # doubles per record row
+        V = sum(b.nc for b in self.baths) * ldb            # doubles per noise row
+        if V > W:
+            self._overlay = False
+            raise ValueError("md.enable_record_overlay: the baths have more noise components than 2 nph")
+        rows = nmd + self.RECORD_SLACK_ROWS
+        self._ps = self._qs = None
+        for b in self.baths:
+            b._noise_dev = None
+        torch.cuda.empty_cache()
+        buf = torch.empty(rows * W, dtype=torch.float64, device=self._dev())
+        self._record_buf = buf
+        self._ps = buf.as_strided((nmd, nd, ldb), (W, ldb, 1), 0)
+        self._qs = buf.as_strided((nmd, nd, ldb), (W, ldb, 1), nd * ldb)
+        base = rows * W - (nmd + 1) * V                    # noise rows 0 .. nmd (row nmd = copy of row 0), end-aligned
+        off = 0
+        for b in self.baths:
+            b._noise_dev = buf.as_strided((nmd, b.nc, ldb), (V, ldb, 1), base + off)
+            b._noise_wrap = buf.as_strided((b.nc, ldb), (ldb, 1), base + nmd * V + off)
+            b._noise_version = getattr(b, "_noise_version", 0) + 1
+            off += b.nc * ldb
+
     def _bind(self):
         """(Re)bind every borrowed device array; cheap, done before each library call."""
         ctx = self._ctx
+        if getattr(self, "_overlay", False):
+            _lib.call("pymd_bind_outputs_strided", ctx, self._ps.data_ptr(), self._qs.data_ptr(), self._etot.data_ptr(),
+                      int(self._ps.stride(0)))
+            _lib.call("pymd_set_noise_wrap_row", ctx, int(self.nmd))
+            for b, bath in enumerate(self.baths):
+                _lib.call("pymd_bind_noise_strided", ctx, b, bath._noise_dev.data_ptr(), int(bath._noise_dev.stride(0)))
+                _lib.call("pymd_bind_bath_outputs", ctx, b, bath._alloc_cur().data_ptr(), _lib.ptr(self._fhis.get(b)))
+            return
         _lib.call("pymd_bind_outputs", ctx, _lib.ptr(self._ps), _lib.ptr(self._qs), self._etot.data_ptr())
         for b, bath in enumerate(self.baths):
             if bath._noise_dev is None:
@@ -305,6 +356,8 @@ class md(object):
         self._savepq = bool(savepq)
         if self.nmd is None or self.nph is None:
             raise ValueError("md.ResetSavepq: nmd or nph is not set!")
+        if getattr(self, "_overlay", False):
+            return                      # the record rows share memory with the noise: every row is rewritten anyway
         self._savepq_alloc()
         if self._ps is not None:
             self._ps.zero_()

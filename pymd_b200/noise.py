@@ -315,6 +315,8 @@ def generate(factors, xi, dt, nmd, out=None):
     lre, lim = factors.device_factors(dev)
     if out is None:
         out = torch.empty((nmd, nc, ldb), dtype=torch.float64, device=dev)
+    if not out.is_contiguous():
+        raise ValueError("noise.generate: injected white noise needs a contiguous noise array (no record overlay)")
     # trajectories are transformed in chunks so that the FFT scratch stays below MAX_WORK_BYTES
     per_col = _lib.load().pymd_noise_work_bytes(nmd, nc, 1)
     cw = max(32, min(ldb, (MAX_WORK_BYTES // per_col) // 32 * 32))
@@ -333,6 +335,8 @@ def generate_philox(factors, dt, nmd, ldb, batch, seed, stream_id, traj0, out):
     import torch
     nf, nc, _ = factors.shape
     dev = out.device
+    if out.stride(2) != 1 or out.stride(1) != ldb:
+        raise ValueError("noise.generate_philox: the output rows must be contiguous [nc][ldb] blocks")
     lre, lim = factors.device_factors(dev)
     per_col = _lib.load().pymd_noise_work_bytes(nmd, nc, 1) + 8 * nf * nc
     cw = max(32, min(ldb, (MAX_WORK_BYTES // per_col) // 32 * 32))
@@ -346,8 +350,12 @@ def generate_philox(factors, dt, nmd, ldb, batch, seed, stream_id, traj0, out):
                   int(stream_id) & 0xFFFFFFFF, int(traj0) + n0, _lib.stream_ptr())
         if n0 + w > batch:
             x[:, :, max(batch - n0, 0):] = 0.0          # padding trajectories stay at rest
-        _lib.call("pymd_noise_generate_chunk", lre.data_ptr(), _lib.ptr(lim), x.data_ptr(), w, nmd, nc, ldb, n0,
-                  float(dt), out.data_ptr(), work.data_ptr(), _lib.stream_ptr())
+        if out.stride(0) == nc * ldb:
+            _lib.call("pymd_noise_generate_chunk", lre.data_ptr(), _lib.ptr(lim), x.data_ptr(), w, nmd, nc, ldb, n0,
+                      float(dt), out.data_ptr(), work.data_ptr(), _lib.stream_ptr())
+        else:                                           # rows of an overlaid record buffer (md.enable_record_overlay)
+            _lib.call("pymd_noise_generate_chunk_ld", lre.data_ptr(), _lib.ptr(lim), x.data_ptr(), w, nmd, nc, ldb, n0,
+                      float(dt), out.data_ptr(), int(out.stride(0)), work.data_ptr(), _lib.stream_ptr())
     return out
 
 

@@ -21,8 +21,14 @@ def ensemble_powerspec(traj_dev, dt, nmd, nvalid, wsq, host=True):
     out = torch.empty(nmd, dtype=torch.float64, device=traj_dev.device)
     work = torch.empty(lib.pymd_powerspec_work_bytes(nmd, nd, ldb, chunk), dtype=torch.uint8,
                        device=traj_dev.device)
-    _lib.call("pymd_powerspec", traj_dev.data_ptr(), nmd, nd, ldb, int(nvalid), float(dt), 1 if wsq else 0,
-              out.data_ptr(), work.data_ptr(), chunk, _lib.stream_ptr())
+    if traj_dev.stride(2) != 1 or traj_dev.stride(1) != ldb:
+        raise ValueError("power: the rows of the saved trajectories must be contiguous [nd][ldb] blocks")
+    if traj_dev.stride(0) == nd * ldb:
+        _lib.call("pymd_powerspec", traj_dev.data_ptr(), nmd, nd, ldb, int(nvalid), float(dt), 1 if wsq else 0,
+                  out.data_ptr(), work.data_ptr(), chunk, _lib.stream_ptr())
+    else:                                               # rows of an overlaid record buffer (md.enable_record_overlay)
+        _lib.call("pymd_powerspec_ld", traj_dev.data_ptr(), int(traj_dev.stride(0)), nmd, nd, ldb, int(nvalid), float(dt),
+                  1 if wsq else 0, out.data_ptr(), work.data_ptr(), chunk, _lib.stream_ptr())
     return out.cpu().numpy() if host else out
 
 

@@ -170,3 +170,41 @@ def test_pipelined_sub_ensembles_equal_one_run_per_sub_ensemble(cuda, overlap):
     assert np.array_equal(r["power_sum"], p1) and np.array_equal(r["power2_sum"], p2)
     assert T.relerr(r["cur_sum"], cs) < 1e-12 and T.relerr(r["cur_sq"], cq) < 1e-12 and abs(r["ekin_sum"] / ek - 1) < 1e-12
     assert T.relerr(m.power2[:, 1], p2 / (Be * nsub)) < 1e-15
+
+
+@pytest.mark.parametrize("case,B", [("aubz", 40), ("chain39", 33)])
+def test_overlaid_records_equal_separate_arrays(cuda, case, B, monkeypatch):
+    """md.enable_record_overlay: saved trajectories written over the consumed noise rows of one shared buffer (what
+    lets 4096 trajectories of config 2 step as one ensemble with savepq).  Same seeds with and without the overlay:
+    ps, qs, currents, kinetic energy, final state and the power spectra are bit-identical; the library refuses a
+    steps() call that would run past the end of the noise table and kernels that do not support strided records."""
+    from pymd_b200 import _lib
+    monkeypatch.setenv("PYMD_FUSED_NT", "4")            # the two-unit kernel on 32-trajectory tiles in both runs
+    c = dict(T.CASES[case]); c["nmd"] = 128
+    out = {}
+    for ov in (False, True):
+        m, _ = T.device_md(c, B, seed=13)
+        if ov:
+            m.enable_record_overlay()
+            assert m._ps.stride(0) == 2 * c["nd"] * m.ldb and m.baths[0]._noise_dev.stride(0) == sum(b.nc for b in m.baths) * m.ldb
+        m.initialise(stream=0); m.ResetHis()
+        for b in m.baths:
+            b._gnoi(segment=0)
+        noise0 = [np.array(b.noise) for b in m.baths]
+        m.ResetSavepq(True)
+        m.steps(5)
+        m.steps(59)
+        if ov:
+            with pytest.raises(_lib.PymdError):
+                m.steps(65)                             # would run past the end of the (overwritten) noise table
+        m.steps(64)
+        m.GetPower()
+        out[ov] = (np.array(m.ps), np.array(m.qs), [np.array(b.cur) for b in m.baths], np.array(m.etot), np.array(m.p),
+                   np.array(m.power[:, 1]), np.array(m.power2[:, 1]), noise0)
+    a, b = out[False], out[True]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+    for x, y in zip(a[2], b[2]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a[5], b[5]) and np.array_equal(a[6], b[6])
+    for x, y in zip(a[7], b[7]):
+        assert np.array_equal(x, y)                     # the generated noise itself (read before stepping)
