@@ -15,7 +15,9 @@ step takes ~0.15 s (8192 md steps for cfg2): with the driver's --steps 20 the ti
 the clock sampler sees sustained FP64 load.  `value` = trajectory-steps/s with the coloured noise already
 resident in HBM; `e2e` = the same metric through the md/phbath/ebath class API from host inputs: upload of the
 spectral factors, noise generation, nmd steps with trajectories saved, power spectra, device->host read of
-spectra and currents (+ NCCL all-reduce), with a breakdown of where the time goes.
+spectra and currents (+ NCCL all-reduce), with a breakdown of where the time goes.  The e2e ensemble steps as one
+piece when its saved trajectories can overlay the consumed noise rows (md.enable_record_overlay: 129 GB for cfg2),
+else in sub-ensembles (ensemble.run_pipelined).
 """
 import os
 

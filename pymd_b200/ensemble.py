@@ -132,14 +132,32 @@ def run_pipelined(mdrun, batch_total, traj0=0, segment=0, overlap=False, reuploa
             if s >= 2:
                 side.wait_event(done[s - 2])            # the buffers of sub-ensemble s-2 are free again
             nev[s][0].record(side)
-            for i, b in enumerate(baths):
+            order = list(range(len(baths)))
+            evs = {}
+            if reupload_factors and s not in staged:
+                # this sub-ensemble's inputs cross the bus now: all uploads go to the copy stream at once, smallest
+                # first, and the baths are generated in that order, so that the upload of the big electron-bath
+                # factors (0.94 GB at config 2) runs beside the noise generation of the leads
+                order.sort(key=lambda i: baths[i].spectral_factors().L.nbytes if hasattr(baths[i].spectral_factors(), "_pinned") else 0)
+                with torch.cuda.stream(copy):
+                    for i in order:
+                        fac = baths[i].spectral_factors()
+                        fac.drop_device_copy()
+                        pair = fac.upload_copy(dev)
+                        for t in pair:
+                            if t is not None:
+                                t.record_stream(side)   # allocated on the copy stream, read by kernels of `side`
+                        fac.adopt_device_copy(dev, pair)
+                        evs[i] = torch.cuda.Event()
+                        evs[i].record(copy)
+            for i in order:
+                b = baths[i]
                 if reupload_factors:
-                    fac = b.spectral_factors()
                     if s in staged:
                         side.wait_event(staged[s][1])
-                        fac.adopt_device_copy(dev, staged[s][0][i])     # uploaded while the previous sub-ensemble stepped
-                    else:
-                        fac.drop_device_copy()
+                        b.spectral_factors().adopt_device_copy(dev, staged[s][0][i])    # uploaded while the previous sub-ensemble stepped
+                    elif i in evs:
+                        side.wait_event(evs[i])
                 b._gnoi(segment=segment, out=bufs[i][s % 2], traj0=traj0 + s * Be)
             staged.pop(s, None)
             nev[s][1].record(side)
@@ -160,6 +178,10 @@ def run_pipelined(mdrun, batch_total, traj0=0, segment=0, overlap=False, reuploa
             if reupload_factors and not overlap and s + 1 < nsub:
                 with torch.cuda.stream(copy):
                     ups = [b.spectral_factors().upload_copy(dev) for b in baths]
+                    for pair in ups:
+                        for t in pair:
+                            if t is not None:
+                                t.record_stream(side)
                     ev = torch.cuda.Event()
                     ev.record(copy)
                 staged[s + 1] = (ups, ev)
