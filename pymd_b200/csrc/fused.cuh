@@ -47,6 +47,7 @@ struct FusedParams {
     const double *dyn, *mp, *aqT, *con3;      // con3: [3][ncon][nd] = c, D c, AqT c
     int off_xp0, off_xp1, off_xq, off_curp, off_conp, off_zero, off_conv;
     int off_opD, off_opQ;     // fused2: dyn / AqT as fragment-ordered shared-memory operands
+    int off_nbt;              // fused3: per-thread packed noise-minus-tail rows [2][256] (unsigned)
     int off_nb3, nbstride, nbzero;   // fused3: combined noise-minus-tail buffer [2][nbzero + 1][LD], last row zero
     long long rec_ld;         // fused3: doubles between consecutive rows of ps / qs (nd * ldb unless overlaid)
     int wrap_row;             // fused3: noise row read as "row nmd" (0: the noise is periodic in place, phbath.py:196)

@@ -256,6 +256,9 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
         const int u = w >> 2, wr = w & 3, cu = NU * u;
         int row[2], own[2];
         bool live[2];
+        // per-thread packed rows of the small baths' noise-minus-tail entries: kept in shared memory (three uses per
+        // step; as registers they were spilled to local memory and reloaded in front of the last barrier of the step)
+        unsigned* NBT = reinterpret_cast<unsigned*>(sm + P.off_nbt);
         unsigned nbpk[2];
         double mrem[2];
         const double* dnz[2];
@@ -277,6 +280,7 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
                 }
                 nbpk[m] |= r << (8 * i);
             }
+            NBT[m * (ZU * ZRW * 32) + tid] = nbpk[m];
             if (P.rem >= 0 && live[m]) {
                 const int ip = P.b[P.rem].inv_g[row[m]];
                 if (ip >= 0) {
@@ -381,10 +385,11 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
         constexpr int BOFF = SPEC == 1 ? 1 : 0;      // bath index of the first shared-memory bath in the specialised layouts
         auto nb_load = [&](int buf, int m, int j, double2 (&v)[NSL]) {
             const double* base = sm + P.off_nb3 + buf * P.nbstride + cu + 8 * j + 2 * lc;
+            const unsigned pk = NBT[m * (ZU * ZRW * 32) + tid];
 #pragma unroll
             for (int i = 0; i < NSL; ++i) {
                 v[i] = make_double2(0.0, 0.0);
-                if (SPEC || i < P.nsm) v[i] = ld2(base + ((nbpk[m] >> (8 * i)) & 255u) * LD);
+                if (SPEC || i < P.nsm) v[i] = ld2(base + ((pk >> (8 * i)) & 255u) * LD);
             }
         };
         // f + sum over the baths, in bath order (the order fused2 and the 8-warp kernel add them in): `nz` for the
@@ -630,7 +635,7 @@ __global__ void __launch_bounds__(ZTH, 1) fused3_kernel(const FusedParams P) {
                     for (int m = 0; m < 2; ++m)
 #pragma unroll
                         for (int i = 0; i < NSL; ++i) {
-                            const int r = (int)((nbpk[m] >> (8 * i)) & 255u);
+                            const int r = (int)((NBT[m * (ZU * ZRW * 32) + tid] >> (8 * i)) & 255u);
                             hrow[m][i] = ((SPEC || i < P.nsm) && r != P.nbzero) ? r - P.b[SPEC ? i + BOFF : P.smb[i]].nbrow0 : -1;
                         }
                     double hC[2][NJ][2];
@@ -919,6 +924,7 @@ size_t plan3(const pymd_ctx* c, FusedParams& fp, bool hasq, int NJ) {
     fp.off_curp = take((c->nbath + 1) * ZSL * N);
     fp.off_conp = take(ZU * 8 * ZRW * 4);
     fp.off_conv = take(4 * NDP);
+    fp.off_nbt = take(ZU * ZRW * 32);            // 2 x 256 unsigned
     int npair = 0, nrows = 0;
     fp.nsm = 0;
     fp.remi = -1;
