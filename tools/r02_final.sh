@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2 validation: whole GPU test suite, smoke, default bench (+ reference arm)
+# round-2 validation: whole GPU test suite, smoke, default bench, ncu capture of the dominant kernel + launch list
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 T="timeout -s KILL"
@@ -15,3 +15,6 @@ try:
 except Exception as e:
     print("bench failed", e); print(open("gpurun_out/final_bench.err").read()[-2000:])
 PY
+$T 600 ncu --set full --import-source on --clock-control none -k regex:fused3_kernel -s 3 -c 1 -o gpurun_out/final_f3 -f python tools/prof_case.py 4096 2 > gpurun_out/final_ncu.log 2>&1
+$T 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/final_launches.csv python bench.py --steps 3 --warmup 3 --piece 64 --no-e2e --no-cpu --no-shard-check > gpurun_out/final_ncu_bench.log 2>&1
+tail -1 gpurun_out/final_ncu.log
