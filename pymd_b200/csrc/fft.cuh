@@ -13,6 +13,18 @@ const double2* twiddle_table(int N);
 enum FftLoad { LOAD_C = 0, LOAD_REAL_PAIRS = 1 };
 enum FftStore { STORE_C = 0, STORE_REAL_ROWS = 1 };
 
+// Power-spectrum tail (spectrum.cu): when the plan holds a radix-128 pass and at least one other pass, that pass is
+// ordered last and fused with the real-FFT untangling, |X_k|^2 and the column sums; `fused` reports whether it was
+// (otherwise the transform is stored as asked and the caller reduces it).
+struct FftPowerTail {
+    int ldb, nvalid;              // column c0g + c is trajectory (c0g + c) % ldb; counted when < nvalid
+    long long c0g;
+    const double2* tw2;           // W_2n table
+    double* partial;              // [n + 1][ncb_total]
+    int ncb_total, cb0, cb_per;   // this chunk owns columns cb0 .. cb0 + cb_per - 1 of `partial`
+    bool fused;
+};
+
 struct FftPlan {
     int n;                // complex length (power of two)
     long long cols;       // columns transformed
@@ -24,6 +36,7 @@ struct FftPlan {
     // STORE_REAL_ROWS only: column c of the transform lands at (c / dst_cw) * dst_cs + c % dst_cw of
     // a destination row (a chunk of dst_cw trajectories of every component row); 0 = plain c.
     long long dst_cw = 0, dst_cs = 0;
+    FftPowerTail* power = nullptr;
 };
 
 // number of passes (launches) fft_columns uses for a length-n transform

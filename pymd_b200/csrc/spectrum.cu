@@ -158,11 +158,16 @@ static int powerspec_impl(const double* traj, int nmd, int nd, int ldb, int nval
         double2* dst = (np % 2) ? bufA : bufB;
         double2* a = bufA;
         double2* b = bufB;
+        // the last radix-128 pass forms |X_k|^2 and the column sums itself when the plan has one (fft.cu)
+        FftPowerTail tail{ldb, nvalid, c0, twN, partial, ncb_total, ch * cb_per, cb_per, false};
+        p.power = &tail;
         int rc = fft_columns(traj + c0, dst, a, b, p, st, nullptr);
         if (rc) return rc;
-        dim3 grid(half / 2 + 1, (unsigned)((cols + PB - 1) / PB));
-        power_partial_kernel<<<grid, PB, 0, st>>>(dst, half, cols, ldb, nvalid, c0, twN, partial, ncb_total, ch * cb_per);
-        PYMD_CUDA_CHECK(cudaGetLastError());
+        if (!tail.fused) {
+            dim3 grid(half / 2 + 1, (unsigned)((cols + PB - 1) / PB));
+            power_partial_kernel<<<grid, PB, 0, st>>>(dst, half, cols, ldb, nvalid, c0, twN, partial, ncb_total, ch * cb_per);
+            PYMD_CUDA_CHECK(cudaGetLastError());
+        }
     }
     power_final_kernel<<<(nmd + 255) / 256, 256, 0, st>>>(partial, ncb_total, nmd, dt, wsq, out);
     PYMD_CUDA_CHECK(cudaGetLastError());

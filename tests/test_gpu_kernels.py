@@ -148,7 +148,7 @@ def test_noise_with_reference_draw_order(cuda, golden):
 
 
 @pytest.mark.parametrize("nmd,nd,batch", [(16, 6, 1), (64, 12, 5), (1024, 39, 33), (256, 6, 3), (4096, 6, 3),
-                                          (16384, 3, 2), (32768, 3, 2)])
+                                          (16384, 3, 2), (32768, 3, 2), (32768, 5, 40), (16384, 2, 33)])
 def test_powerspec_matches_oracle(cuda, nmd, nd, batch):
     import torch
     from pymd_b200.spectrum import ensemble_powerspec, powerspec, powerspec2
@@ -162,6 +162,14 @@ def test_powerspec_matches_oracle(cuda, nmd, nd, batch):
     r1 = sum(O.powerspec(x[:, :, n], dt, nmd)[:, 1] for n in range(batch))
     r2 = sum(O.powerspec2(x[:, :, n], dt, nmd)[:, 1] for n in range(batch))
     assert T.relerr(s1, r1) < 1e-12 and T.relerr(s2, r2) < 1e-12
+    if nmd >= 16384:                                    # the fused last pass against the separate pass + reduction
+        import os
+        os.environ["PYMD_POWER_FUSED"] = "0"
+        try:
+            u1 = ensemble_powerspec(d, dt, nmd, batch, True)
+        finally:
+            del os.environ["PYMD_POWER_FUSED"]
+        assert T.relerr(s1, u1) < 1e-13
     one = powerspec(x[:, :, 0], dt, nmd)
     ref = O.powerspec(x[:, :, 0], dt, nmd)
     assert np.allclose(one[:, 0], ref[:, 0], rtol=1e-15) and T.relerr(one[:, 1], ref[:, 1]) < 1e-12
