@@ -105,14 +105,16 @@ def algorithmic(c):
         out["fdl"] = dict(L=L, P=P,
                           near_executed=sum(2 * n * n * (L / 2.0 + 1.0) for n in ncs),
                           far_executed=sum(8.0 * n * n * P * (L + 1) / L + 2 * n * 5.0 * 2 * L * np.log2(2 * L) / L for n in ncs))
-    if c["name"] == "cfg2":
-        S, nc = 32, c["ncl"]
+    if ncs and ml >= 24:                            # kFarMinMl (csrc/engine.cuh)
+        # on-chip path (csrc/fused3.cu + far.cu; only when the run really used both kernels, see run_ours)
+        S = 32
         near = (S + 1) / 2.0 + 1.0                     # average number of taps inside the 32-step super-block
-        out["tail"] = 2 * (2 * nc * nc * (ml - 1 - near))          # taps older than the super-block: far field
+        out["tail"] = sum(2 * n * n * (ml - 1 - near) for n in ncs)        # taps older than the super-block: far field
         out["fused"] = total - out["tail"]
-        # executed by the far kernel per trajectory-step: two real FFTs of length 128 per bath dof
-        # (2.5 n log2 n each) and 65 complex nc x nc products (8 flops per complex multiply-add)
-        out["far_executed"] = 2 * (2 * nc * 2.5 * 128 * 7 + 65 * 8 * nc * nc) / S
+        # executed by the far kernel per trajectory-step and window of 97 taps: two real FFTs of length 128 per bath
+        # dof (2.5 n log2 n each) and 65 complex nc x nc products (8 flops per complex multiply-add)
+        nseg = max(1, (ml - 3 + 96) // 97)
+        out["far_executed"] = sum(nseg * (2 * n * 2.5 * 128 * 7 + 65 * 8 * n * n) for n in ncs) / S
     return out
 
 
