@@ -677,7 +677,8 @@ int fft_columns(const void* src, void* dst, double2* bufA, double2* bufB, const 
         fft_pass128s_kernel<LMODE, SMODE><<<grid, dim3(32, 16), smem128s, stream>>>(cur, out, p.n, Ns, p.cols, ci, co, tw, \
                                                                                    p.n, sld, dld, sc, cw, cs);        \
     } while (0)
-            static const int staged = [] { const char* e = getenv("PYMD_FFT_STAGED"); return e ? atoi(e) : 1; }();
+            const char* es = getenv("PYMD_FFT_STAGED");     // read per call: the tests compare both versions
+            const int staged = es ? atoi(es) : 1;
             // 8-byte cp.async needs 8-byte aligned real rows, 16-byte ones 16-byte aligned complex rows: always true
             // for the buffers of this library (256-byte aligned allocations, even leading dimensions)
             const bool al = lm == LOAD_C ? (reinterpret_cast<uintptr_t>(cur) % 16 == 0)

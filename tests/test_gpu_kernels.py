@@ -51,6 +51,33 @@ def test_column_fft_matches_numpy(cuda, n, sign):
     assert T.relerr(d.cpu().numpy(), ref) < 5e-15 * max(1, np.log2(n))
 
 
+@pytest.mark.parametrize("n,cols", [(16384, 4776), (8192, 2400 + 8)])
+def test_column_fft_many_tiles_per_cta(cuda, n, cols):
+    """Column counts beyond one tile per CTA of the radix-128 passes (74 column CTAs x 32): the cp.async stage ring
+    wraps and the last tile is ragged.  Staged and register-prefetch passes do the same arithmetic (bitwise equal);
+    sampled columns against numpy."""
+    import os
+    import torch
+    from pymd_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(n + cols)
+    z = torch.randn((n, cols, 2), generator=g, dtype=torch.float64)
+    outs = {}
+    work = torch.empty(_lib.load().pymd_fft_work_bytes(n, cols), dtype=torch.uint8, device=cuda)
+    for staged in ("1", "0", "2"):
+        os.environ["PYMD_FFT_STAGED"] = staged
+        try:
+            d = z.to(cuda)
+            _lib.call("pymd_fft_columns", d.data_ptr(), n, cols, -1, work.data_ptr(), _lib.stream_ptr())
+            outs[staged] = d
+        finally:
+            del os.environ["PYMD_FFT_STAGED"]
+    assert torch.equal(outs["1"], outs["0"]) and torch.equal(outs["2"], outs["0"])
+    pick = [0, 31, 32, 2367, 2368, 2369, cols - 33, cols - 1]
+    zc = torch.view_as_complex(z)[:, pick].numpy()
+    got = torch.view_as_complex(outs["1"])[:, pick].cpu().numpy()
+    assert T.relerr(got, np.fft.fft(zc, axis=0)) < 5e-15 * np.log2(n)
+
+
 def test_myfft_conventions_on_device(cuda):
     """myfft.Fourier1D / iFourier1D (myfft.py:15-52) on device arrays, incl. the round trip the
     reference prints as its self-check (myfft.py:55-76)."""
@@ -107,12 +134,12 @@ def test_noise_pipeline_matches_oracle(cuda, case, batch):
             assert T.relerr(got[:, :, n], om.baths[b].noise) < 1e-12, (b, n)
 
 
-@pytest.mark.parametrize("nmd", [256, 4096, 16384, 32768])
-def test_noise_pipeline_long_records(cuda, nmd):
+@pytest.mark.parametrize("nmd,batch", [(256, 2), (4096, 2), (16384, 2), (32768, 2), (16384, 1000)])
+def test_noise_pipeline_long_records(cuda, nmd, batch):
     """Record lengths whose half-length FFT plans contain the fused radix-128 pass (128; 128 x 16;
-    128 x 64; 128 x 128), real-pair loads and real-row stores included."""
+    128 x 64; 128 x 128), real-pair loads and real-row stores included; 1000 trajectories: more column tiles than
+    CTAs in the radix-128 passes (the cp.async stage ring wraps)."""
     c = dict(T.CASES["ph2"], nmd=nmd)
-    batch = 2
     m, j = T.device_md(c, batch)
     xi, _ = T.draw(c, m, batch, seed=5)
     om = T.oracle_md(c, j)
@@ -120,8 +147,9 @@ def test_noise_pipeline_long_records(cuda, nmd):
         bath.gnoi(xi=xi[0][b])
         got = bath.noise.reshape(nmd, bath.nc, batch)
         fac = bath.spectral_factors().as_oracle()
-        om.baths[b].gnoi(xi=xi[0][b][:, :, 1], factors=fac)
-        assert T.relerr(got[:, :, 1], om.baths[b].noise) < 1e-12, b
+        for n in sorted({1, batch - 1}):
+            om.baths[b].gnoi(xi=xi[0][b][:, :, n], factors=fac)
+            assert T.relerr(got[:, :, n], om.baths[b].noise) < 1e-12, (b, n)
 
 
 def test_noise_with_reference_draw_order(cuda, golden):
@@ -148,7 +176,7 @@ def test_noise_with_reference_draw_order(cuda, golden):
 
 
 @pytest.mark.parametrize("nmd,nd,batch", [(16, 6, 1), (64, 12, 5), (1024, 39, 33), (256, 6, 3), (4096, 6, 3),
-                                          (16384, 3, 2), (32768, 3, 2), (32768, 5, 40), (16384, 2, 33)])
+                                          (16384, 3, 2), (32768, 3, 2), (32768, 5, 40), (16384, 2, 33), (16384, 40, 70)])
 def test_powerspec_matches_oracle(cuda, nmd, nd, batch):
     import torch
     from pymd_b200.spectrum import ensemble_powerspec, powerspec, powerspec2
