@@ -155,8 +155,12 @@ __global__ void __launch_bounds__(SX* SY) shape_kernel(const double* __restrict_
 // takes n8 tiles w, w+8, ...; the B fragments (xi rows of the two frequencies) come straight from
 // global memory into registers, Y = L xi is 4 DMMA chains per m8 tile (Re/Im of the two
 // frequencies), and the Hermitian pre-processing of the half-length real transform is the epilogue.
+// 16 warps for the large complex operands (electron bath: 128 registers, no spills; 123 vs 128 ms for 4096
+// trajectories of 60 dofs), 8 warps otherwise (the real 64-dof variant would spill at 128 registers)
 template <int KKMAX, bool CPLX>
-__global__ void __launch_bounds__(256, 1) shape_dmma_kernel(const double* __restrict__ lre, const double* __restrict__ lim,
+__host__ __device__ constexpr int shape_threads() { return KKMAX == 16 && CPLX ? 512 : 256; }
+template <int KKMAX, bool CPLX>
+__global__ void __launch_bounds__((shape_threads<KKMAX, CPLX>()), 1) shape_dmma_kernel(const double* __restrict__ lre, const double* __restrict__ lim,
                                                             const double* __restrict__ xi, int N, int nc, int ldb,
                                                             int n0, int cw, const double2* __restrict__ twN,
                                                             double2* __restrict__ Z) {
@@ -170,7 +174,8 @@ __global__ void __launch_bounds__(256, 1) shape_dmma_kernel(const double* __rest
     double* A1i = sh + plane;
     double* A2r = sh + 2 * plane;
     double* A2i = sh + 3 * plane;
-    for (int e = tid; e < 8 * MT * 4 * KK; e += 256) {
+    constexpr int SHAPE_THREADS = shape_threads<KKMAX, CPLX>();
+    for (int e = tid; e < 8 * MT * 4 * KK; e += SHAPE_THREADS) {
         const int i = e / (4 * KK), j = e % (4 * KK);
         const bool in = i < nc && j < nc;
         const size_t o1 = ((size_t)k1 * nc + i) * nc + j, o2 = ((size_t)k2 * nc + i) * nc + j;
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(256, 1) shape_dmma_kernel(const double* __rest
     }
     __syncthreads();
     const double2 w1 = twN[k1], w2 = twN[k2];
-    for (int nt = warp; nt < cw / 8; nt += 8) {
+    for (int nt = warp; nt < cw / 8; nt += SHAPE_THREADS / 32) {
         const int col = n0 + nt * 8;
         double b1[KKMAX], b2[KKMAX];
 #pragma unroll
@@ -250,7 +255,7 @@ int launch_shape(const double* lre, const double* lim, const double* xi, int nmd
         PYMD_CUDA_CHECK(cudaFuncSetAttribute(shape_dmma_kernel<KKMAX, CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    shape_dmma_kernel<KKMAX, CPLX><<<nmd / 4 + 1, 256, smem, st>>>(lre, lim, xi, nmd, nc, ldb, n0, cw, twN, Z);
+    shape_dmma_kernel<KKMAX, CPLX><<<nmd / 4 + 1, shape_threads<KKMAX, CPLX>(), smem, st>>>(lre, lim, xi, nmd, nc, ldb, n0, cw, twN, Z);
     PYMD_CUDA_CHECK(cudaGetLastError());
     return PYMD_OK;
 }
